@@ -1,0 +1,500 @@
+// abm_ref: oracle harness around the UNMODIFIED reference implementation.
+//
+// TEST INFRASTRUCTURE ONLY.  This translation unit is compiled against the reference headers
+// where they lie under /root/reference/src (see oracle/Makefile); no reference source is copied
+// into this repository.  It exists to (1) export reference-built problems as ABMP files,
+// (2) emit golden step traces of the reference SparseBasisSampler, (3) time the reference
+// sampler on host cores (bench.py --impl reference / cpu_baseline), (4) run long reference
+// chains for posterior marginals.  Nothing in the product path may link or execute it.
+//
+// Include order mirrors the reference's main.cpp -> Experiments.h (the headers are
+// include-order dependent).
+#include <boost/serialization/access.hpp>
+#include <chrono>
+#include <future>
+#include <thread>
+
+#include "Trajectory.h"
+#include "Forecast.h"
+#include "Likelihood.h"
+#include "PredPreyProblem.h"
+#include "SparseBasisSampler.h"
+
+#include "abmcmc_b200/abmp_io.hpp"
+#include "abmcmc_b200/reference_flatten.hpp"
+
+using abmcmc::AbmpFile;
+typedef ABM::occupation_type occ_t;
+
+// ---------------------------------------------------------------------------------------------
+// Step-by-step access to the reference sampler.  step() is the body of the do-loop of
+// nextSampleWithInfeasibleImportance() (SparseBasisSampler.h:221-246) re-issued call by call on the
+// reference's own Proposal / perturb / getLogValue / calcRatioOfSums / applyProposal, so that a
+// trace can be recorded per Metropolis step; `selfcheck` proves it is state-identical to the
+// unmodified operator().
+template <class T>
+struct TracedSampler : public SparseBasisSampler<T> {
+    using Base = SparseBasisSampler<T>;
+    using Base::Base;
+
+    struct StepRecord {
+        int j;
+        bool accepted;
+        T infeasibility;  // of the proposal
+    };
+
+    StepRecord step() {
+        typename Base::Proposal proposal(*this);
+        this->importanceFunc->perturb(this->X, proposal.changedXIndices);
+        for (size_t nzi = 0; nzi < proposal.changedXIndices.size(); ++nzi)
+            std::swap(this->X[proposal.changedXIndices[nzi]], proposal.changedXValues[nzi]);
+        double proposedLogImportance = this->importanceFunc->getLogValue(this->X);
+        double ratioOfSums = proposal.calcRatioOfSums(this->basisDistribution);
+        double acceptance = exp(proposedLogImportance - this->currentLogImportance) * ratioOfSums;
+        StepRecord rec{proposal.proposedj, false, proposal.infeasibility};
+        if (Random::nextDouble() < acceptance) {
+            this->stats.addSample(true, this->currentInfeasibility == 0, proposal.infeasibility == 0);
+            this->currentLogImportance = proposedLogImportance;
+            this->applyProposal(proposal, false);
+            rec.accepted = true;
+        } else {
+            for (size_t nzi = 0; nzi < proposal.changedXIndices.size(); ++nzi)
+                this->X[proposal.changedXIndices[nzi]] = proposal.changedXValues[nzi];
+            this->importanceFunc->undo();
+            this->stats.addSample(false, this->currentInfeasibility == 0, proposal.infeasibility == 0);
+        }
+        return rec;
+    }
+};
+
+static uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+static uint64_t hashX(const std::vector<occ_t> &X) {  // sum_i X_i * mix64(i)  (mod 2^64)
+    uint64_t h = 0;
+    for (size_t i = 0; i < X.size(); ++i) h += uint64_t(int64_t(X[i])) * mix64(i);
+    return h;
+}
+static uint64_t bitsOf(double d) {
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int G>
+AbmpFile exportProblem(const PredPreyProblem<G> &problem, int seed, double pMakeObs, double pObsIfPresent) {
+    typedef PredPreyAgent<G> Agent;
+    AbmpFile f;
+    abmcmc::flattenTableau<TableauNormMinimiser<occ_t>, occ_t>(f, problem.tableau, problem.posterior.factors, problem.kappa);
+    abmcmc::flattenPredPreyImportance<Agent>(f, G, problem.nTimesteps());
+    f.f64["pp_params"] = {problem.pPredator, problem.pPrey, pMakeObs, pObsIfPresent};
+    f.i32["gen_seed"] = {seed};
+    std::vector<int32_t> rtIdx, rtVal;
+    const std::vector<occ_t> &rt = problem.realTrajectory;
+    for (size_t e = 0; e < rt.size(); ++e)
+        if (rt[e] != 0) {
+            rtIdx.push_back(int32_t(e));
+            rtVal.push_back(rt[e]);
+        }
+    f.i32["rt_idx"] = rtIdx;
+    f.i32["rt_val"] = rtVal;
+    std::vector<int32_t> ot, oa, on;
+    std::vector<double> op;
+    for (const auto &o : problem.likelihood.observations) {
+        ot.push_back(o.state.time);
+        oa.push_back(int(o.state.agent));
+        on.push_back(o.lowerBound);
+        op.push_back(o.pObserveIfPresent);
+    }
+    f.i32["obs_time"] = ot;
+    f.i32["obs_agent"] = oa;
+    f.i32["obs_n"] = on;
+    f.f64["obs_p"] = op;
+    return f;
+}
+
+// Rebuild a reference PredPreyProblem<G> from an ABMP file: the same field-by-field assembly the
+// reference's own load() does (PredPreyProblem.h:92-99), with the tableau filled from the flat
+// arrays instead of a Boost archive.
+template <int G>
+PredPreyProblem<G> importProblem(const AbmpFile &f) {
+    typedef PredPreyAgent<G> Agent;
+    PredPreyProblem<G> p;
+    const auto &meta = f.I("pp_meta");
+    if (meta[0] != G) throw std::runtime_error("importProblem: grid size mismatch");
+    int T = meta[1];
+    p.pPredator = f.D("pp_params")[0];
+    p.pPrey = f.D("pp_params")[1];
+    p.kappa = f.D("kappa")[0];
+    p.realTrajectory = Trajectory<Agent>(T);
+    const auto &ri = f.I("rt_idx"), &rv = f.I("rt_val");
+    for (size_t k = 0; k < ri.size(); ++k) p.realTrajectory[ri[k]] = rv[k];
+    std::vector<AgentStateObservation<Agent>> observations;
+    const auto &ot = f.I("obs_time"), &oa = f.I("obs_agent"), &on = f.I("obs_n");
+    const auto &op = f.D("obs_p");
+    for (size_t k = 0; k < ot.size(); ++k)
+        observations.emplace_back(State<Agent>(ot[k], Agent(oa[k])), on[k], op[k]);
+    p.prior = Prior<Agent>(T, p.startStatePrior());
+    p.likelihood = Likelihood<Agent>(observations);
+    p.posterior = p.likelihood * p.prior;
+
+    const auto &dims = f.I("dims");
+    int nTabRows = dims[0], nTabCols = dims[1];
+    auto &tab = p.tableau;
+    tab.rows.resize(nTabRows);
+    tab.cols.resize(nTabCols);
+    tab.nAuxiliaryVars = dims[2];
+    tab.L.assign(f.I("tab_L").begin(), f.I("tab_L").end());
+    tab.U.assign(f.I("tab_U").begin(), f.I("tab_U").end());
+    tab.F.assign(f.I("tab_F").begin(), f.I("tab_F").end());
+    const auto &cb = f.u8.at("col_basic");
+    for (int j = 0; j < nTabCols; ++j) tab.cols[j].isBasic = cb[j] != 0;
+    const auto &nbCol = f.I("nb_col"), &nbPtr = f.I("nb_ptr"), &nbRow = f.I("nb_row"), &nbVal = f.I("nb_val");
+    for (size_t c = 0; c < nbCol.size(); ++c)
+        for (int k = nbPtr[c]; k < nbPtr[c + 1]; ++k) {
+            tab.cols[nbCol[c]].insert(nbRow[k]);
+            tab.rows[nbRow[k]][nbCol[c]] = nbVal[k];
+        }
+    if ((int)p.posterior.factors.size() != nTabRows) throw std::runtime_error("importProblem: factor count mismatch");
+    return p;
+}
+
+template <int G>
+std::vector<occ_t> priorSample(const PredPreyProblem<G> &problem) {
+    return problem.prior.nextSample(false);  // FiguresForPaper.h:56,162
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int G>
+int cmdGen(int T, int seed, double kappa, const std::string &out, double pPred, double pPrey, double pMakeObs,
+           double pObsIfPresent) {
+    auto t0 = std::chrono::steady_clock::now();
+    Random::gen.seed(seed);  // FiguresForPaper.h:33
+    PredPreyProblem<G> problem(T, pPred, pPrey, pMakeObs, pObsIfPresent, kappa);
+    auto t1 = std::chrono::steady_clock::now();
+    AbmpFile f = exportProblem<G>(problem, seed, pMakeObs, pObsIfPresent);
+    f.f64["gen_seconds"] = {std::chrono::duration<double>(t1 - t0).count()};
+    f.write(out);
+    const auto &d = f.I("dims");
+    fprintf(stderr, "gen G=%d T=%d: tableau %d x %d, nAux=%d nNonBasic=%d nnz=%d, %zu unique factor tables, built in %.2fs\n",
+            G, T, d[0], d[1], d[2], d[3], d[4], f.I("ut_lo").size(), f.D("gen_seconds")[0]);
+    return 0;
+}
+
+// Writes nChains prior samples (event vectors, int8, [nChains][nEvents]) drawn as FiguresForPaper.h:56.
+template <int G>
+int cmdInit(const AbmpFile &f, int nChains, int seed, const std::string &out) {
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    Random::gen.seed(seed);
+    FILE *fo = fopen(out.c_str(), "wb");
+    if (!fo) throw std::runtime_error("cannot open output");
+    for (int c = 0; c < nChains; ++c) {
+        std::vector<occ_t> s = priorSample<G>(problem);
+        std::vector<int8_t> b(s.begin(), s.end());
+        fwrite(b.data(), 1, b.size(), fo);
+    }
+    fclose(fo);
+    return 0;
+}
+
+struct SilenceStdout {  // the reference prints progress lines to std::cout from its constructors
+    std::streambuf *old;
+    std::ostringstream sink;
+    SilenceStdout() : old(std::cout.rdbuf(sink.rdbuf())) {}
+    ~SilenceStdout() { std::cout.rdbuf(old); }
+};
+
+// Golden trace.  Stream layout (little-endian), all through one AbmpFile for convenience:
+//   init_state i8[nEvents]; post-ctor: init_iters, X0 i32[nRows], delta0 i8[nCols], DE0 f64[nCols],
+//   leaf0 f64[nCols] (basisDistribution.get), sum0, logImp0;
+//   per step: tr_j i32, tr_acc u8, tr_inf i32 (proposal infeasibility);
+//   checkpoints every `every` steps: ck_hash (two i32 per u64), ck_logimp f64, ck_sum f64, ck_inf i32;
+//   final: X, delta, DE, leaf, counters.
+template <int G>
+int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int every, const std::string &out) {
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    Random::gen.seed(initSeed);
+    std::vector<occ_t> init = priorSample<G>(problem);
+    Random::gen.seed(chainSeed);
+    std::unique_ptr<TracedSampler<occ_t>> sp;
+    std::string ctorLog;
+    {
+        SilenceStdout quiet;
+        sp.reset(new TracedSampler<occ_t>(problem.tableau, problem.posterior.factors,
+                                          problem.posterior.perturbableFunctionFactory(), init, problem.kappa));
+        ctorLog = quiet.sink.str();
+    }
+    auto &s = *sp;
+    AbmpFile t;
+    int initIters = 0;
+    sscanf(ctorLog.c_str(), "Found feasible solution in %d", &initIters);
+    t.i32["seeds"] = {initSeed, chainSeed};
+    t.i32["init_iters"] = {initIters};
+    t.i8["init_state"] = std::vector<int8_t>(init.begin(), init.end());
+    auto snapshot = [&](const std::string &sfx) {
+        t.i32["X" + sfx] = std::vector<int32_t>(s.X.begin(), s.X.end());
+        t.i8["delta" + sfx] = std::vector<int8_t>(s.delta.begin(), s.delta.end());
+        t.f64["DE" + sfx] = s.currentDE;
+        std::vector<double> leaf(s.nCols());
+        for (int j = 0; j < s.nCols(); ++j) leaf[j] = s.basisDistribution.get(j);
+        t.f64["leaf" + sfx] = leaf;
+        t.f64["scal" + sfx] = {s.basisDistribution.sum(), s.currentLogImportance};
+        t.i32["inf" + sfx] = {int32_t(s.currentInfeasibility)};
+    };
+    snapshot("0");
+    std::vector<int32_t> trJ, trInf, ckHash, ckInf;
+    std::vector<uint8_t> trAcc;
+    std::vector<double> ckLogImp, ckSum;
+    trJ.reserve(nSteps);
+    for (long k = 0; k < nSteps; ++k) {
+        auto r = s.step();
+        trJ.push_back(r.j);
+        trAcc.push_back(r.accepted ? 1 : 0);
+        trInf.push_back(int32_t(r.infeasibility));
+        if ((k + 1) % every == 0 || k + 1 == nSteps) {
+            uint64_t h = hashX(s.X);
+            ckHash.push_back(int32_t(uint32_t(h)));
+            ckHash.push_back(int32_t(uint32_t(h >> 32)));
+            ckLogImp.push_back(s.currentLogImportance);
+            ckSum.push_back(s.basisDistribution.sum());
+            ckInf.push_back(int32_t(s.currentInfeasibility));
+        }
+    }
+    t.i32["tr_j"] = trJ;
+    t.u8["tr_acc"] = trAcc;
+    t.i32["tr_inf"] = trInf;
+    t.i32["ck_every"] = {every};
+    t.i32["ck_hash"] = ckHash;
+    t.f64["ck_logimp"] = ckLogImp;
+    t.f64["ck_sum"] = ckSum;
+    t.i32["ck_inf"] = ckInf;
+    snapshot("N");
+    std::vector<int32_t> ctr;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) ctr.push_back(s.stats.nProposals[a][b]);
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) ctr.push_back(s.stats.nAccepted[a][b]);
+    t.i32["counters"] = ctr;
+    t.write(out);
+    fprintf(stderr, "trace: init_iters=%d steps=%ld accepted=%d feasible-ending=%d\n", initIters, nSteps,
+            s.stats.totalAccepted(), s.stats.nFeasibleSamples());
+    return 0;
+}
+
+// Proves TracedSampler::step() == the unmodified operator(): two samplers, same seeds, one driven
+// by operator(), the other by step() until feasible; all state compared after every sample.
+template <int G>
+int cmdSelfcheck(const AbmpFile &f, int nSamples) {
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    Random::gen.seed(7);
+    std::vector<occ_t> init = priorSample<G>(problem);
+    std::mt19937 genA, genB;
+    SilenceStdout quiet;
+    Random::gen.seed(99);
+    SparseBasisSampler<occ_t> a(problem.tableau, problem.posterior.factors, problem.posterior.perturbableFunctionFactory(), init, problem.kappa);
+    genA = Random::gen;
+    Random::gen.seed(99);
+    TracedSampler<occ_t> b(problem.tableau, problem.posterior.factors, problem.posterior.perturbableFunctionFactory(), init, problem.kappa);
+    genB = Random::gen;
+    for (int n = 0; n < nSamples; ++n) {
+        Random::gen = genA;
+        a();
+        genA = Random::gen;
+        Random::gen = genB;
+        do { b.step(); } while (b.currentInfeasibility > 0);
+        genB = Random::gen;
+        bool same = a.X == b.X && a.delta == b.delta && a.currentDE == b.currentDE &&
+                    bitsOf(a.currentLogImportance) == bitsOf(b.currentLogImportance) &&
+                    bitsOf(a.basisDistribution.sum()) == bitsOf(b.basisDistribution.sum()) &&
+                    a.stats.nSamples() == b.stats.nSamples() && a.stats.totalAccepted() == b.stats.totalAccepted() &&
+                    genA == genB;
+        if (!same) {
+            fprintf(stderr, "selfcheck: MISMATCH at sample %d\n", n);
+            return 1;
+        }
+    }
+    fprintf(stderr, "selfcheck: traced step() identical to operator() over %d samples (%d steps)\n", nSamples, a.stats.nSamples());
+    return 0;
+}
+
+struct TimingResult {
+    long steps = 0, feasible = 0, accepted = 0;
+    double seconds = 0;
+};
+
+// sampleTiming protocol (FiguresForPaper.h:151-178) on one thread: construct from a prior sample,
+// nSamples/4 burn-in calls, then time nSamples calls of sampler(); steps from sampler.stats.
+template <int G>
+TimingResult timeOneChain(const PredPreyProblem<G> &problem, std::vector<occ_t> init, int threadSeed, long nSamples, double maxSeconds) {
+    Random::gen.seed(threadSeed);  // thread-local generator (Random.h:15)
+    SparseBasisSampler<occ_t> sampler(problem.tableau, problem.posterior.factors,
+                                      problem.posterior.perturbableFunctionFactory(), init, problem.kappa);
+    for (long b = 0; b < nSamples / 4; ++b) sampler();
+    long steps0 = sampler.stats.nSamples(), acc0 = sampler.stats.totalAccepted();
+    auto t0 = std::chrono::steady_clock::now();
+    long done = 0;
+    for (; done < nSamples; ++done) {
+        sampler();
+        if ((done & 1023) == 1023 && maxSeconds > 0 &&
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > maxSeconds) { ++done; break; }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    TimingResult r;
+    r.steps = sampler.stats.nSamples() - steps0;
+    r.accepted = sampler.stats.totalAccepted() - acc0;
+    r.feasible = done;
+    r.seconds = std::chrono::duration<double>(t1 - t0).count();
+    return r;
+}
+
+template <int G>
+int cmdTime(const AbmpFile &f, int nThreads, long nSamples, double maxSeconds) {
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    Random::gen.seed(4321);
+    std::vector<std::vector<occ_t>> inits;
+    for (int t = 0; t < nThreads; ++t) inits.push_back(priorSample<G>(problem));
+    std::vector<std::future<TimingResult>> fut;
+    auto w0 = std::chrono::steady_clock::now();
+    {
+        SilenceStdout quiet;
+        for (int t = 0; t < nThreads; ++t)  // one independent chain per host thread (FiguresForPaper.h:54-57)
+            fut.push_back(std::async(std::launch::async, [&problem, &inits, t, nSamples, maxSeconds]() {
+                return timeOneChain<G>(problem, inits[t], 1000 + t, nSamples, maxSeconds);
+            }));
+        for (auto &x : fut) x.wait();
+    }
+    double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+    long steps = 0, feas = 0, acc = 0;
+    double maxSec = 0, rate = 0;
+    for (auto &x : fut) {
+        TimingResult r = x.get();
+        steps += r.steps;
+        feas += r.feasible;
+        acc += r.accepted;
+        maxSec = std::max(maxSec, r.seconds);
+        rate += r.steps / r.seconds;
+    }
+    printf("{\"impl\": \"reference\", \"grid\": %d, \"threads\": %d, \"steps\": %ld, \"feasible_samples\": %ld, \"accepted\": %ld, "
+           "\"timed_seconds_max\": %.6f, \"steps_per_s\": %.3f, \"wall_seconds_incl_setup\": %.3f}\n",
+           G, nThreads, steps, feas, acc, maxSec, rate, wall);
+    return 0;
+}
+
+// Long reference chains for posterior marginals: per thread one chain, `burnin` + nSamples calls of
+// sampler(); accumulates the end-state occupancy (ModelState(traj,T,T), ModelState.h:27-36) and the
+// whole-trajectory event marginals.  Output: ABMP with endstate_sum i64-as-f64[S], event_sum f64[nEvents],
+// n_samples.
+template <int G>
+int cmdMarginals(const AbmpFile &f, int nThreads, long nSamples, long burnin, const std::string &out) {
+    typedef PredPreyAgent<G> Agent;
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    int T = problem.nTimesteps();
+    Random::gen.seed(8765);
+    std::vector<std::vector<occ_t>> inits;
+    for (int t = 0; t < nThreads; ++t) inits.push_back(priorSample<G>(problem));
+    struct Acc { std::vector<double> end, ev; long n = 0, steps = 0; };
+    std::vector<std::future<Acc>> fut;
+    {
+        SilenceStdout quiet;
+        for (int t = 0; t < nThreads; ++t)
+            fut.push_back(std::async(std::launch::async, [&problem, &inits, t, T, nSamples, burnin]() {
+                Random::gen.seed(5000 + t);
+                SparseBasisSampler<occ_t> sampler(problem.tableau, problem.posterior.factors,
+                                                  problem.posterior.perturbableFunctionFactory(), inits[t], problem.kappa);
+                for (long b = 0; b < burnin; ++b) sampler();
+                Acc a;
+                int nEvents = T * Agent::domainSize() * Agent::actDomainSize();
+                a.end.assign(Agent::domainSize(), 0.0);
+                a.ev.assign(nEvents, 0.0);
+                long s0 = sampler.stats.nSamples();
+                for (long n = 0; n < nSamples; ++n) {
+                    const std::vector<occ_t> &x = sampler();
+                    ModelState<Agent> endState(x, T, T);
+                    for (int k = 0; k < Agent::domainSize(); ++k) a.end[k] += endState[k];
+                    for (int e = 0; e < nEvents; ++e) a.ev[e] += x[e];
+                }
+                a.n = nSamples;
+                a.steps = sampler.stats.nSamples() - s0;
+                return a;
+            }));
+        for (auto &x : fut) x.wait();
+    }
+    AbmpFile o;
+    std::vector<double> end, ev;
+    double n = 0, steps = 0;
+    std::vector<double> perChainEnd;
+    for (auto &x : fut) {
+        Acc a = x.get();
+        if (end.empty()) { end.assign(a.end.size(), 0.0); ev.assign(a.ev.size(), 0.0); }
+        for (size_t k = 0; k < end.size(); ++k) end[k] += a.end[k];
+        for (size_t k = 0; k < ev.size(); ++k) ev[k] += a.ev[k];
+        for (size_t k = 0; k < a.end.size(); ++k) perChainEnd.push_back(a.end[k] / a.n);
+        n += a.n;
+        steps += a.steps;
+    }
+    o.f64["endstate_sum"] = end;
+    o.f64["event_sum"] = ev;
+    o.f64["perchain_endstate_mean"] = perChainEnd;
+    o.f64["n_samples"] = {n, steps, double(nThreads)};
+    o.write(out);
+    return 0;
+}
+
+#define DISPATCH_G(G_, CALL)                                   \
+    switch (G_) {                                              \
+        case 3: { constexpr int G = 3; return CALL; }          \
+        case 4: { constexpr int G = 4; return CALL; }          \
+        case 8: { constexpr int G = 8; return CALL; }          \
+        case 16: { constexpr int G = 16; return CALL; }        \
+        case 32: { constexpr int G = 32; return CALL; }        \
+        case 64: { constexpr int G = 64; return CALL; }        \
+        default: fprintf(stderr, "unsupported grid size %d\n", G_); return 2; \
+    }
+
+static int run(int argc, char **argv) {
+    if (argc < 2) {
+        fprintf(stderr,
+                "usage:\n"
+                "  abm_ref gen G T seed kappa out.abmp [pPred pPrey pMakeObs pObsIfPresent]\n"
+                "  abm_ref init in.abmp nChains seed out.i8\n"
+                "  abm_ref trace in.abmp initSeed chainSeed nSteps checkpointEvery out.abmp\n"
+                "  abm_ref selfcheck in.abmp nSamples\n"
+                "  abm_ref time in.abmp nThreads nSamplesPerThread [maxSeconds]\n"
+                "  abm_ref marginals in.abmp nThreads nSamples burnin out.abmp\n");
+        return 2;
+    }
+    std::string cmd = argv[1];
+    if (cmd == "gen") {
+        int g = atoi(argv[2]), T = atoi(argv[3]), seed = atoi(argv[4]);
+        double kappa = atof(argv[5]);
+        std::string out = argv[6];
+        double pPred = argc > 7 ? atof(argv[7]) : 0.05, pPrey = argc > 8 ? atof(argv[8]) : 0.05;
+        double pObs = argc > 9 ? atof(argv[9]) : 0.05, pObsIf = argc > 10 ? atof(argv[10]) : 1.0;
+        DISPATCH_G(g, cmdGen<G>(T, seed, kappa, out, pPred, pPrey, pObs, pObsIf));
+    }
+    AbmpFile f = AbmpFile::read(argv[2]);
+    int g = f.I("pp_meta")[0];
+    if (cmd == "init") { DISPATCH_G(g, cmdInit<G>(f, atoi(argv[3]), atoi(argv[4]), argv[5])); }
+    if (cmd == "trace") { DISPATCH_G(g, cmdTrace<G>(f, atoi(argv[3]), atoi(argv[4]), atol(argv[5]), atoi(argv[6]), argv[7])); }
+    if (cmd == "selfcheck") { DISPATCH_G(g, cmdSelfcheck<G>(f, atoi(argv[3]))); }
+    if (cmd == "time") { DISPATCH_G(g, cmdTime<G>(f, atoi(argv[3]), atol(argv[4]), argc > 5 ? atof(argv[5]) : 0.0)); }
+    if (cmd == "marginals") { DISPATCH_G(g, cmdMarginals<G>(f, atoi(argv[3]), atol(argv[4]), atol(argv[5]), argv[6])); }
+    fprintf(stderr, "unknown command %s\n", cmd.c_str());
+    return 2;
+}
+
+int main(int argc, char **argv) {
+    try {
+        return run(argc, argv);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "abm_ref: %s\n", e.what());
+        return 1;
+    } catch (const char *e) {
+        fprintf(stderr, "abm_ref: %s\n", e);
+        return 1;
+    }
+}

@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Regenerates the golden fixtures in this directory from the UNMODIFIED reference.
+
+Needs /root/reference (read-only) and a host compiler; run from the repository root:
+    make -C oracle ref && python tests/golden/make_golden.py [--with-32]
+Problems: FiguresForPaper::generateStandardProblemFile protocol (FiguresForPaper.h:25-37): seed 1234,
+pPredator = pPrey = 0.05, pMakeObservation = 0.05, pObserveIfPresent = 1.0, kappa = 10.
+Traces: oracle/ref/abm_ref.cpp `trace` (initial state = prior.nextSample(false) under initSeed; sampler
+constructed and stepped under chainSeed with the reference's own mt19937 Random::gen).
+"""
+import lzma
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+REF = HERE.parent.parent / "oracle" / "_ref" / "abm_ref"
+
+
+def xz(src: Path, dst: Path):
+    dst.write_bytes(lzma.compress(src.read_bytes(), preset=9 | lzma.PRESET_EXTREME))
+    print(f"{dst.name}: {dst.stat().st_size} bytes")
+
+
+def main():
+    with32 = "--with-32" in sys.argv
+    tmp = Path(tempfile.mkdtemp())
+    problems = [(8, 4), (16, 8)] + ([(32, 16)] if with32 else [])
+    for g, t in problems:
+        raw = tmp / f"pp{g}-{t}.abmp"
+        subprocess.run([str(REF), "gen", str(g), str(t), "1234", "10.0", str(raw)], check=True, stdout=subprocess.DEVNULL)
+        xz(raw, HERE / f"pp{g}-{t}.abmp.xz")
+    # (problem, initSeed, chainSeed, nSteps, checkpointEvery)
+    traces = [("pp8-4", 11, 101, 20000, 500), ("pp8-4", 12, 102, 20000, 500), ("pp16-8", 12, 202, 20000, 500)]
+    for name, s0, s1, n, every in traces:
+        raw = tmp / f"trace_{name}_{s1}.abmp"
+        subprocess.run([str(REF), "trace", str(tmp / f"{name}.abmp"), str(s0), str(s1), str(n), str(every), str(raw)], check=True)
+        xz(raw, HERE / f"trace_{name}_{s1}.abmp.xz")
+
+
+if __name__ == "__main__":
+    main()

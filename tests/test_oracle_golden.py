@@ -1,0 +1,103 @@
+"""Pins oracle/sbs_oracle.c to the reference: golden step traces emitted by the UNMODIFIED reference
+SparseBasisSampler (oracle/ref/abm_ref.cpp `trace`, fixtures made by tests/golden/make_golden.py).
+Everything is compared bitwise -- integers, accept decisions and doubles."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle.oracle import OracleChain, OracleProblem, mt_uniforms
+
+TRACES = [("pp8-4.abmp.xz", "trace_pp8-4_101.abmp.xz"), ("pp8-4.abmp.xz", "trace_pp8-4_102.abmp.xz"),
+          ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz")]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def hash_X(X):
+    # sum_i X_i * splitmix64(i) mod 2^64 (abm_ref.cpp hashX)
+    i = np.arange(X.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = i + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int((X.astype(np.int64).astype(np.uint64) * z).sum(dtype=np.uint64))
+
+
+@pytest.mark.parametrize("prob,trace", TRACES)
+def test_oracle_matches_reference_trace(prob, trace):
+    p, t = load_golden(prob), load_golden(trace)
+    P = OracleProblem(p)
+    c = OracleChain(P, t["init_state"])
+    c.seed_mt(int(t["seeds"][1]))
+    # constructor + findInitialFeasibleSolution (SparseBasisSampler.h:107-185, 254-263)
+    assert c.find_feasible() == int(t["init_iters"][0])
+    assert np.array_equal(c.X, t["X0"])
+    assert np.array_equal(c.delta, t["delta0"])
+    assert np.array_equal(bits(c.DE), bits(t["DE0"]))
+    assert np.array_equal(bits(c.leaf), bits(t["leaf0"]))
+    assert bits([c.sum, c.log_importance]).tolist() == bits(t["scal0"]).tolist()
+    assert c.infeasibility == 0
+    # Metropolis steps, checkpoint by checkpoint (SparseBasisSampler.h:219-249)
+    every = int(t["ck_every"][0])
+    n = t["tr_j"].size
+    ck_hash = t["ck_hash"].view(np.uint32).astype(np.uint64)
+    ck_hash = ck_hash[0::2] | (ck_hash[1::2] << np.uint64(32))
+    for k in range(n // every):
+        j, acc, inf = c.step(every, trace=True)
+        sl = slice(k * every, (k + 1) * every)
+        assert np.array_equal(j, t["tr_j"][sl])
+        assert np.array_equal(acc, t["tr_acc"][sl])
+        assert np.array_equal(inf, t["tr_inf"][sl])
+        assert c.hash_X == int(ck_hash[k]) == hash_X(c.X)
+        assert bits([c.log_importance])[0] == bits(t["ck_logimp"])[k]
+        assert bits([c.sum])[0] == bits(t["ck_sum"])[k]
+        assert c.infeasibility == int(t["ck_inf"][k])
+    assert np.array_equal(c.X, t["XN"])
+    assert np.array_equal(c.delta, t["deltaN"])
+    assert np.array_equal(bits(c.DE), bits(t["DEN"]))
+    assert np.array_equal(bits(c.leaf), bits(t["leafN"]))
+    assert np.array_equal(c.counters, t["counters"])
+
+
+def test_injected_uniform_stream_equals_mt_stream():
+    """Feeding the oracle the mt19937/generate_canonical doubles as an injected stream reproduces the
+    trace: this is the route by which the GPU kernel is fed the reference's uniforms."""
+    p, t = load_golden("pp8-4.abmp.xz"), load_golden("trace_pp8-4_101.abmp.xz")
+    P = OracleProblem(p)
+    c = OracleChain(P, t["init_state"])
+    n_init, n = int(t["init_iters"][0]), 5000
+    u = mt_uniforms(int(t["seeds"][1]), n_init + 2 * n)
+    c.set_injected(u)
+    assert c.find_feasible() == n_init
+    j, acc, inf = c.step(n, trace=True)
+    assert np.array_equal(j, t["tr_j"][:n]) and np.array_equal(acc, t["tr_acc"][:n]) and np.array_equal(inf, t["tr_inf"][:n])
+
+
+def test_problem_structure_matches_survey():
+    """Sizes quoted in SURVEY.md section 8 for the seed-1234 instances."""
+    for name, rows, cols, nnz in (("pp8-4.abmp.xz", 3456, 2658, 13738), ("pp16-8.abmp.xz", 27136, 20788, 112552)):
+        p = load_golden(name)
+        P = OracleProblem(p)
+        assert (P.n_rows, P.n_cols, int(p["dims"][4])) == (rows, cols, nnz)
+        assert np.abs(p["nb_val"]).max() == 1  # PredPrey basis entries are all +-1
+        # sampler row i == event id i for i < nEvents: no equality among the first nEvents rows
+        ne = int(p["pp_meta"][2])
+        assert np.all(p["tab_L"][:ne] != p["tab_U"][:ne])
+
+
+def test_end_state_occupancy_counts_agents():
+    p, t = load_golden("pp8-4.abmp.xz"), load_golden("trace_pp8-4_101.abmp.xz")
+    c = OracleChain(OracleProblem(p), t["init_state"])
+    c.seed_mt(5)
+    c.find_feasible()
+    c.step(200)
+    while c.infeasibility:
+        c.step(1)
+    X = c.X
+    A, S, T = 6, 128, 4
+    last = X[(T - 1) * S * A:T * S * A].reshape(S, A)
+    # every non-DIE act yields one agent at T, GIVEBIRTH two (PredPreyAgent.h:98-115)
+    assert c.end_state.sum() == last[:, 1:].sum() + last[:, 5].sum()
