@@ -1,0 +1,577 @@
+// C-ABI implementation (include/abmcmc_b200.h): host-side problem builder, device memory management and
+// kernel launches.  No CPU compute fallback exists: without a CUDA device every entry point that would
+// compute returns ABM_ERR_CUDA.
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "abmcmc_b200.h"
+#include "abm_kernels.cuh"
+
+using namespace abm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ABM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+struct DeviceArena {
+    std::vector<void *> ptrs;
+    size_t bytes = 0;
+    ~DeviceArena() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <class T>
+    cudaError_t alloc(T **out, size_t count) {
+        void *p = nullptr;
+        size_t b = std::max<size_t>(count, 1) * sizeof(T);
+        cudaError_t e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p);
+        bytes += b;
+        *out = static_cast<T *>(p);
+        return cudaSuccess;
+    }
+    template <class T>
+    cudaError_t upload(const T **out, const std::vector<T> &v) {
+        T *p = nullptr;
+        cudaError_t e = alloc(&p, v.size());
+        if (e != cudaSuccess) return e;
+        if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        *out = p;
+        return e;
+    }
+};
+
+}  // namespace
+
+struct abm_problem {
+    int device = 0;
+    DevProblem d{};
+    abm_problem_info info{};
+    DeviceArena arena;
+    std::vector<int32_t> xoff;   // physical Xb offset of each sampler row (host copy for read-back)
+};
+
+struct abm_chains {
+    const abm_problem *p = nullptr;
+    DevChains d{};
+    DeviceArena arena;
+    int32_t n = 0;
+    uint64_t seed = 0, firstChain = 0;
+    cudaStream_t stream = nullptr;
+    bool initialised = false, feasible = false;
+};
+
+extern "C" {
+
+const char *abm_last_error(void) { return g_err.c_str(); }
+int abm_version(void) { return 1; }
+int abm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **out) {
+    if (!desc || !out) return fail(ABM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (abm_device_count() <= device || device < 0) return fail(ABM_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+    const int nTab = desc->n_tab_rows, nCols = desc->n_nonbasic;
+    if (nTab <= 0 || nCols <= 0) return fail(ABM_ERR_INVALID, "empty problem");
+
+    // sampler rows = tableau rows that are not equalities, in order (SparseBasisSampler.h:128-140)
+    std::vector<int32_t> rowOf(nTab, -1);
+    int nRows = 0;
+    for (int i = 0; i < nTab; ++i)
+        if (desc->tab_L[i] != desc->tab_U[i]) rowOf[i] = nRows++;
+    const int nnz = desc->nb_ptr[nCols];
+    const int G = desc->grid_size, T = desc->n_timesteps;
+    const int S = 2 * G * G, nStates = T * S, nEvents = nStates * kActs;
+    if (G > 0) {
+        if (nEvents > nRows) return fail(ABM_ERR_INVALID, "PredPrey importance needs one row per event");
+        for (int i = 0; i < nEvents; ++i)
+            if (rowOf[i] != i) return fail(ABM_ERR_INVALID, "event rows must be the first, non-equality tableau rows");
+        if (!desc->imp_lgamma || !desc->imp_logratio) return fail(ABM_ERR_INVALID, "missing importance tables");
+    }
+
+    std::vector<int32_t> colPtr(desc->nb_ptr, desc->nb_ptr + nCols + 1), colRow(nnz), colVal(nnz);
+    std::vector<int32_t> rowPtr(nRows + 1, 0), rowCol(nnz), rowVal(nnz), rowF(nRows);
+    std::vector<long> xmin(nRows), xmax(nRows);
+    for (int i = 0; i < nTab; ++i)
+        if (rowOf[i] >= 0) rowF[rowOf[i]] = desc->tab_F[i], xmin[rowOf[i]] = xmax[rowOf[i]] = desc->tab_F[i];
+    int maxColNnz = 0;
+    for (int j = 0; j < nCols; ++j) {
+        maxColNnz = std::max(maxColNnz, colPtr[j + 1] - colPtr[j]);
+        for (int k = colPtr[j]; k < colPtr[j + 1]; ++k) {
+            const int r = desc->nb_row[k] >= 0 && desc->nb_row[k] < nTab ? rowOf[desc->nb_row[k]] : -1;
+            if (r < 0) return fail(ABM_ERR_INVALID, "non-basic column has an entry in an equality row");
+            if (k > colPtr[j] && colRow[k - 1] >= r) return fail(ABM_ERR_INVALID, "column entries must be ascending by row");
+            colRow[k] = r;
+            colVal[k] = desc->nb_val[k];
+            if (colVal[k] < -127 || colVal[k] > 127 || colVal[k] == 0) return fail(ABM_ERR_INVALID, "tableau entry out of int8 range");
+            rowPtr[r + 1]++;
+            (colVal[k] < 0 ? xmin[r] : xmax[r]) += colVal[k];
+        }
+    }
+    if (maxColNnz > 32) return fail(ABM_ERR_INVALID, "columns with more than 32 entries are not supported");
+    for (int i = 0; i < nRows; ++i) {
+        rowPtr[i + 1] += rowPtr[i];
+        if (xmin[i] < -128 || xmax[i] > 127) return fail(ABM_ERR_INVALID, "row value range exceeds int8");
+    }
+    {
+        std::vector<int32_t> fill(rowPtr.begin(), rowPtr.end() - 1);
+        for (int j = 0; j < nCols; ++j)   // rows[i] gets its entries in ascending column order (:148-153)
+            for (int k = colPtr[j]; k < colPtr[j + 1]; ++k) {
+                rowCol[fill[colRow[k]]] = j;
+                rowVal[fill[colRow[k]]++] = colVal[k];
+            }
+    }
+
+    // physical layout of X: event rows 8 bytes per agent state, then the remaining rows
+    const int evBytes = nStates * kStateBytes;
+    std::vector<int32_t> xoff(nRows);
+    for (int i = 0; i < nRows; ++i)
+        xoff[i] = i < nEvents ? (i / kActs) * kStateBytes + i % kActs : evBytes + (i - nEvents);
+    const int xStride = ((evBytes + (nRows - nEvents)) + 15) & ~15;
+    if (xStride >= (1 << 24)) return fail(ABM_ERR_INVALID, "too many rows");
+
+    // factor tables
+    int nVal = desc->ut_off[desc->n_tables];
+    std::vector<double> facVal(desc->ut_val, desc->ut_val + nVal);
+    std::vector<int4> rowParam(nRows);
+    for (int i = 0, b = 0; i < nTab; ++i) {
+        if (rowOf[i] < 0) continue;
+        const int id = desc->fac_id[b];
+        if (id < 0 || id >= desc->n_tables) return fail(ABM_ERR_INVALID, "bad factor id");
+        const int lo = desc->ut_lo[id], len = desc->ut_off[id + 1] - desc->ut_off[id];
+        const long L = desc->tab_L[i], U = desc->tab_U[i];
+        const long dlo = std::min(std::max(xmin[b], L), U), dhi = std::max(std::min(xmax[b], U), L);
+        if (dlo < lo || dhi > lo + len - 1) return fail(ABM_ERR_INVALID, "factor table does not cover the reachable range of its row");
+        rowParam[b] = make_int4(xoff[b], desc->tab_L[i], desc->tab_U[i], desc->ut_off[id] - lo);
+        ++b;
+    }
+
+    // column records
+    std::vector<uint32_t> recOff(nCols + 1);
+    std::vector<int32_t> rec;
+    rec.reserve((size_t)nnz * 24);
+    int maxCoupled = 1;
+    struct Pair { int u, k, m; };
+    std::vector<Pair> pairs;
+    std::vector<int32_t> pu;
+    std::vector<int16_t> pkm;
+    std::vector<int32_t> staleF;
+    std::vector<char> seen(std::max(nStates, 1), 0);
+    for (int j = 0; j < nCols; ++j) {
+        while (rec.size() % 4) rec.push_back(0);
+        recOff[j] = uint32_t(rec.size() / 4);
+        const int n = colPtr[j + 1] - colPtr[j];
+        pairs.clear();
+        pairs.push_back({j, kSelfMarker, 0});
+        for (int k = 0; k < n; ++k) {
+            const int i = colRow[colPtr[j] + k];
+            for (int r = rowPtr[i]; r < rowPtr[i + 1]; ++r)
+                if (rowCol[r] != j) pairs.push_back({rowCol[r], k, rowVal[r]});
+        }
+        std::stable_sort(pairs.begin(), pairs.end(), [](const Pair &a, const Pair &b) { return a.u < b.u || (a.u == b.u && a.k < b.k); });
+        pu.clear();
+        pkm.clear();
+        int C = 0;
+        for (size_t a = 0; a < pairs.size();) {
+            size_t b = a;
+            while (b < pairs.size() && pairs[b].u == pairs[a].u) ++b;
+            const int run = int(b - a);
+            if (int(pu.size() % 32) + run > 32)
+                while (pu.size() % 32) { pu.push_back(-1); pkm.push_back(0); }
+            for (size_t q = a; q < b; ++q) {
+                pu.push_back(pairs[q].u);
+                pkm.push_back(int16_t((pairs[q].k & 0xff) | (pairs[q].m << 8)));
+            }
+            ++C;
+            a = b;
+        }
+        maxCoupled = std::max(maxCoupled, C);
+        // stale factors in TrajectoryImportance::perturb insertion order (TrajectoryImportance.h:41-53)
+        staleF.clear();
+        if (G > 0) {
+            auto ins = [&](int sid) { if (!seen[sid]) { seen[sid] = 1; staleF.push_back(sid); } };
+            for (int k = 0; k < n; ++k) {
+                const int i = colRow[colPtr[j] + k];
+                if (i >= nEvents) continue;
+                const int sid = i / kActs, t = sid / S, psi = sid % S;
+                const int x = psi % G, y = (psi / G) % G, other = 1 - psi / (G * G);
+                const int base = t * S + other * G * G;
+                ins(sid);
+                ins(base + (x + G - 1) % G + G * y);
+                ins(base + (x + 1) % G + G * y);
+                ins(base + x + G * ((y + 1) % G));
+                ins(base + x + G * ((y + G - 1) % G));
+            }
+            for (int sid : staleF) seen[sid] = 0;
+        }
+        rec.push_back(n);
+        rec.push_back(int32_t(pu.size()));
+        rec.push_back(C);
+        rec.push_back(int32_t(staleF.size()));
+        for (int k = 0; k < n; ++k) {
+            const int i = colRow[colPtr[j] + k];
+            const int4 rp = rowParam[i];
+            rec.push_back((rp.x & 0xffffff) | (colVal[colPtr[j] + k] << 24));
+            rec.push_back(rp.y);
+            rec.push_back(rp.z);
+            rec.push_back(rp.w);
+        }
+        rec.insert(rec.end(), pu.begin(), pu.end());
+        for (size_t q = 0; q < pkm.size(); q += 2) {
+            const uint32_t lo16 = uint16_t(pkm[q]), hi16 = q + 1 < pkm.size() ? uint16_t(pkm[q + 1]) : 0;
+            rec.push_back(int32_t(lo16 | (hi16 << 16)));
+        }
+        rec.insert(rec.end(), staleF.begin(), staleF.end());
+        if (rec.size() / 4 > 0xfffffff0ull) return fail(ABM_ERR_INVALID, "record table too large");
+    }
+    while (rec.size() % 4) rec.push_back(0);
+    recOff[nCols] = uint32_t(rec.size() / 4);
+    if (maxCoupled > 2047) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2047 others");
+
+    std::vector<double> impTab(7 + 24, 0.0);
+    if (G > 0) {
+        std::copy(desc->imp_lgamma, desc->imp_lgamma + 7, impTab.begin());
+        std::copy(desc->imp_logratio, desc->imp_logratio + 24, impTab.begin() + 7);
+    }
+
+    abm_problem *p = new abm_problem();
+    p->device = device;
+    p->xoff = xoff;
+    DevProblem &d = p->d;
+    d.nRows = nRows; d.nCols = nCols; d.nEvents = nEvents; d.xStride = xStride;
+    int depth = 0;
+    while ((1 << depth) < nCols) ++depth;   // bit length of nCols-1
+    if (nCols == 1) depth = 0;
+    d.treeDepth = depth;
+    d.t1Len = (nCols + 31) / 32;
+    d.t2Len = (nCols + 1023) / 1024;
+    d.evBytes = evBytes;
+    d.G = G; d.S = S; d.T = T; d.nStates = nStates;
+    d.maxCoupled = maxCoupled;
+    int nSyn = 0;
+    for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
+    d.nSynopsis = nSyn;
+    d.kappa = desc->kappa;
+    std::vector<int32_t> colEvent(desc->nb_col, desc->nb_col + nCols);
+    cudaError_t e = cudaSuccess;
+    auto up = [&](auto **dst, const auto &v) { if (e == cudaSuccess) e = p->arena.upload(dst, v); };
+    up(&d.recOff, recOff); up(&d.rec, rec); up(&d.facVal, facVal); up(&d.impTab, impTab);
+    up(&d.colPtr, colPtr); up(&d.colRow, colRow); up(&d.colVal, colVal);
+    up(&d.rowPtr, rowPtr); up(&d.rowCol, rowCol); up(&d.rowVal, rowVal);
+    up(&d.rowF, rowF); up(&d.rowParam, rowParam); up(&d.colEvent, colEvent);
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(ABM_ERR_CUDA, std::string("problem upload: ") + cudaGetErrorString(e));
+    }
+    abm_problem_info &inf = p->info;
+    inf.n_rows = nRows; inf.n_cols = nCols; inf.nnz = nnz; inf.n_events = nEvents;
+    inf.max_col_nnz = maxColNnz; inf.max_coupled = maxCoupled; inf.tree_depth = depth; inf.n_states = nStates;
+    inf.chain_state_bytes = int64_t(xStride) + int64_t(nCols) * 17 + int64_t(d.t1Len + d.t2Len) * 8;
+    inf.shared_bytes = int64_t(p->arena.bytes);
+    *out = p;
+    return ABM_OK;
+}
+
+int abm_problem_destroy(abm_problem *p) {
+    if (!p) return ABM_OK;
+    cudaSetDevice(p->device);
+    delete p;
+    return ABM_OK;
+}
+
+int abm_problem_get_info(const abm_problem *p, abm_problem_info *info) {
+    if (!p || !info) return fail(ABM_ERR_INVALID, "null argument");
+    *info = p->info;
+    return ABM_OK;
+}
+
+int abm_problem_n_synopsis(const abm_problem *p) { return p ? p->d.nSynopsis : 0; }
+
+// ------------------------------------------------------------------------------------------------
+int abm_chains_create(const abm_problem *p, int32_t nChains, uint64_t seed, uint64_t firstChainId, void *stream,
+                      abm_chains **out) {
+    if (!p || !out || nChains <= 0) return fail(ABM_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(p->device));
+    abm_chains *c = new abm_chains();
+    c->p = p;
+    c->n = nChains;
+    c->seed = seed;
+    c->firstChain = firstChainId;
+    c->stream = static_cast<cudaStream_t>(stream);
+    const DevProblem &P = p->d;
+    DevChains &d = c->d;
+    d.nChains = nChains;
+    const size_t n = size_t(nChains);
+    const int scrCap = std::max(P.maxCoupled - kSCap, 0);
+    cudaError_t e = cudaSuccess;
+    auto al = [&](auto **dst, size_t count) { if (e == cudaSuccess) e = c->arena.alloc(dst, count); };
+    al(&d.Xb, n * P.xStride); al(&d.colRec, n * P.nCols); al(&d.delta, n * P.nCols);
+    al(&d.tier1, n * P.t1Len); al(&d.tier2, n * P.t2Len);
+    al(&d.logImp, n); al(&d.infeas, n); al(&d.iter, n); al(&d.counters, n * 8);
+    al(&d.scrU, n * scrCap); al(&d.scrD, n * scrCap * 3); al(&d.scrTask, n * 32 * 32);
+    al(&d.endStateSum, size_t(std::max(P.S, 1))); al(&d.synSum, n * std::max(P.nSynopsis, 1));
+    al(&d.synSumSq, n * std::max(P.nSynopsis, 1)); al(&d.nSamples, n);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(ABM_ERR_CUDA, std::string("chain allocation: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return ABM_OK;
+}
+
+int abm_chains_destroy(abm_chains *c) {
+    if (!c) return ABM_OK;
+    cudaSetDevice(c->p->device);
+    cudaStreamSynchronize(c->stream);
+    delete c;
+    return ABM_OK;
+}
+
+int abm_chains_synchronize(abm_chains *c) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ABM_OK;
+}
+
+int abm_chains_init(abm_chains *c, const int8_t *initEvents, int32_t nInit) {
+    if (!c || nInit < 0 || (nInit > 0 && !initEvents)) return fail(ABM_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const DevProblem &P = c->p->d;
+    DevChains &d = c->d;
+    const size_t n = size_t(c->n);
+    int8_t *dInit = nullptr;
+    if (nInit > 0) {
+        CUDA_TRY(cudaMalloc(&dInit, n * nInit));
+        CUDA_TRY(cudaMemcpyAsync(dInit, initEvents, n * nInit, cudaMemcpyHostToDevice, c->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(d.Xb, 0, n * P.xStride, c->stream));
+    CUDA_TRY(cudaMemsetAsync(d.infeas, 0, n * sizeof(int32_t), c->stream));
+    CUDA_TRY(cudaMemsetAsync(d.logImp, 0, n * sizeof(double), c->stream));
+    CUDA_TRY(cudaMemsetAsync(d.iter, 0, n * sizeof(unsigned long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, n * 8 * sizeof(long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(d.tier1, 0, n * P.t1Len * sizeof(double), c->stream));
+    CUDA_TRY(cudaMemsetAsync(d.tier2, 0, n * P.t2Len * sizeof(double), c->stream));
+    const int threads = 256;
+    dim3 gridC(std::min((P.nCols + threads - 1) / threads, 64), c->n), gridR(std::min((P.nRows + threads - 1) / threads, 64), c->n);
+    initDeltaKernel<<<gridC, threads, 0, c->stream>>>(P, d, dInit, nInit);
+    initRowsKernel<<<gridR, threads, 0, c->stream>>>(P, d);
+    initColsKernel<<<gridC, threads, 0, c->stream>>>(P, d);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (dInit) CUDA_TRY(cudaFree(dInit));
+    c->initialised = true;
+    c->feasible = false;
+    return ABM_OK;
+}
+
+static size_t stepSmemBytes() { return size_t(kWarpsPerCta) * (kSCap * 4 + 3 * kSCap * 8 + kTCap * 2); }
+
+static RunParams baseParams(const abm_chains *c) {
+    RunParams r{};
+    r.seed = c->seed;
+    r.firstChain = c->firstChain;
+    return r;
+}
+
+int abm_chains_find_feasible(abm_chains *c, int64_t maxIterations, const double *uniforms, int64_t nUniforms,
+                             int64_t *iterationsOut) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    if (!c->initialised) return fail(ABM_ERR_STATE, "abm_chains_init has not been called");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const DevProblem &P = c->p->d;
+    const size_t n = size_t(c->n);
+    if (maxIterations <= 0) maxIterations = INT64_MAX;
+    double *dU = nullptr;
+    long long *dIters = nullptr;
+    CUDA_TRY(cudaMalloc(&dIters, n * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(dIters, 0, n * sizeof(long long), c->stream));
+    if (uniforms) {
+        CUDA_TRY(cudaMalloc(&dU, n * nUniforms * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(dU, uniforms, n * nUniforms * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        maxIterations = std::min<int64_t>(maxIterations, nUniforms);
+    }
+    const int grid = (c->n + kWarpsPerCta - 1) / kWarpsPerCta;
+    std::vector<int32_t> inf(n);
+    int64_t done = 0;
+    bool allFeasible = false;
+    while (done < maxIterations) {
+        const int64_t chunk = std::min<int64_t>(maxIterations - done, 1 << 16);
+        RunParams r = baseParams(c);
+        r.nSteps = chunk;
+        r.injU = dU;
+        r.uStride = nUniforms;
+        r.uOffset = done;   // valid because with injected uniforms all chains advance in lock step per launch
+        r.itersOut = dIters;
+        stepKernel<MODE_INIT><<<grid, kWarpsPerCta * 32, stepSmemBytes(), c->stream>>>(P, c->d, r);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(inf.data(), c->d.infeas, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        done += chunk;
+        allFeasible = std::all_of(inf.begin(), inf.end(), [](int32_t v) { return v == 0; });
+        if (allFeasible) break;
+    }
+    if (iterationsOut) {
+        std::vector<long long> it(n);
+        CUDA_TRY(cudaMemcpy(it.data(), dIters, n * sizeof(long long), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < n; ++k) iterationsOut[k] = it[k];
+    }
+    CUDA_TRY(cudaFree(dIters));
+    if (dU) CUDA_TRY(cudaFree(dU));
+    if (!allFeasible) return fail(ABM_ERR_NOT_FEASIBLE, "feasibility search hit its iteration limit");
+    setStateKernel<<<grid, kWarpsPerCta * 32, 0, c->stream>>>(P, c->d);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->feasible = true;
+    return ABM_OK;
+}
+
+int abm_chains_step(abm_chains *c, int64_t nSteps) {
+    if (!c || nSteps < 0) return fail(ABM_ERR_INVALID, "bad argument");
+    if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    RunParams r = baseParams(c);
+    r.nSteps = nSteps;
+    const int grid = (c->n + kWarpsPerCta - 1) / kWarpsPerCta;
+    stepKernel<MODE_MCMC><<<grid, kWarpsPerCta * 32, stepSmemBytes(), c->stream>>>(c->p->d, c->d, r);
+    CUDA_TRY(cudaGetLastError());
+    return ABM_OK;
+}
+
+int abm_chains_step_traced(abm_chains *c, int64_t nSteps, const double *uniforms, const int32_t *proposals,
+                           int32_t *outJ, uint8_t *outAcc, int32_t *outInf) {
+    if (!c || nSteps < 0) return fail(ABM_ERR_INVALID, "bad argument");
+    if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const size_t n = size_t(c->n), ns = size_t(nSteps);
+    DeviceArena tmp;
+    RunParams r = baseParams(c);
+    r.nSteps = nSteps;
+    double *dU = nullptr;
+    int32_t *dJ = nullptr, *dOutJ = nullptr, *dOutInf = nullptr;
+    uint8_t *dOutAcc = nullptr;
+    if (uniforms) {
+        CUDA_TRY(tmp.alloc(&dU, n * ns * 2));
+        CUDA_TRY(cudaMemcpyAsync(dU, uniforms, n * ns * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        r.injU = dU;
+        r.uStride = 2 * nSteps;
+    }
+    if (proposals) {
+        CUDA_TRY(tmp.alloc(&dJ, n * ns));
+        CUDA_TRY(cudaMemcpyAsync(dJ, proposals, n * ns * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        r.injJ = dJ;
+    }
+    CUDA_TRY(tmp.alloc(&dOutJ, n * ns));
+    CUDA_TRY(tmp.alloc(&dOutAcc, n * ns));
+    CUDA_TRY(tmp.alloc(&dOutInf, n * ns));
+    r.outJ = dOutJ; r.outAcc = dOutAcc; r.outInf = dOutInf;
+    const int grid = (c->n + kWarpsPerCta - 1) / kWarpsPerCta;
+    stepKernel<MODE_MCMC><<<grid, kWarpsPerCta * 32, stepSmemBytes(), c->stream>>>(c->p->d, c->d, r);
+    CUDA_TRY(cudaGetLastError());
+    if (outJ) CUDA_TRY(cudaMemcpyAsync(outJ, dOutJ, n * ns * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (outAcc) CUDA_TRY(cudaMemcpyAsync(outAcc, dOutAcc, n * ns, cudaMemcpyDeviceToHost, c->stream));
+    if (outInf) CUDA_TRY(cudaMemcpyAsync(outInf, dOutInf, n * ns * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ABM_OK;
+}
+
+int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
+    (void)nSamples; (void)maxSteps;
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    return fail(ABM_ERR_STATE, "abm_chains_sample: not implemented yet");
+}
+
+// ------------------------------------------------------------------------------------------------
+int abm_chains_get_state(abm_chains *c, int32_t chain, int32_t *X, int8_t *delta, double *currentDE, double *tree,
+                         double *logImportance, int32_t *infeasibility) {
+    if (!c || chain < 0 || chain >= c->n) return fail(ABM_ERR_INVALID, "bad chain index");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const DevProblem &P = c->p->d;
+    const size_t ch = size_t(chain);
+    if (X) {
+        std::vector<int8_t> xb(P.xStride);
+        CUDA_TRY(cudaMemcpy(xb.data(), c->d.Xb + ch * P.xStride, P.xStride, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < P.nRows; ++i) X[i] = xb[c->p->xoff[i]];
+    }
+    if (delta) CUDA_TRY(cudaMemcpy(delta, c->d.delta + ch * P.nCols, P.nCols, cudaMemcpyDeviceToHost));
+    if (currentDE || tree) {
+        std::vector<double2> cr(P.nCols);
+        std::vector<double> t1(P.t1Len), t2(P.t2Len);
+        CUDA_TRY(cudaMemcpy(cr.data(), c->d.colRec + ch * P.nCols, sizeof(double2) * P.nCols, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(t1.data(), c->d.tier1 + ch * P.t1Len, sizeof(double) * P.t1Len, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(t2.data(), c->d.tier2 + ch * P.t2Len, sizeof(double) * P.t2Len, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < P.nCols; ++j) {
+            if (currentDE) currentDE[j] = cr[j].x;
+            if (tree) tree[j] = (j & 31) ? cr[j].y : ((j & 1023) ? t1[j >> 5] : t2[j >> 10]);
+        }
+    }
+    if (logImportance) CUDA_TRY(cudaMemcpy(logImportance, c->d.logImp + ch, sizeof(double), cudaMemcpyDeviceToHost));
+    if (infeasibility) CUDA_TRY(cudaMemcpy(infeasibility, c->d.infeas + ch, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return ABM_OK;
+}
+
+int abm_chains_get_counters(abm_chains *c, abm_mcmc_counters *perChain) {
+    if (!c || !perChain) return fail(ABM_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    static_assert(sizeof(abm_mcmc_counters) == 64, "counter layout");
+    CUDA_TRY(cudaMemcpy(perChain, c->d.counters, size_t(c->n) * 64, cudaMemcpyDeviceToHost));
+    return ABM_OK;
+}
+
+int abm_chains_get_infeasibility(abm_chains *c, int32_t *perChain) {
+    if (!c || !perChain) return fail(ABM_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(perChain, c->d.infeas, size_t(c->n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return ABM_OK;
+}
+
+int abm_chains_get_trajectories(abm_chains *c, int8_t *events) {
+    if (!c || !events) return fail(ABM_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const DevProblem &P = c->p->d;
+    std::vector<int8_t> xb(size_t(c->n) * P.xStride);
+    CUDA_TRY(cudaMemcpy(xb.data(), c->d.Xb, xb.size(), cudaMemcpyDeviceToHost));
+    for (int ch = 0; ch < c->n; ++ch)
+        for (int e = 0; e < P.nEvents; ++e)
+            events[size_t(ch) * P.nEvents + e] = xb[size_t(ch) * P.xStride + c->p->xoff[e]];
+    return ABM_OK;
+}
+
+int abm_chains_get_statistics(abm_chains *c, int64_t *, int64_t *, int64_t *, int64_t *, int) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    return fail(ABM_ERR_STATE, "abm_chains_get_statistics: not implemented yet");
+}
+
+int abm_chains_reset_statistics(abm_chains *c) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    return ABM_OK;
+}
+
+}  // extern "C"

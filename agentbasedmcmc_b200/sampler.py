@@ -1,0 +1,212 @@
+"""Host-side mirror of the reference's sampler interface on top of the C-ABI.
+
+``SparseBasisSampler`` keeps the reference names (SparseBasisSampler.h:31-101): ``X``, ``delta``, ``currentDE``,
+``currentInfeasibility``, ``currentLogImportance``, ``stats``, ``nRows()``, ``nCols()``, ``__call__`` (= operator()),
+``findInitialFeasibleSolution`` -- but one object drives ``n_chains`` independent chains on one GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+from ._capi import AbmError, ProblemDesc, ProblemInfo, check
+
+
+def _ptr(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+class Problem:
+    """Shared read-only structure of a sampler (tableau, bounds, factor tables, importance tables) on one GPU.
+
+    Built from an ABMP dict (``abmp.read_abmp``), i.e. from what the reference's constructor reads out of its
+    ``TableauNormMinimiser`` + factor closures (SparseBasisSampler.h:107-158).
+    """
+
+    def __init__(self, abmp: dict, device: int = 0, with_importance: bool = True):
+        L = _capi.load()
+        self.abmp = abmp
+        self.device = device
+        k = {}
+        for name in ("tab_L", "tab_U", "tab_F", "nb_col", "nb_ptr", "nb_row", "nb_val", "fac_id", "ut_lo", "ut_off"):
+            k[name] = np.ascontiguousarray(abmp[name], dtype=np.int32)
+        for name in ("ut_val", "imp_lgamma", "imp_logratio"):
+            k[name] = np.ascontiguousarray(abmp.get(name, np.zeros(24)), dtype=np.float64)
+        d = ProblemDesc()
+        d.n_tab_rows, d.n_nonbasic = int(abmp["dims"][0]), int(abmp["dims"][3])
+        for name in ("tab_L", "tab_U", "tab_F", "nb_col", "nb_ptr", "nb_row", "nb_val", "fac_id", "ut_lo", "ut_off"):
+            setattr(d, name, _ptr(k[name], C.c_int32))
+        d.n_tables = k["ut_lo"].size
+        d.ut_val = _ptr(k["ut_val"], C.c_double)
+        d.kappa = float(abmp["kappa"][0])
+        use_imp = with_importance and "pp_meta" in abmp
+        d.grid_size = int(abmp["pp_meta"][0]) if use_imp else 0
+        d.n_timesteps = int(abmp["pp_meta"][1]) if use_imp else 0
+        d.imp_lgamma = _ptr(k["imp_lgamma"], C.c_double)
+        d.imp_logratio = _ptr(k["imp_logratio"], C.c_double)
+        h = C.c_void_p()
+        check(L.abm_problem_create(C.byref(d), device, C.byref(h)))
+        self.h = h
+        info = ProblemInfo()
+        check(L.abm_problem_get_info(self.h, C.byref(info)))
+        self.info = info
+        self.n_rows, self.n_cols, self.n_events = info.n_rows, info.n_cols, info.n_events
+        self.grid_size, self.n_timesteps = d.grid_size, d.n_timesteps
+        self.n_synopsis = L.abm_problem_n_synopsis(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            _capi.load().abm_problem_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+@dataclass
+class MCMCStatistics:
+    """MCMCStatistics (MCMCStatistics.h/.cpp), summed over the chains it was built from."""
+    nProposals: np.ndarray  # [2][2] indexed [startFeasible][proposalFeasible]
+    nAccepted: np.ndarray
+
+    def nSamples(self):
+        return int(self.nProposals.sum())
+
+    def totalAccepted(self):
+        return int(self.nAccepted.sum())
+
+    def nRejected(self, a, b):
+        return int(self.nProposals[a, b] - self.nAccepted[a, b])
+
+    def nInfeasibleSamples(self):  # MCMCStatistics.cpp:36-38
+        return int(self.nProposals[0, 0] + self.nAccepted[1, 0] + self.nRejected(0, 1))
+
+    def nFeasibleSamples(self):  # MCMCStatistics.cpp:40-42
+        return int(self.nProposals[1, 1] + self.nAccepted[0, 1] + self.nRejected(1, 0))
+
+
+class SparseBasisSampler:
+    """``n_chains`` SparseBasisSampler chains on one GPU (reference: one object == one chain)."""
+
+    def __init__(self, problem: Problem, initial_states=None, n_chains: int | None = None, seed: int = 0,
+                 first_chain_id: int = 0, stream=None, find_feasible: bool = True):
+        L = _capi.load()
+        self.problem = problem
+        if initial_states is not None:
+            initial_states = np.ascontiguousarray(initial_states, dtype=np.int8)
+            if initial_states.ndim == 1:
+                initial_states = initial_states[None, :]
+            if n_chains is None:
+                n_chains = initial_states.shape[0]
+            if initial_states.shape[0] != n_chains:
+                raise ValueError("initial_states must have one row per chain")
+        if n_chains is None:
+            n_chains = 1
+        self.n_chains = n_chains
+        h = C.c_void_p()
+        check(L.abm_chains_create(problem.h, n_chains, seed, first_chain_id, C.c_void_p(stream or 0), C.byref(h)))
+        self.h = h
+        n_init = 0 if initial_states is None else initial_states.shape[1]
+        check(L.abm_chains_init(self.h, _ptr(initial_states, C.c_int8), n_init))
+        self.init_iterations = None
+        if find_feasible:
+            self.findInitialFeasibleSolution()
+
+    def close(self):
+        if getattr(self, "h", None):
+            _capi.load().abm_chains_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def nRows(self):
+        return self.problem.n_rows
+
+    def nCols(self):
+        return self.problem.n_cols
+
+    # SparseBasisSampler.h:254-263 (+ :183-184)
+    def findInitialFeasibleSolution(self, max_iterations: int = 0, uniforms=None):
+        it = np.zeros(self.n_chains, np.int64)
+        n_u = 0
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(self.n_chains, -1)
+            n_u = uniforms.shape[1]
+        check(_capi.load().abm_chains_find_feasible(self.h, max_iterations, _ptr(uniforms, C.c_double), n_u,
+                                                    _ptr(it, C.c_int64)))
+        self.init_iterations = it
+        return it
+
+    def step(self, n_steps: int):
+        """n_steps Metropolis steps on every chain (asynchronous)."""
+        check(_capi.load().abm_chains_step(self.h, n_steps))
+
+    def step_traced(self, n_steps: int, uniforms=None, proposals=None):
+        """Steps with injected randomness; returns (j, accepted, proposalInfeasibility), each [n_chains][n_steps]."""
+        n = self.n_chains
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(n, 2 * n_steps)
+        if proposals is not None:
+            proposals = np.ascontiguousarray(proposals, dtype=np.int32).reshape(n, n_steps)
+        j = np.empty((n, n_steps), np.int32)
+        acc = np.empty((n, n_steps), np.uint8)
+        inf = np.empty((n, n_steps), np.int32)
+        check(_capi.load().abm_chains_step_traced(self.h, n_steps, _ptr(uniforms, C.c_double), _ptr(proposals, C.c_int32),
+                                                  _ptr(j, C.c_int32), _ptr(acc, C.c_uint8), _ptr(inf, C.c_int32)))
+        return j, acc, inf
+
+    def synchronize(self):
+        check(_capi.load().abm_chains_synchronize(self.h))
+
+    def state(self, chain: int = 0):
+        """(X, delta, currentDE, tree, currentLogImportance, currentInfeasibility) of one chain."""
+        P = self.problem
+        X = np.empty(P.n_rows, np.int32)
+        delta = np.empty(P.n_cols, np.int8)
+        DE = np.empty(P.n_cols, np.float64)
+        tree = np.empty(P.n_cols, np.float64)
+        li = C.c_double()
+        inf = C.c_int32()
+        check(_capi.load().abm_chains_get_state(self.h, chain, _ptr(X, C.c_int32), _ptr(delta, C.c_int8), _ptr(DE, C.c_double),
+                                                _ptr(tree, C.c_double), C.byref(li), C.byref(inf)))
+        return X, delta, DE, tree, li.value, inf.value
+
+    @property
+    def X(self):
+        return self.state(0)[0]
+
+    def counters(self):
+        out = np.zeros((self.n_chains, 8), np.int64)
+        check(_capi.load().abm_chains_get_counters(self.h, _ptr(out, C.c_int64)))
+        return out
+
+    @property
+    def stats(self):
+        c = self.counters().sum(axis=0)
+        return MCMCStatistics(c[:4].reshape(2, 2), c[4:].reshape(2, 2))
+
+    def infeasibility(self):
+        out = np.zeros(self.n_chains, np.int32)
+        check(_capi.load().abm_chains_get_infeasibility(self.h, _ptr(out, C.c_int32)))
+        return out
+
+    def trajectories(self):
+        out = np.zeros((self.n_chains, self.problem.n_events), np.int8)
+        check(_capi.load().abm_chains_get_trajectories(self.h, _ptr(out, C.c_int8)))
+        return out
+
+
+def leaf_probabilities(tree: np.ndarray) -> np.ndarray:
+    """MutableCategoricalArray::get for every index (MutableCategoricalArray.h:78, .cpp:30-39): tree[i] minus the
+    descendant sum accumulated in the reference's order (offsets 1, 2, 4, ... while the offset bit of i is clear)."""
+    n = tree.size
+    idx = np.arange(n)
+    s = np.zeros(n)
+    off = 1
+    while off < n:
+        m = ((idx & (2 * off - 1)) == 0) & (idx + off < n)
+        s[m] = s[m] + tree[idx[m] + off]
+        off <<= 1
+    return tree - s

@@ -1,0 +1,152 @@
+/* abmcmc_b200.h -- C ABI of the B200-native SparseBasisSampler.
+ *
+ * The reference (danftang/AgentBasedMCMC) has no FFI: its seam is the C++ class
+ * SparseBasisSampler<T> (src/SparseBasisSampler.h:31-101).  This header is the C-ABI a drop-in for that
+ * class binds to; every entry point cites the reference interface it replaces.  A header-only C++
+ * adaptor with the reference's constructor signature lives in include/abmcmc_b200/gpu_sampler.hpp;
+ * INTEGRATION.md shows the binding.
+ *
+ * Conventions: opaque handles; every function returns 0 on success or a negative abm_status and sets
+ * a thread-local message readable through abm_last_error(); no exception crosses the boundary; host
+ * buffers are caller-owned and copied before the call returns; a handle is bound to one CUDA device
+ * and is not thread-safe (the reference is "one sampler per thread" too, FiguresForPaper.h:54-57).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with ABM_ERR_CUDA.
+ */
+#ifndef ABMCMC_B200_H
+#define ABMCMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABM_API __attribute__((visibility("default")))
+
+typedef enum {
+    ABM_OK = 0,
+    ABM_ERR_INVALID = -1,     /* bad argument / unsupported problem shape */
+    ABM_ERR_CUDA = -2,        /* CUDA runtime error or no device */
+    ABM_ERR_STATE = -3,       /* call sequence error (e.g. step before init) */
+    ABM_ERR_NOT_FEASIBLE = -4 /* feasibility search hit its iteration limit */
+} abm_status;
+
+typedef struct abm_problem abm_problem; /* shared read-only structure, replicated per device */
+typedef struct abm_chains abm_chains;   /* a batch of independent Markov chains on one device */
+
+/* Flat description of what SparseBasisSampler's constructor reads from its arguments
+ * (SparseBasisSampler.h:107-158): the tableau restricted to non-basic columns, bounds and constants
+ * per tableau row, the factor closures tabulated on the host, kappa, and -- for the importance
+ * function TrajectoryImportance<PredPreyAgent<G>> (TrajectoryImportance.h, agents/PredPreyAgent.h) --
+ * the two small tables it can ever add.  Array meanings equal the ABMP container
+ * (include/abmcmc_b200/abmp_io.hpp). */
+typedef struct {
+    int32_t n_tab_rows;      /* tableau.rows.size(): one row per constraint, equalities included   */
+    int32_t n_nonbasic;      /* tableau.nNonBasic(): the sampler's columns                        */
+    const int32_t *tab_L;    /* [n_tab_rows] tableau.L (INT32_MIN = unbounded)                     */
+    const int32_t *tab_U;    /* [n_tab_rows] tableau.U (INT32_MAX = unbounded); L==U <=> equality  */
+    const int32_t *tab_F;    /* [n_tab_rows] tableau.F                                            */
+    const int32_t *nb_col;   /* [n_nonbasic] tableau column (= variable / event id) of each column */
+    const int32_t *nb_ptr;   /* [n_nonbasic+1] CSR pointer into nb_row / nb_val                    */
+    const int32_t *nb_row;   /* [nnz] tableau row index, ascending inside a column                */
+    const int32_t *nb_val;   /* [nnz] integer entry M_ij                                          */
+    const int32_t *fac_id;   /* [n_rows] factor table of each sampler row (non-equality rows, in order) */
+    int32_t n_tables;
+    const int32_t *ut_lo;    /* [n_tables] first tabulated argument                               */
+    const int32_t *ut_off;   /* [n_tables+1] offsets into ut_val                                  */
+    const double *ut_val;    /* factor values f(x), x = lo .. lo+len-1 (clamp of reachable range) */
+    double kappa;            /* SparseBasisSampler::kappa (:33)                                   */
+    int32_t grid_size;       /* PredPrey GRIDSIZE; 0 = no importance function (log W == 0)        */
+    int32_t n_timesteps;
+    const double *imp_lgamma;   /* [7]  lgamma(occ+1) for occ>1 else 0 (TrajectoryImportance.h:96) */
+    const double *imp_logratio; /* [2][2][6] log(pi/pibar) by type, has-neighbour flag, act (:105) */
+} abm_problem_desc;
+
+typedef struct {
+    int32_t n_rows, n_cols, nnz, n_events;
+    int32_t max_col_nnz, max_coupled; /* longest column; most columns sharing a row with one column */
+    int32_t tree_depth;               /* bit length of n_cols-1 (MutableCategoricalArray.cpp:41-48) */
+    int32_t n_states;                 /* T * 2 * G * G (0 without importance)                    */
+    int64_t chain_state_bytes;        /* HBM bytes of one chain                                   */
+    int64_t shared_bytes;             /* HBM bytes of the shared structure                        */
+} abm_problem_info;
+
+/* Per-chain Metropolis counters: MCMCStatistics::nProposals / nAccepted (MCMCStatistics.h:14-15),
+ * index [startFeasible][proposalFeasible], widened to 64 bit. */
+typedef struct {
+    int64_t n_proposals[2][2];
+    int64_t n_accepted[2][2];
+} abm_mcmc_counters;
+
+ABM_API const char *abm_last_error(void);
+ABM_API int abm_version(void);
+ABM_API int abm_device_count(void); /* 0 when no CUDA device is usable */
+
+/* ---- problem: replaces the tableau-copy half of SparseBasisSampler::SparseBasisSampler (:121-158) */
+ABM_API int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **out);
+ABM_API int abm_problem_destroy(abm_problem *p);
+ABM_API int abm_problem_get_info(const abm_problem *p, abm_problem_info *info);
+
+/* ---- chains: n_chains independent samplers; chain c draws from the Philox4x32-10 stream keyed by
+ * (seed, first_chain_id + c).  stream = a cudaStream_t (NULL = default stream). */
+ABM_API int abm_chains_create(const abm_problem *p, int32_t n_chains, uint64_t seed, uint64_t first_chain_id,
+                              void *stream, abm_chains **out);
+ABM_API int abm_chains_destroy(abm_chains *c);
+
+/* The state-initialising half of the constructor (:144-178): delta from the initial trajectory
+ * (init_events[c][e] > 0  =>  delta = -1), X = F + M.[delta==-1], currentDE, basisDistribution == 1.
+ * init_events: host, [n_chains][n_init] int8 (n_init may be 0: all delta = +1). */
+ABM_API int abm_chains_init(abm_chains *c, const int8_t *init_events, int32_t n_init);
+
+/* findInitialFeasibleSolution (:254-263) + importanceFunc->setState / getLogValue (:183-184).
+ * Uniforms: Philox unless `uniforms` (host, [n_chains][n_uniforms], one per iteration) is given.
+ * iterations_out (host, [n_chains], may be NULL) receives the per-chain iteration count. */
+ABM_API int abm_chains_find_feasible(abm_chains *c, int64_t max_iterations, const double *uniforms,
+                                     int64_t n_uniforms, int64_t *iterations_out);
+
+/* n_steps iterations of the do-loop of nextSampleWithInfeasibleImportance (:221-246) on every chain
+ * (feasible or not: one step == one MCMCStatistics::addSample).  Asynchronous on the chains' stream. */
+ABM_API int abm_chains_step(abm_chains *c, int64_t n_steps);
+
+/* Same, with the random inputs injected and the decisions returned, for parity testing:
+ *   uniforms  host [n_chains][2*n_steps]  (u1 = column draw, u2 = accept draw), or NULL for Philox
+ *   proposals host [n_chains][n_steps] column indices replacing the sum-tree draw, or NULL
+ *   out_j / out_accepted / out_infeasibility  host [n_chains][n_steps], each may be NULL
+ * (out_infeasibility is Proposal::infeasibility, :303).  Synchronous. */
+ABM_API int abm_chains_step_traced(abm_chains *c, int64_t n_steps, const double *uniforms, const int32_t *proposals,
+                                   int32_t *out_j, uint8_t *out_accepted, int32_t *out_infeasibility);
+
+/* operator() (:212-214) for every chain: step until n_samples further feasible states were visited
+ * (a feasible state is a sample each time the loop condition :247 sees infeasibility == 0), accumulating
+ * the ensemble statistics below after each one.  max_steps bounds the work per chain. */
+ABM_API int abm_chains_sample(abm_chains *c, int64_t n_samples, int64_t max_steps);
+
+ABM_API int abm_chains_synchronize(abm_chains *c);
+
+/* ---- state read-back (public members X, delta, currentDE, basisDistribution, currentInfeasibility,
+ * currentLogImportance, stats; SparseBasisSampler.h:44-54).  Any pointer may be NULL.
+ * tree = the raw sum-tree nodes in the reference's index order (MutableCategoricalArray.h:38). */
+ABM_API int abm_chains_get_state(abm_chains *c, int32_t chain, int32_t *X, int8_t *delta, double *currentDE,
+                                 double *tree, double *log_importance, int32_t *infeasibility);
+ABM_API int abm_chains_get_counters(abm_chains *c, abm_mcmc_counters *per_chain /* [n_chains] */);
+ABM_API int abm_chains_get_infeasibility(abm_chains *c, int32_t *per_chain /* [n_chains] */);
+/* Event trajectories (the first n_events entries of X, Trajectory.h:27-29) of all chains, int8,
+ * host [n_chains][n_events]. */
+ABM_API int abm_chains_get_trajectories(abm_chains *c, int8_t *events);
+
+/* ---- ensemble statistics (FiguresForPaper.h:93-104,245-263; diagnostics/MeanAndVariance.h:35-45)
+ * accumulated on the device by abm_chains_sample:
+ *   end_state_sum [n_agent_states]  sum over chains and samples of ModelState(traj,T,T) occupancies
+ *   syn_sum / syn_sumsq [n_chains][n_synopsis]  per-chain sums of the synopsis statistics
+ *   n_samples [n_chains]
+ * All are int64 (exact).  Pointers are HOST buffers unless device_ptrs != 0 (then device buffers on the
+ * chains' device, so a caller can hand them to an NCCL all-reduce without a host round trip). */
+ABM_API int abm_chains_get_statistics(abm_chains *c, int64_t *end_state_sum, int64_t *syn_sum, int64_t *syn_sumsq,
+                                      int64_t *n_samples, int device_ptrs);
+ABM_API int abm_chains_reset_statistics(abm_chains *c);
+ABM_API int abm_problem_n_synopsis(const abm_problem *p); /* floor(log2(G)) - 1 (FiguresForPaper.h:246) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABMCMC_B200_H */

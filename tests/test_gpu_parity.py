@@ -1,0 +1,128 @@
+"""GPU parity: the CUDA sampler (through the C-ABI) against the oracle and the reference's golden traces.
+
+Contract (BASELINE.json north_star): integer trajectory updates and accept decisions bit-exact under the same
+uniform / proposal streams; doubles (currentDE, sum-tree, log importance) within 1e-9 relative -- they differ from
+the host only through exp() (CUDA libdevice vs glibc, <= 1 ulp each)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _gpu():
+    from agentbasedmcmc_b200 import sampler
+    return sampler
+
+
+def _close(a, b, rtol=RTOL, atol=1e-12):
+    return np.allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("prob,trace,n_steps", [("pp8-4.abmp.xz", "trace_pp8-4_101.abmp.xz", 20000),
+                                                ("pp8-4.abmp.xz", "trace_pp8-4_102.abmp.xz", 20000),
+                                                ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz", 20000)])
+def test_reference_golden_trace(prob, trace, n_steps):
+    """Same mt19937 uniform stream as the reference run -> same columns, decisions, infeasibilities and X."""
+    from oracle.oracle import mt_uniforms
+    S = _gpu()
+    p, t = load_golden(prob), load_golden(trace)
+    n_init = int(t["init_iters"][0])
+    u = mt_uniforms(int(t["seeds"][1]), n_init + 2 * n_steps)
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, t["init_state"], find_feasible=False)
+    it = smp.findInitialFeasibleSolution(uniforms=u[:n_init + 8].copy() if n_init + 8 <= u.size else u)
+    assert int(it[0]) == n_init
+    X, delta, DE, tree, logimp, inf = smp.state(0)
+    assert inf == 0
+    assert np.array_equal(X, t["X0"])
+    assert np.array_equal(delta, t["delta0"])
+    assert _close(DE, t["DE0"])
+    # get(u) is a difference of O(tree[0]) sums: compare with an absolute tolerance scaled by the root
+    assert _close(S.leaf_probabilities(tree), t["leaf0"], atol=1e-13 * tree[0])
+    assert _close([tree[0], logimp], t["scal0"])
+    j, acc, pinf = smp.step_traced(n_steps, uniforms=u[n_init:n_init + 2 * n_steps])
+    assert np.array_equal(j[0], t["tr_j"][:n_steps])
+    assert np.array_equal(acc[0], t["tr_acc"][:n_steps])
+    assert np.array_equal(pinf[0], t["tr_inf"][:n_steps])
+    X, delta, DE, tree, logimp, inf = smp.state(0)
+    assert np.array_equal(X, t["XN"])
+    assert np.array_equal(delta, t["deltaN"])
+    assert _close(DE, t["DEN"])
+    assert _close(S.leaf_probabilities(tree), t["leafN"], atol=1e-13 * tree[0])
+    assert _close([tree[0], logimp], t["scalN"])
+    c = smp.counters()[0]
+    assert np.array_equal(c, t["counters"])
+
+
+@pytest.mark.parametrize("prob,n_chains,n_steps", [("pp8-4.abmp.xz", 16, 4000), ("pp16-8.abmp.xz", 6, 3000)])
+def test_philox_free_running_matches_oracle(prob, n_chains, n_steps):
+    """Free-running mode: device Philox4x32-10 streams keyed by (seed, chain) == the oracle's; many chains per launch."""
+    from oracle.oracle import OracleChain, OracleProblem
+    S = _gpu()
+    p = load_golden(prob)
+    rng = np.random.default_rng(5)
+    n_events = int(p["pp_meta"][2])
+    init = (rng.random((n_chains, n_events)) < 0.02).astype(np.int8)
+    seed, first = 0xABCDEF12345, 1000
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, init, seed=seed, first_chain_id=first)
+    OP = OracleProblem(p)
+    j, acc, pinf = smp.step_traced(n_steps)
+    ctr = smp.counters()
+    for c in range(n_chains):
+        oc = OracleChain(OP, init[c])
+        oc.seed_philox(seed, first + c)
+        assert oc.find_feasible() == int(smp.init_iterations[c])
+        oj, oacc, oinf = oc.step(n_steps, trace=True)
+        assert np.array_equal(j[c], oj) and np.array_equal(acc[c], oacc) and np.array_equal(pinf[c], oinf)
+        X, delta, DE, tree, logimp, inf = smp.state(c)
+        assert np.array_equal(X, oc.X) and np.array_equal(delta, oc.delta) and inf == oc.infeasibility
+        assert _close(DE, oc.DE) and _close(tree, oc.tree) and _close(logimp, oc.log_importance)
+        assert np.array_equal(ctr[c], oc.counters)
+
+
+def test_injected_proposals_replay():
+    """replay mode: column stream and accept uniforms injected."""
+    from oracle.oracle import OracleChain, OracleProblem
+    S = _gpu()
+    p = load_golden("pp8-4.abmp.xz")
+    rng = np.random.default_rng(9)
+    n_steps, n_chains = 3000, 4
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=3)
+    OP = OracleProblem(p)
+    props = rng.integers(0, P.n_cols, size=(n_chains, n_steps), dtype=np.int32)
+    u = rng.random((n_chains, 2 * n_steps))
+    j, acc, pinf = smp.step_traced(n_steps, uniforms=u, proposals=props)
+    assert np.array_equal(j, props)
+    for c in range(n_chains):
+        oc = OracleChain(OP)
+        oc.seed_philox(3, c)
+        oc.find_feasible()
+        oc.set_injected(u[c], proposals=props[c])
+        oj, oacc, oinf = oc.step(n_steps, trace=True)
+        assert np.array_equal(acc[c], oacc) and np.array_equal(pinf[c], oinf)
+        assert np.array_equal(smp.state(c)[0], oc.X)
+
+
+def test_async_step_matches_traced_step():
+    """abm_chains_step (no trace, async) advances the chains exactly like the traced entry point."""
+    S = _gpu()
+    p = load_golden("pp8-4.abmp.xz")
+    P = S.Problem(p)
+    a = S.SparseBasisSampler(P, n_chains=8, seed=77)
+    b = S.SparseBasisSampler(P, n_chains=8, seed=77)
+    a.step(1500)
+    a.step(500)
+    a.synchronize()
+    b.step_traced(2000)
+    for c in range(8):
+        sa, sb = a.state(c), b.state(c)
+        assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
+        assert np.array_equal(sa[2], sb[2]) and np.array_equal(sa[3], sb[3]) and sa[4] == sb[4]
+    assert np.array_equal(a.counters(), b.counters())
+    assert a.stats.nSamples() == 8 * 2000
