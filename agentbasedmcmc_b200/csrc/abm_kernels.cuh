@@ -163,7 +163,7 @@ __device__ __forceinline__ int warpSumInt(int v) {
 // (SparseBasisSampler.h:221-246).  MODE_INIT: findInitialFeasibleSolution (:254-263): same proposal,
 // always applied, no importance, no statistics, until the chain is feasible.
 template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) stepKernel(DevProblem P, DevChains S, RunParams R) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P, DevChains S, RunParams R) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chain = blockIdx.x * kWarpsPerCta + warp;

@@ -384,6 +384,59 @@ int cmdTime(const AbmpFile &f, int nThreads, long nSamples, double maxSeconds) {
     return 0;
 }
 
+
+// bench.py --impl reference: nThreads persistent reference samplers (one chain per host thread, as
+// FiguresForPaper.h:54-57), advanced in `warmup + steps` rounds of `samplesPerStep` calls of sampler() each.
+// Prints one JSON object with the wall time and Metropolis-step count of every timed round.
+template <int G>
+int cmdBench(const AbmpFile &f, int nThreads, long samplesPerStep, int warmup, int steps) {
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    Random::gen.seed(4321);
+    std::vector<std::vector<occ_t>> inits;
+    for (int t = 0; t < nThreads; ++t) inits.push_back(priorSample<G>(problem));
+    std::vector<std::unique_ptr<SparseBasisSampler<occ_t>>> samplers(nThreads);
+    std::vector<std::mt19937> gens(nThreads);
+    auto c0 = std::chrono::steady_clock::now();
+    {
+        SilenceStdout quiet;
+        std::vector<std::future<void>> fut;
+        for (int t = 0; t < nThreads; ++t)
+            fut.push_back(std::async(std::launch::async, [&, t]() {
+                Random::gen.seed(1000 + t);
+                samplers[t].reset(new SparseBasisSampler<occ_t>(problem.tableau, problem.posterior.factors,
+                                                                problem.posterior.perturbableFunctionFactory(), inits[t], problem.kappa));
+                gens[t] = Random::gen;
+            }));
+        for (auto &x : fut) x.wait();
+    }
+    double setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
+    std::vector<double> secs;
+    std::vector<long> stepCounts;
+    for (int r = 0; r < warmup + steps; ++r) {
+        long before = 0;
+        for (auto &s : samplers) before += s->stats.nSamples();
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::future<void>> fut;
+        for (int t = 0; t < nThreads; ++t)
+            fut.push_back(std::async(std::launch::async, [&, t]() {
+                Random::gen = gens[t];
+                for (long k = 0; k < samplesPerStep; ++k) (*samplers[t])();
+                gens[t] = Random::gen;
+            }));
+        for (auto &x : fut) x.wait();
+        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        long after = 0;
+        for (auto &s : samplers) after += s->stats.nSamples();
+        if (r >= warmup) { secs.push_back(dt); stepCounts.push_back(after - before); }
+    }
+    printf("{\"impl\": \"reference\", \"grid\": %d, \"threads\": %d, \"samples_per_step\": %ld, \"setup_seconds\": %.3f, \"step_seconds\": [", G, nThreads, samplesPerStep, setup);
+    for (size_t k = 0; k < secs.size(); ++k) printf("%s%.6f", k ? ", " : "", secs[k]);
+    printf("], \"chain_steps\": [");
+    for (size_t k = 0; k < stepCounts.size(); ++k) printf("%s%ld", k ? ", " : "", stepCounts[k]);
+    printf("]}\n");
+    return 0;
+}
+
 // Long reference chains for posterior marginals: per thread one chain, `burnin` + nSamples calls of
 // sampler(); accumulates the end-state occupancy (ModelState(traj,T,T), ModelState.h:27-36) and the
 // whole-trajectory event marginals.  Output: ABMP with endstate_sum i64-as-f64[S], event_sum f64[nEvents],
@@ -464,6 +517,7 @@ static int run(int argc, char **argv) {
                 "  abm_ref trace in.abmp initSeed chainSeed nSteps checkpointEvery out.abmp\n"
                 "  abm_ref selfcheck in.abmp nSamples\n"
                 "  abm_ref time in.abmp nThreads nSamplesPerThread [maxSeconds]\n"
+                "  abm_ref bench in.abmp nThreads samplesPerStep warmup steps\n"
                 "  abm_ref marginals in.abmp nThreads nSamples burnin out.abmp\n");
         return 2;
     }
@@ -482,6 +536,7 @@ static int run(int argc, char **argv) {
     if (cmd == "trace") { DISPATCH_G(g, cmdTrace<G>(f, atoi(argv[3]), atoi(argv[4]), atol(argv[5]), atoi(argv[6]), argv[7])); }
     if (cmd == "selfcheck") { DISPATCH_G(g, cmdSelfcheck<G>(f, atoi(argv[3]))); }
     if (cmd == "time") { DISPATCH_G(g, cmdTime<G>(f, atoi(argv[3]), atol(argv[4]), argc > 5 ? atof(argv[5]) : 0.0)); }
+    if (cmd == "bench") { DISPATCH_G(g, cmdBench<G>(f, atoi(argv[3]), atol(argv[4]), atoi(argv[5]), atoi(argv[6]))); }
     if (cmd == "marginals") { DISPATCH_G(g, cmdMarginals<G>(f, atoi(argv[3]), atol(argv[4]), atol(argv[5]), argv[6])); }
     fprintf(stderr, "unknown command %s\n", cmd.c_str());
     return 2;
