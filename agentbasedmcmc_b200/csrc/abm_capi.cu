@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -125,7 +126,9 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
             if (k > colPtr[j] && colRow[k - 1] >= r) return fail(ABM_ERR_INVALID, "column entries must be ascending by row");
             colRow[k] = r;
             colVal[k] = desc->nb_val[k];
-            if (colVal[k] < -127 || colVal[k] > 127 || colVal[k] == 0) return fail(ABM_ERR_INVALID, "tableau entry out of int8 range");
+            // PredPrey bases have unit entries only; the kernels tabulate the two possible
+            // one-step moves of a row per proposal, so anything else is rejected rather than mis-sampled
+            if (colVal[k] != 1 && colVal[k] != -1) return fail(ABM_ERR_INVALID, "only tableau entries of +-1 are supported");
             rowPtr[r + 1]++;
             (colVal[k] < 0 ? xmin[r] : xmax[r]) += colVal[k];
         }
@@ -168,46 +171,77 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         ++b;
     }
 
-    // column records
+    // lanes per chain: the records are laid out for it (chunks of W coupled columns)
+    int W = 8;
+    if (const char *e = getenv("ABM_GROUP_WIDTH")) W = atoi(e);
+    if (W != 8 && W != 16 && W != 32) return fail(ABM_ERR_INVALID, "ABM_GROUP_WIDTH must be 8, 16 or 32");
+
+    // column records (layout: abm_device.h)
     std::vector<uint32_t> recOff(nCols + 1);
     std::vector<int32_t> rec;
     rec.reserve((size_t)nnz * 24);
-    int maxCoupled = 1;
+    int maxCoupled = 1, maxTasks = 1, maxSF = 0;
     struct Pair { int u, k, m; };
     std::vector<Pair> pairs;
-    std::vector<int32_t> pu;
-    std::vector<int16_t> pkm;
-    std::vector<int32_t> staleF;
+    std::vector<int32_t> slotU, chunkHdr, staleF, nodes;
+    std::vector<uint16_t> contrib;
     std::vector<char> seen(std::max(nStates, 1), 0);
     for (int j = 0; j < nCols; ++j) {
         while (rec.size() % 4) rec.push_back(0);
         recOff[j] = uint32_t(rec.size() / 4);
         const int n = colPtr[j + 1] - colPtr[j];
         pairs.clear();
-        pairs.push_back({j, kSelfMarker, 0});
+        pairs.push_back({j, -1, 0});   // the proposed column itself (changedDE[j] = -currentDE[j], :294)
         for (int k = 0; k < n; ++k) {
             const int i = colRow[colPtr[j] + k];
             for (int r = rowPtr[i]; r < rowPtr[i + 1]; ++r)
                 if (rowCol[r] != j) pairs.push_back({rowCol[r], k, rowVal[r]});
         }
         std::stable_sort(pairs.begin(), pairs.end(), [](const Pair &a, const Pair &b) { return a.u < b.u || (a.u == b.u && a.k < b.k); });
-        pu.clear();
-        pkm.clear();
-        int C = 0;
-        for (size_t a = 0; a < pairs.size();) {
-            size_t b = a;
-            while (b < pairs.size() && pairs[b].u == pairs[a].u) ++b;
-            const int run = int(b - a);
-            if (int(pu.size() % 32) + run > 32)
-                while (pu.size() % 32) { pu.push_back(-1); pkm.push_back(0); }
-            for (size_t q = a; q < b; ++q) {
-                pu.push_back(pairs[q].u);
-                pkm.push_back(int16_t((pairs[q].k & 0xff) | (pairs[q].m << 8)));
-            }
-            ++C;
-            a = b;
+        // distinct columns ascending, each with its shared rows in row order
+        slotU.clear();
+        std::vector<std::pair<size_t, size_t>> runs;
+        for (size_t a2 = 0; a2 < pairs.size();) {
+            size_t b2 = a2;
+            while (b2 < pairs.size() && pairs[b2].u == pairs[a2].u) ++b2;
+            slotU.push_back(pairs[a2].u);
+            runs.push_back({a2, b2});
+            a2 = b2;
         }
+        const int C = int(slotU.size());
+        const int nChunks = (C + W - 1) / W;
         maxCoupled = std::max(maxCoupled, C);
+        slotU.resize(size_t(nChunks) * W, -1);
+        chunkHdr.assign(nChunks, 0);
+        contrib.clear();
+        for (int c = 0; c < nChunks; ++c) {
+            int maxCnt = 0;
+            for (int q = 0; q < W; ++q) {
+                const int l = c * W + q;
+                if (l < C && pairs[runs[l].first].k >= 0) maxCnt = std::max(maxCnt, int(runs[l].second - runs[l].first));
+            }
+            if (contrib.size() >= (1u << 23)) return fail(ABM_ERR_INVALID, "contribution table of a column too large");
+            chunkHdr[c] = maxCnt | int32_t(contrib.size() << 8);
+            for (int t = 0; t < maxCnt; ++t)
+                for (int q = 0; q < W; ++q) {
+                    const int l = c * W + q;
+                    uint16_t v = kNoContrib;
+                    if (l < C && pairs[runs[l].first].k >= 0 && t < int(runs[l].second - runs[l].first)) {
+                        const Pair &pr = pairs[runs[l].first + t];
+                        v = uint16_t((pr.k & 0xff) | ((pr.m & 0xff) << 8));
+                    }
+                    contrib.push_back(v);
+                }
+        }
+        // distinct tree nodes a commit of this column touches (sizes the task list)
+        nodes.clear();
+        for (int l = 0; l < C; ++l) {
+            int a2 = slotU[l];
+            nodes.push_back(a2);
+            while (a2) { a2 &= a2 - 1; nodes.push_back(a2); }
+        }
+        std::sort(nodes.begin(), nodes.end());
+        maxTasks = std::max(maxTasks, int(std::unique(nodes.begin(), nodes.end()) - nodes.begin()));
         // stale factors in TrajectoryImportance::perturb insertion order (TrajectoryImportance.h:41-53)
         staleF.clear();
         if (G > 0) {
@@ -226,10 +260,15 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
             }
             for (int sid : staleF) seen[sid] = 0;
         }
-        rec.push_back(n);
-        rec.push_back(int32_t(pu.size()));
-        rec.push_back(C);
-        rec.push_back(int32_t(staleF.size()));
+        if (staleF.size() > 255) return fail(ABM_ERR_INVALID, "too many stale factors for one column");
+        maxSF = std::max(maxSF, int(staleF.size()));
+        const size_t base = rec.size();
+        const size_t contribWord = 4 + size_t(4) * n + nChunks + slotU.size();
+        const size_t staleWord = contribWord + (contrib.size() + 1) / 2;
+        rec.push_back(n | (int32_t(staleF.size()) << 8) | (C << 16));
+        rec.push_back(nChunks);
+        rec.push_back(int32_t(contribWord));
+        rec.push_back(int32_t(staleWord));
         for (int k = 0; k < n; ++k) {
             const int i = colRow[colPtr[j] + k];
             const int4 rp = rowParam[i];
@@ -238,17 +277,19 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
             rec.push_back(rp.z);
             rec.push_back(rp.w);
         }
-        rec.insert(rec.end(), pu.begin(), pu.end());
-        for (size_t q = 0; q < pkm.size(); q += 2) {
-            const uint32_t lo16 = uint16_t(pkm[q]), hi16 = q + 1 < pkm.size() ? uint16_t(pkm[q + 1]) : 0;
+        rec.insert(rec.end(), chunkHdr.begin(), chunkHdr.end());
+        rec.insert(rec.end(), slotU.begin(), slotU.end());
+        for (size_t q = 0; q < contrib.size(); q += 2) {
+            const uint32_t lo16 = contrib[q], hi16 = q + 1 < contrib.size() ? contrib[q + 1] : 0;
             rec.push_back(int32_t(lo16 | (hi16 << 16)));
         }
         rec.insert(rec.end(), staleF.begin(), staleF.end());
+        if (rec.size() - base != staleWord + staleF.size()) return fail(ABM_ERR_INVALID, "internal: record layout");
         if (rec.size() / 4 > 0xfffffff0ull) return fail(ABM_ERR_INVALID, "record table too large");
     }
     while (rec.size() % 4) rec.push_back(0);
     recOff[nCols] = uint32_t(rec.size() / 4);
-    if (maxCoupled > 2047) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2047 others");
+    if (maxCoupled > 2040) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2040 others");
 
     std::vector<double> impTab(7 + 24, 0.0);
     if (G > 0) {
@@ -269,7 +310,10 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.t2Len = (nCols + 1023) / 1024;
     d.evBytes = evBytes;
     d.G = G; d.S = S; d.T = T; d.nStates = nStates;
-    d.maxCoupled = maxCoupled;
+    d.groupWidth = W;
+    d.rowsCap = (maxColNnz + 7) & ~7;
+    d.sCap = (maxCoupled + 7) & ~7;
+    d.tCap = (maxTasks + 7) & ~7;
     int nSyn = 0;
     for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
     d.nSynopsis = nSyn;
@@ -288,7 +332,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     abm_problem_info &inf = p->info;
     inf.n_rows = nRows; inf.n_cols = nCols; inf.nnz = nnz; inf.n_events = nEvents;
     inf.max_col_nnz = maxColNnz; inf.max_coupled = maxCoupled; inf.tree_depth = depth; inf.n_states = nStates;
-    inf.chain_state_bytes = int64_t(xStride) + int64_t(nCols) * 17 + int64_t(d.t1Len + d.t2Len) * 8;
+    inf.chain_state_bytes = int64_t(xStride) + int64_t(nCols) * 17 + int64_t(d.t1Len + d.t2Len) * 8 + int64_t(d.sCap) * 16;
     inf.shared_bytes = int64_t(p->arena.bytes);
     *out = p;
     return ABM_OK;
@@ -325,13 +369,12 @@ int abm_chains_create(const abm_problem *p, int32_t nChains, uint64_t seed, uint
     DevChains &d = c->d;
     d.nChains = nChains;
     const size_t n = size_t(nChains);
-    const int scrCap = std::max(P.maxCoupled - kSCap, 0);
     cudaError_t e = cudaSuccess;
     auto al = [&](auto **dst, size_t count) { if (e == cudaSuccess) e = c->arena.alloc(dst, count); };
     al(&d.Xb, n * P.xStride); al(&d.colRec, n * P.nCols); al(&d.delta, n * P.nCols);
     al(&d.tier1, n * P.t1Len); al(&d.tier2, n * P.t2Len);
     al(&d.logImp, n); al(&d.infeas, n); al(&d.iter, n); al(&d.counters, n * 8);
-    al(&d.scrU, n * scrCap); al(&d.scrD, n * scrCap * 3); al(&d.scrTask, n * 32 * 32);
+    al(&d.scratch, n * P.sCap);
     al(&d.endStateSum, size_t(std::max(P.S, 1))); al(&d.synSum, n * std::max(P.nSynopsis, 1));
     al(&d.synSumSq, n * std::max(P.nSynopsis, 1)); al(&d.nSamples, n);
     if (e != cudaSuccess) {
@@ -388,7 +431,31 @@ int abm_chains_init(abm_chains *c, const int8_t *initEvents, int32_t nInit) {
     return ABM_OK;
 }
 
-static size_t stepSmemBytes() { return size_t(kWarpsPerCta) * (kSCap * 4 + 3 * kSCap * 8 + kTCap * 2); }
+}  // extern "C" (templates below need C++ linkage)
+
+template <int MODE, int W>
+static cudaError_t launchStepW(const abm_chains *c, const RunParams &r) {
+    const DevProblem &P = c->p->d;
+    constexpr int NG = 32 / W;
+    const int chainsPerCta = kWarpsPerCta * NG;
+    const int grid = (c->n + chainsPerCta - 1) / chainsPerCta;
+    const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap);
+    cudaError_t e = cudaFuncSetAttribute(stepKernel<MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    stepKernel<MODE, W><<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launchStep(const abm_chains *c, const RunParams &r) {
+    switch (c->p->d.groupWidth) {
+        case 8: return launchStepW<MODE, 8>(c, r);
+        case 16: return launchStepW<MODE, 16>(c, r);
+        default: return launchStepW<MODE, 32>(c, r);
+    }
+}
+
+extern "C" {
 
 static RunParams baseParams(const abm_chains *c) {
     RunParams r{};
@@ -414,7 +481,6 @@ int abm_chains_find_feasible(abm_chains *c, int64_t maxIterations, const double 
         CUDA_TRY(cudaMemcpyAsync(dU, uniforms, n * nUniforms * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         maxIterations = std::min<int64_t>(maxIterations, nUniforms);
     }
-    const int grid = (c->n + kWarpsPerCta - 1) / kWarpsPerCta;
     std::vector<int32_t> inf(n);
     int64_t done = 0;
     bool allFeasible = false;
@@ -426,8 +492,7 @@ int abm_chains_find_feasible(abm_chains *c, int64_t maxIterations, const double 
         r.uStride = nUniforms;
         r.uOffset = done;   // valid because with injected uniforms all chains advance in lock step per launch
         r.itersOut = dIters;
-        stepKernel<MODE_INIT><<<grid, kWarpsPerCta * 32, stepSmemBytes(), c->stream>>>(P, c->d, r);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launchStep<MODE_INIT>(c, r));
         CUDA_TRY(cudaMemcpyAsync(inf.data(), c->d.infeas, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         done += chunk;
@@ -442,7 +507,7 @@ int abm_chains_find_feasible(abm_chains *c, int64_t maxIterations, const double 
     CUDA_TRY(cudaFree(dIters));
     if (dU) CUDA_TRY(cudaFree(dU));
     if (!allFeasible) return fail(ABM_ERR_NOT_FEASIBLE, "feasibility search hit its iteration limit");
-    setStateKernel<<<grid, kWarpsPerCta * 32, 0, c->stream>>>(P, c->d);
+    setStateKernel<<<(c->n + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, c->stream>>>(P, c->d);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->feasible = true;
@@ -455,9 +520,7 @@ int abm_chains_step(abm_chains *c, int64_t nSteps) {
     CUDA_TRY(cudaSetDevice(c->p->device));
     RunParams r = baseParams(c);
     r.nSteps = nSteps;
-    const int grid = (c->n + kWarpsPerCta - 1) / kWarpsPerCta;
-    stepKernel<MODE_MCMC><<<grid, kWarpsPerCta * 32, stepSmemBytes(), c->stream>>>(c->p->d, c->d, r);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launchStep<MODE_MCMC>(c, r));
     return ABM_OK;
 }
 
@@ -488,9 +551,7 @@ int abm_chains_step_traced(abm_chains *c, int64_t nSteps, const double *uniforms
     CUDA_TRY(tmp.alloc(&dOutAcc, n * ns));
     CUDA_TRY(tmp.alloc(&dOutInf, n * ns));
     r.outJ = dOutJ; r.outAcc = dOutAcc; r.outInf = dOutInf;
-    const int grid = (c->n + kWarpsPerCta - 1) / kWarpsPerCta;
-    stepKernel<MODE_MCMC><<<grid, kWarpsPerCta * 32, stepSmemBytes(), c->stream>>>(c->p->d, c->d, r);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launchStep<MODE_MCMC>(c, r));
     if (outJ) CUDA_TRY(cudaMemcpyAsync(outJ, dOutJ, n * ns * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     if (outAcc) CUDA_TRY(cudaMemcpyAsync(outAcc, dOutAcc, n * ns, cudaMemcpyDeviceToHost, c->stream));
     if (outInf) CUDA_TRY(cudaMemcpyAsync(outInf, dOutInf, n * ns * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

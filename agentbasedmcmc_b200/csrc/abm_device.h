@@ -1,11 +1,12 @@
 // Device-side data layout of the B200 sampler (shared between the host builder and the kernels).
 //
 // Shared, read-only, replicated per GPU ("problem"):
-//   * one packed RECORD per basis column j (the CSR column, the rows' bounds and factor tables, and the
-//     pre-joined list of (coupled column u, row k) pairs that Proposal::Proposal discovers by walking
-//     rows[i] for every i in cols[j], SparseBasisSampler.h:297-313).  The join is static, so it is done
-//     once on the host; the kernel streams a record with coalesced loads instead of chasing
-//     colPtr -> rowIdx -> rowPtr -> colIdx.
+//   * one packed RECORD per basis column j: the CSR column with each row's bounds and factor table, and the
+//     pre-joined list of the columns u coupled to j through a shared row together with the rows they share.
+//     Proposal::Proposal discovers that list at run time by walking rows[i] for every i in cols[j]
+//     (SparseBasisSampler.h:297-313) and accumulates into a std::map; the join is static, so the host does it
+//     once and the kernel streams one record with coalesced loads instead of chasing
+//     colPtr -> rowIdx -> rowPtr -> colIdx and inserting into a tree.
 // Per chain, mutable, chain-contiguous in HBM:
 //   * Xb     int8   [xStride]   X (SparseBasisSampler.h:44); event rows padded to 8 bytes per agent
 //                               state so one aligned 64-bit load yields all 6 act counts of a state
@@ -23,21 +24,27 @@ namespace abm {
 
 constexpr int kActs = 6;            // PredPreyAgentBase::actDomainSize(), PredPreyAgent.h:46
 constexpr int kStateBytes = 8;      // bytes reserved per agent state in Xb (6 acts + 2 pad)
-constexpr int kSelfMarker = 0xff;   // pair entry that stands for the proposed column itself
+constexpr int kNoContrib = 0xffff;  // empty slot in a contribution plane
 
-// record header (4 int32 words)
-//   [0] n      rows in the column (<= 32)
-//   [1] nPairs padded pair count (runs of equal u never straddle a 32-entry chunk; pad u = -1)
-//   [2] C      distinct columns in the pair list, the proposed column included
-//   [3] nSF    stale factors (TrajectoryImportance::perturb insertion order, de-duplicated)
-// then n x {xoff | m<<24, L, U, tabBase}, nPairs x u, ceil(nPairs/2) words of int16 {k | m<<8}, nSF x sid
+// Record of column j (int32 words; W = lanes per chain the problem was built for):
+//   [0] n | nSF << 8 | C << 16     rows in the column; stale factors; coupled columns incl. j itself
+//   [1] nChunks = ceil(C / W)
+//   [2] word offset of the contribution planes (uint16 units start at that word)
+//   [3] word offset of the stale-factor list
+//   rows:     n x {xoff | m << 24, L, U, tabBase}
+//   chunkHdr: nChunks x (maxCnt | contribOffset16 << 8)   maxCnt = most shared rows of a column in the chunk
+//   slotU:    nChunks*W x u, ascending, padded with -1
+//   contrib:  per chunk, maxCnt planes of W uint16 {k | m_u << 8} (row k of the column, entry M_{i_k,u}),
+//             plane t holding each slot's t-th shared row in ascending row order; kNoContrib = none
+//   staleF:   nSF x state id, TrajectoryImportance::perturb insertion order, de-duplicated
 struct DevProblem {
     int nRows, nCols, nEvents, xStride;
     int treeDepth;          // D = bit length of nCols-1
     int t1Len, t2Len;
     int evBytes;            // bytes of the padded event region of Xb = nStates * kStateBytes
     int G, S, T, nStates;   // PredPrey geometry (G == 0: no importance)
-    int maxCoupled;         // max C over columns
+    int groupWidth;         // W
+    int rowsCap, sCap, tCap;   // per-chain shared-memory capacities: rows, coupled columns, commit tasks
     int nSynopsis;
     double kappa;
     const uint32_t *recOff; // [nCols+1] record offsets in units of 4 words
@@ -62,17 +69,11 @@ struct DevChains {
     int32_t *infeas;         // currentInfeasibility (:49)
     unsigned long long *iter;   // Philox counter: iterations (init + MH) done so far
     long long *counters;     // [nChains][8]
-    // commit scratch overflow (entries beyond the shared-memory capacity), per chain
-    int32_t *scrU;
-    double *scrD;            // 3 doubles per entry: DEnew, base, dlt
-    uint16_t *scrTask;
+    double2 *scratch;        // [nChains][sCap] per step: {DE', new own-node base} of every coupled column
     // statistics
     long long *endStateSum;  // [S]   ensemble sum
     long long *synSum, *synSumSq; // [nChains][nSynopsis]
     long long *nSamples;     // [nChains]
-    int32_t *endOcc;         // [nChains][S] current end-state occupancy
-    long long *endAcc;       // [nChains][S] per-chain accumulated end-state occupancy
-    long long *endStamp;     // [nChains][S] sample index of the last flush
 };
 
 }  // namespace abm

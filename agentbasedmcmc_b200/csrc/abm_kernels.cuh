@@ -1,4 +1,11 @@
-// CUDA kernels of the B200 SparseBasisSampler (sm_100a).  One warp owns one Markov chain.
+// CUDA kernels of the B200 SparseBasisSampler (sm_100a).
+//
+// Work decomposition: a GROUP of W lanes (W = 8, 16 or 32) owns one Markov chain, so a warp advances
+// 32/W independent chains in lock step.  One Metropolis step has only a handful of rows, a few dozen
+// coupled columns and several strictly sequential floating-point chains (the reference's summation
+// orders are kept), so a full warp per chain leaves most lanes idle in most instructions; narrow groups
+// share every issued instruction between several chains.  All control flow is warp-uniform (loop bounds
+// are maxima over the warp's groups); per-group work is predicated.
 //
 // Reference semantics are cited per function (paths relative to /root/reference/src).  Floating point
 // is IEEE double with the reference's evaluation order; the file is compiled with -fmad=false so no
@@ -13,8 +20,6 @@
 namespace abm {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kSCap = 64;    // distinct-column entries kept in shared memory per warp (rest: global scratch)
-constexpr int kTCap = 128;   // commit tasks kept in shared memory per warp (rest: global scratch)
 constexpr unsigned kFull = 0xffffffffu;
 
 enum { MODE_MCMC = 0, MODE_INIT = 1 };
@@ -73,7 +78,7 @@ __device__ __forceinline__ int infeasOf(int x, int L, int U) { return x < L ? L 
 __device__ __forceinline__ double DEtoBasisProb(double DE) { return DE < 0.0 ? exp(DE) : 1.0; }
 
 // ------------------------------------------------------------------------------------------------
-// Per-warp view of one chain's HBM state.
+// One chain's HBM state.
 struct Chain {
     int8_t *Xb;
     double2 *colRec;
@@ -85,49 +90,6 @@ struct Chain {
         return &tier2[i >> 10];
     }
 };
-
-// Per-warp commit scratch: the first kSCap / kTCap entries live in shared memory, the rest in a
-// per-chain global overflow area (only columns coupled to > kSCap others ever reach it).
-struct Scratch {
-    int *sU;
-    double *sD;   // [3][kSCap]: DEnew, base, dlt
-    uint16_t *sT;
-    int *gU;
-    double *gD;
-    uint16_t *gT;
-    __device__ __forceinline__ int &U(int l) const { return l < kSCap ? sU[l] : gU[l - kSCap]; }
-    __device__ __forceinline__ double &DEn(int l) const { return l < kSCap ? sD[l] : gD[3 * (l - kSCap)]; }
-    __device__ __forceinline__ double &Base(int l) const { return l < kSCap ? sD[kSCap + l] : gD[3 * (l - kSCap) + 1]; }
-    __device__ __forceinline__ double &Dl(int l) const { return l < kSCap ? sD[2 * kSCap + l] : gD[3 * (l - kSCap) + 2]; }
-    __device__ __forceinline__ uint16_t &T(int t) const { return t < kTCap ? sT[t] : gT[t - kTCap]; }
-};
-
-// MutableCategoricalArray::operator()(RNG&), MutableCategoricalArray.h:119-132, evaluated five tree
-// levels per memory round trip: lane r fetches the node reached by the branch pattern r, then the same
-// strict comparisons / subtractions as the reference are resolved with shuffles.  Every lane returns j.
-__device__ __forceinline__ int treeDescend(const Chain &ch, int nCols, int depth, double target, int lane) {
-    int idx = 0;
-    int hi = depth - 1;
-    while (hi >= 0) {
-        int tierBase = hi >= 10 ? 10 : (hi >= 5 ? 5 : 0);
-        int lo = max(tierBase, hi - 4);
-        int nl = hi - lo + 1;
-        int c = idx + (lane << lo);
-        double v = 0.0;
-        if (lane > 0 && lane < (1 << nl) && c < nCols) v = *ch.node(c);
-        int pref = 0;
-        for (int b = nl - 1; b >= 0; --b) {
-            int rc = pref | (1 << b);
-            double vv = __shfl_sync(kFull, v, rc);
-            if (idx + (rc << lo) < nCols) {
-                if (vv > target) pref = rc; else target = __dsub_rn(target, vv);
-            }
-        }
-        idx += pref << lo;
-        hi = lo - 1;
-    }
-    return idx;
-}
 
 // ------------------------------------------------------------------------------------------------
 // PredPrey trajectory importance (TrajectoryImportance.h:90-113 on PredPreyAgent.h:124-182).
@@ -158,178 +120,238 @@ __device__ __forceinline__ int warpSumInt(int v) {
     return v;
 }
 
+template <int W>
+__device__ __forceinline__ int groupSumInt(int v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+template <int W>
+__device__ __forceinline__ int groupInclusiveScan(int v, int gl) {
+#pragma unroll
+    for (int o = 1; o < W; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, o, W);
+        if (gl >= o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ int warpMax(int v) { return __reduce_max_sync(kFull, v); }
+
+// Bytes of shared memory one chain (group) needs; must match the carve-up in stepKernel.
+__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap) {
+    return sCap * 8 + rowsCap * 16 + 32 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7);
+}
+
 // ------------------------------------------------------------------------------------------------
-// One chain per warp.  MODE_MCMC: the loop body of nextSampleWithInfeasibleImportance
-// (SparseBasisSampler.h:221-246).  MODE_INIT: findInitialFeasibleSolution (:254-263): same proposal,
-// always applied, no importance, no statistics, until the chain is feasible.
-template <int MODE>
+// MODE_MCMC: the loop body of nextSampleWithInfeasibleImportance (SparseBasisSampler.h:221-246).
+// MODE_INIT: findInitialFeasibleSolution (:254-263): same proposal, always applied, no importance, no
+// statistics, until the chain is feasible.
+template <int MODE, int W>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P, DevChains S, RunParams R) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
+    constexpr int NG = 32 / W;
+    constexpr int LW = W == 32 ? 5 : (W == 16 ? 4 : 3);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int chain = blockIdx.x * kWarpsPerCta + warp;
-    if (chain >= S.nChains) return;
+    const int gl = lane & (W - 1), g = lane / W;
+    const int chain = (blockIdx.x * kWarpsPerCta + warp) * NG + g;
+    const bool chainValid = chain < S.nChains;
+    const int chainC = chainValid ? chain : 0;   // pointer arithmetic only; every access is predicated
 
-    constexpr int kWarpSmem = kSCap * 4 + 3 * kSCap * 8 + kTCap * 2;
-    unsigned char *ws = smemRaw + warp * kWarpSmem;
-    Scratch sc;
-    sc.sD = reinterpret_cast<double *>(ws);
-    sc.sU = reinterpret_cast<int *>(ws + 3 * kSCap * 8);
-    sc.sT = reinterpret_cast<uint16_t *>(ws + 3 * kSCap * 8 + kSCap * 4);
-    const int scrCap = max(P.maxCoupled - kSCap, 0);
-    sc.gU = S.scrU + (size_t)chain * scrCap;
-    sc.gD = S.scrD + (size_t)chain * scrCap * 3;
-    sc.gT = S.scrTask + (size_t)chain * 32 * 32;
+    // ---- per-chain shared memory
+    const int gBytes = groupSmemBytes(P.rowsCap, P.sCap, P.tCap);
+    unsigned char *gs = smemRaw + (size_t)(warp * NG + g) * gBytes;
+    double *sDl = reinterpret_cast<double *>(gs);                        // [sCap] delta of set() per coupled column
+    double *sG = sDl + P.sCap;                                           // [rowsCap][2] per row: DE' term for a coupled column
+                                                                         //   whose flip moves the row by -1 / +1
+    double *sNode = sG + 2 * P.rowsCap;                                  // [32] tree nodes of one descent round
+    int *sU = reinterpret_cast<int *>(sNode + 32);                       // [sCap] coupled columns, ascending
+    int *sXoff = sU + P.sCap;                                            // [rowsCap] Xb offsets of the rows
+    uint16_t *sTask = reinterpret_cast<uint16_t *>(sXoff + P.rowsCap);   // [tCap] commit tasks
+    uint16_t *sXX = sTask + P.tCap;                                      // [rowsCap] x | xn << 8 (int8 each)
 
     Chain ch;
-    ch.Xb = S.Xb + (size_t)chain * P.xStride;
-    ch.colRec = S.colRec + (size_t)chain * P.nCols;
-    ch.delta = S.delta + (size_t)chain * P.nCols;
-    ch.tier1 = S.tier1 + (size_t)chain * P.t1Len;
-    ch.tier2 = S.tier2 + (size_t)chain * P.t2Len;
+    ch.Xb = S.Xb + (size_t)chainC * P.xStride;
+    ch.colRec = S.colRec + (size_t)chainC * P.nCols;
+    ch.delta = S.delta + (size_t)chainC * P.nCols;
+    ch.tier1 = S.tier1 + (size_t)chainC * P.t1Len;
+    ch.tier2 = S.tier2 + (size_t)chainC * P.t2Len;
+    double2 *scratch = S.scratch + (size_t)chainC * P.sCap;
 
-    double logImp = S.logImp[chain];
-    int infeas = S.infeas[chain];
-    unsigned long long iter = S.iter[chain];
+    double logImp = chainValid ? S.logImp[chain] : 0.0;
+    int infeas = chainValid ? S.infeas[chain] : 0;
+    unsigned long long iter = chainValid ? S.iter[chain] : 0ull;
     int cProp[4] = {0, 0, 0, 0}, cAcc[4] = {0, 0, 0, 0};
-    const unsigned long long chainId = R.firstChain + (unsigned long long)chain;
+    long long itersDone = 0;
+    const unsigned long long chainId = R.firstChain + (unsigned long long)chainC;
     const double kappa = P.kappa;
     const double *__restrict__ facVal = P.facVal;
+    const int nCols = P.nCols;
 
-    long long s = 0;
-    for (; s < R.nSteps; ++s) {
-        if (MODE == MODE_INIT && infeas == 0) break;
+    for (long long s = 0; s < R.nSteps; ++s) {
+        const bool act = chainValid && (MODE == MODE_MCMC || infeas > 0);
+        if (MODE == MODE_INIT && !__any_sync(kFull, act)) break;
 
         // ---- uniforms: one Philox block per iteration, or the injected stream
-        double u1, u2 = 0.0;
-        if (R.injU) {
-            const double *up = R.injU + (size_t)chain * R.uStride + R.uOffset;
-            if (MODE == MODE_INIT) u1 = up[s];
-            else { u1 = up[2 * s]; u2 = up[2 * s + 1]; }
-        } else {
-            uint32_t w[4];
-            philox4x32_10((uint32_t)iter, (uint32_t)(iter >> 32), (uint32_t)chainId, (uint32_t)(chainId >> 32),
-                          (uint32_t)R.seed, (uint32_t)(R.seed >> 32), w);
-            u1 = canonical_from_words(w[0], w[1]);
-            u2 = canonical_from_words(w[2], w[3]);
+        double u1 = 0.5, u2 = 0.0;
+        if (act) {
+            if (R.injU) {
+                const double *up = R.injU + (size_t)chain * R.uStride + R.uOffset;
+                if (MODE == MODE_INIT) u1 = up[s];
+                else { u1 = up[2 * s]; u2 = up[2 * s + 1]; }
+            } else {
+                uint32_t w[4];
+                philox4x32_10((uint32_t)iter, (uint32_t)(iter >> 32), (uint32_t)chainId, (uint32_t)(chainId >> 32),
+                              (uint32_t)R.seed, (uint32_t)(R.seed >> 32), w);
+                u1 = canonical_from_words(w[0], w[1]);
+                u2 = canonical_from_words(w[2], w[3]);
+            }
         }
 
-        // ---- Proposal::Proposal (:288-315)
-        const double root = ch.tier2[0];
-        int j = treeDescend(ch, P.nCols, P.treeDepth, __dmul_rn(u1, root), lane);   // :289
-        if (R.injJ) j = R.injJ[(size_t)chain * R.nSteps + s];
+        // ---- column draw: MutableCategoricalArray::operator()(RNG&), MutableCategoricalArray.h:119-132.
+        // LW tree levels per memory round trip: lane r fetches the node reached by branch pattern r, then the
+        // reference's strict comparisons / subtractions are resolved with shuffles.  A child index >= nCols
+        // holds 0.0: "0.0 > target" is false and "target - 0.0" is a no-op, which is the reference's skip.
+        const double root = act ? ch.tier2[0] : 1.0;
+        int j = 0;
+        {
+            double target = __dmul_rn(u1, root);
+            for (int hi = P.treeDepth - 1; hi >= 0; hi -= 5) {
+                const int lo = max(hi - 4, 0);
+                const int nl = hi - lo + 1;
+#pragma unroll
+                for (int k = 0; k < NG; ++k) {   // 31 candidate nodes of this round, 32/W per lane
+                    const int r = gl + W * k;
+                    const int c = j + (r << lo);
+                    double v = 0.0;
+                    if (act && r > 0 && r < (1 << nl) && c < nCols) v = *ch.node(c);
+                    sNode[r] = v;
+                }
+                __syncwarp();
+                int pref = 0;
+                for (int b = nl - 1; b >= 0; --b) {
+                    const int rc = pref | (1 << b);
+                    const double vv = sNode[rc];
+                    if (vv > target) pref = rc; else target = __dsub_rn(target, vv);
+                }
+                j += pref << lo;
+                __syncwarp();
+            }
+        }
+        if (act && R.injJ) j = R.injJ[(size_t)chain * R.nSteps + s];
 
-        const int32_t *__restrict__ rec = P.rec + (size_t)P.recOff[j] * 4;
-        const int4 hdr = __ldg(reinterpret_cast<const int4 *>(rec));
-        const int n = hdr.x, nPairs = hdr.y, C = hdr.z, nSF = hdr.w;
+        // ---- Proposal::Proposal (:288-315): record of column j
+        const int32_t *__restrict__ rec = P.rec + (size_t)P.recOff[act ? j : 0] * 4;
+        int4 hdr = make_int4(0, 0, 0, 0);
+        if (act) hdr = __ldg(reinterpret_cast<const int4 *>(rec));
+        const int n = hdr.x & 0xff, nSF = (hdr.x >> 8) & 0xff, C = (hdr.x >> 16) & 0xffff, nChunks = hdr.y;
         const int4 *__restrict__ recRows = reinterpret_cast<const int4 *>(rec + 4);
-        const int32_t *__restrict__ pairU = rec + 4 + 4 * n;
-        const int16_t *__restrict__ pairKM = reinterpret_cast<const int16_t *>(pairU + nPairs);
-        const int32_t *__restrict__ staleF = pairU + nPairs + ((nPairs + 1) >> 1);
-        const int dj = ch.delta[j];
+        const int32_t *__restrict__ chunkHdr = rec + 4 + 4 * n;
+        const int32_t *__restrict__ slotU = chunkHdr + nChunks;
+        const uint16_t *__restrict__ contrib = reinterpret_cast<const uint16_t *>(rec + hdr.z);
+        const int32_t *__restrict__ staleF = rec + hdr.w;
+        const int dj = act ? ch.delta[j] : 1;
 
-        // rows of the proposed column: lane k holds row k
-        int xoff = 0, L = 0, U = 0, tb = 0, x = 0, xn = 0, dinf = 0;
-        double dE = 0.0;
-        if (lane < n) {
-            int4 r = __ldg(recRows + lane);
-            xoff = r.x & 0xffffff;
-            int m = r.x >> 24;
-            L = r.y; U = r.z; tb = r.w;
-            x = ch.Xb[xoff];
-            xn = x + m * dj;                                                           // :299-300
-            dE = __dsub_rn(energyOf(xn, L, U, tb, facVal, kappa), energyOf(x, L, U, tb, facVal, kappa));  // :302
-            dinf = infeasOf(xn, L, U) - infeasOf(x, L, U);                              // :303
+        // rows of the proposed column
+        const int nW = warpMax(n);
+        int dinf = 0;
+        for (int rb = 0; rb < nW; rb += W) {
+            const int k = rb + gl;
+            if (k < n) {
+                const int4 r = __ldg(recRows + k);
+                const int xoff = r.x & 0xffffff, m = r.x >> 24;
+                const int x = ch.Xb[xoff];
+                const int xn = x + m * dj;                                                  // :299-300
+                sXoff[k] = xoff;
+                sXX[k] = (uint16_t)((x & 0xff) | ((xn & 0xff) << 8));
+                const double dE = __dsub_rn(energyOf(xn, r.y, r.z, r.w, facVal, kappa), energyOf(x, r.y, r.z, r.w, facVal, kappa));  // :302
+                // what this row adds to DE' of a coupled column whose flip would move the row by -1 / +1
+                // (:309-310, unit entries): (energy(x'+s) - energy(x+s)) - dE
+                sG[2 * k] = __dsub_rn(__dsub_rn(energyOf(xn - 1, r.y, r.z, r.w, facVal, kappa), energyOf(x - 1, r.y, r.z, r.w, facVal, kappa)), dE);
+                sG[2 * k + 1] = __dsub_rn(__dsub_rn(energyOf(xn + 1, r.y, r.z, r.w, facVal, kappa), energyOf(x + 1, r.y, r.z, r.w, facVal, kappa)), dE);
+                dinf += infeasOf(xn, r.y, r.z) - infeasOf(x, r.y, r.z);                    // :303
+            }
         }
-        const int infN = infeas + warpSumInt(dinf);
+        const int infN = infeas + groupSumInt<W>(dinf);
+        __syncwarp();
 
-        // coupled columns: lane p holds pair p = (u, k); runs of equal u are contiguous (sorted) and the
-        // contributions of one u are added in row order, as the map accumulation at :305-312 does
+        // coupled columns, one per lane, ascending.  A column's DE' is currentDE[u] plus one term per shared
+        // row in row order -- the order in which the reference's map accumulation visits them (:305-312).
         double changeInSum = 0.0;
-        int nDistinct = 0;
-        for (int base = 0; base < nPairs; base += 32) {
-            const int p = base + lane;
-            int u = -1, km = 0;
-            if (p < nPairs) { u = __ldg(pairU + p); km = __ldg(pairKM + p); }
-            const bool real = u >= 0;
-            const int k = km & 0xff;
-            const bool self = real && k == kSelfMarker;
-            const int mu = km >> 8;
-            int du = 0;
-            if (real && !self) du = ch.delta[u];
-            const int uprev = __shfl_up_sync(kFull, u, 1);
-            const bool head = real && (lane == 0 || uprev != u);
+        const int chunksW = warpMax(nChunks);
+        for (int c = 0; c < chunksW; ++c) {
+            const bool cv = c < nChunks;
+            const int slot = c * W + gl;
+            int u = -1, chdr = 0;
+            if (cv) { u = __ldg(slotU + slot); chdr = __ldg(chunkHdr + c); }
+            const bool real = u >= 0, self = real && u == j;
+            const int maxCnt = chdr & 0xff;
+            const uint16_t *__restrict__ plane = contrib + (chdr >> 8) + gl;
             double2 cr = make_double2(0.0, 0.0);
-            if (head) cr = ch.colRec[u];
-            // row data of row k
-            const int ks = k & 31;
-            const int xk = __shfl_sync(kFull, x, ks), xnk = __shfl_sync(kFull, xn, ks);
-            const int Lk = __shfl_sync(kFull, L, ks), Uk = __shfl_sync(kFull, U, ks), tbk = __shfl_sync(kFull, tb, ks);
-            const double dEk = __shfl_sync(kFull, dE, ks);
-            double cval = 0.0;
-            if (real && !self) {
-                const int sft = mu * du;                                                 // :308
-                cval = __dsub_rn(__dsub_rn(energyOf(xnk + sft, Lk, Uk, tbk, facVal, kappa),
-                                           energyOf(xk + sft, Lk, Uk, tbk, facVal, kappa)), dEk);   // :309-310
-            }
-            double acc = self ? -cr.x : __dadd_rn(cr.x, cval);                          // :294 / try_emplace + first +=
-            for (int r = 1; r < 32; ++r) {
-                const int tu = __shfl_down_sync(kFull, u, r);
-                const double tv = __shfl_down_sync(kFull, cval, r);
-                const bool more = head && (lane + r < 32) && tu == u;
-                if (more) acc = __dadd_rn(acc, tv);
-                if (!__any_sync(kFull, more)) break;
-            }
-            // per distinct column: new probability, old leaf value (get(u) = tree[u] - descendantSum(u),
-            // MutableCategoricalArray.h:78, .cpp:30-39) and what set(u, p) will need (.cpp:10-17)
-            double term = 0.0, newP = 0.0, ssum = 0.0, nodeOld = 0.0;
-            if (head) {
-                newP = DEtoBasisProb(acc);
-                nodeOld = (u & 31) ? cr.y : *ch.node(u);
-                double dsum = 0.0;
-                ssum = newP;
-                for (int off = 1; (off & u) == 0 && off < P.nCols; off <<= 1) {
-                    const int d = u + off;
-                    if (d < P.nCols) {
-                        const double t = *ch.node(d);
-                        dsum = __dadd_rn(dsum, t);
-                        ssum = __dadd_rn(ssum, t);
+            int du = 0;
+            if (real) { cr = ch.colRec[u]; du = ch.delta[u]; }
+            double acc = cr.x;                                                               // try_emplace(u, currentDE[u])
+            const int tW = warpMax(maxCnt);
+            for (int t = 0; t < tW; ++t) {
+                if (real && t < maxCnt) {
+                    const int ct = __ldg(plane + t * W);
+                    if (ct != kNoContrib) {
+                        const int k = ct & 0xff, mu = (int)(int8_t)(ct >> 8);
+                        const int sft = mu * du;                                             // :308, +-1 (unit entries)
+                        acc = __dadd_rn(acc, sG[2 * k + (sft > 0 ? 1 : 0)]);
                     }
                 }
-                term = __dsub_rn(newP, __dsub_rn(nodeOld, dsum));                        // :279-280
             }
-            const unsigned hb = __ballot_sync(kFull, head);
-            if (MODE == MODE_MCMC) {
-                // changeInSum += ... in ascending column order (:278-281)
-                unsigned rest = hb;
-                while (rest) {
-                    const int src = __ffs(rest) - 1;
-                    changeInSum = __dadd_rn(changeInSum, __shfl_sync(kFull, term, src));
-                    rest &= rest - 1;
+            if (self) acc = -cr.x;                                                           // :294
+            // new probability, old leaf value get(u) = tree[u] - descendantSum(u) (MutableCategoricalArray.h:78,
+            // .cpp:30-39), and the sum / delta that set(u, p') will compute (.cpp:10-17)
+            double newP = 0.0, nodeOld = 0.0, dsum = 0.0, ssum = 0.0;
+            int nDesc = 0;
+            if (real) {
+                newP = DEtoBasisProb(acc);
+                nodeOld = (u & 31) ? cr.y : *ch.node(u);
+                ssum = newP;
+                nDesc = u ? (__ffs(u) - 1) : P.treeDepth;
+            }
+            const int descW = warpMax(nDesc);
+            for (int i = 0; i < descW; ++i) {
+                const int d = u + (1 << i);
+                if (i < nDesc && d < nCols) {
+                    const double t = *ch.node(d);
+                    dsum = __dadd_rn(dsum, t);
+                    ssum = __dadd_rn(ssum, t);
                 }
             }
-            if (head) {
-                const int l = nDistinct + __popc(hb & ((1u << lane) - 1u));
-                sc.U(l) = u;
-                sc.DEn(l) = acc;
-                sc.Base(l) = ssum;
-                sc.Dl(l) = __dsub_rn(ssum, nodeOld);                                     // delta of set(), .cpp:17
+            const double term = __dsub_rn(newP, __dsub_rn(nodeOld, dsum));                   // :279-280
+            if (real) {
+                sU[slot] = u;
+                sDl[slot] = __dsub_rn(ssum, nodeOld);                                        // delta of set(), .cpp:17
+                scratch[slot] = make_double2(acc, ssum);
             }
-            nDistinct += __popc(hb);
+            if (MODE == MODE_MCMC) {
+                // changeInSum += ... in ascending column order (:278-281); padding slots carry term == 0 - 0
+#pragma unroll
+                for (int q = 0; q < W; ++q) {
+                    const double tq = __shfl_sync(kFull, term, q, W);
+                    if (c * W + q < C) changeInSum = __dadd_rn(changeInSum, tq);
+                }
+            }
         }
+        __syncwarp();
 
-        bool accept = true;
+        bool accept = act;
         double logImpN = logImp;
         if (MODE == MODE_MCMC) {
             // ---- importance: perturb + refresh (TrajectoryImportance.h:36-54, 90-113)
-            if (P.G > 0 && nSF > 0) {
+            const int sfW = warpMax(nSF);
+            if (sfW > 0) {
                 const int G = P.G, GG = G * G;
                 const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(ch.Xb);
-                for (int fb = 0; fb < nSF; fb += 32) {
-                    const int f = fb + lane;
-                    const bool act = f < nSF;
-                    int sid = 0, type = 0, ns[4] = {0, 0, 0, 0};
+                for (int fb = 0; fb < sfW; fb += W) {
+                    const int f = fb + gl;
+                    const bool fa = f < nSF;
+                    int sid = -1, type = 0, ns[4] = {-1, -1, -1, -1};
                     unsigned long long own = 0ull, nb[4] = {0ull, 0ull, 0ull, 0ull};
-                    if (act) {
+                    if (fa) {
                         sid = __ldg(staleF + f);
                         const int t = sid / P.S, psi = sid - t * P.S;
                         type = psi / GG;
@@ -346,113 +368,132 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
                     }
                     unsigned long long ownN = own, nbN[4] = {nb[0], nb[1], nb[2], nb[3]};
                     // apply the proposal's event changes (the X swap at :225-228) to the loaded words
-                    for (int r = 0; r < n; ++r) {
-                        const int xo = __shfl_sync(kFull, xoff, r);
-                        const int xv = __shfl_sync(kFull, xn, r);
-                        if (act && xo < P.evBytes) {
-                            const int rs = xo >> 3, sh = (xo & 7) * 8;
-                            const unsigned long long ins = (unsigned long long)(xv & 0xff) << sh, msk = ~(0xffull << sh);
-                            if (rs == sid) ownN = (ownN & msk) | ins;
+                    for (int r = 0; r < nW; ++r) {
+                        if (fa && r < n) {
+                            const int xo = sXoff[r];
+                            if (xo < P.evBytes) {
+                                const int rs = xo >> 3, sh = (xo & 7) * 8;
+                                const unsigned long long ins = (unsigned long long)(sXX[r] >> 8) << sh, msk = ~(0xffull << sh);
+                                if (rs == sid) ownN = (ownN & msk) | ins;
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (rs == ns[q]) nbN[q] = (nbN[q] & msk) | ins;
+                                for (int q = 0; q < 4; ++q)
+                                    if (rs == ns[q]) nbN[q] = (nbN[q] & msk) | ins;
+                            }
                         }
                     }
                     double diff = 0.0;
-                    if (act) {
+                    if (fa) {
                         const bool fl = (posMask(nb[0]) | posMask(nb[1]) | posMask(nb[2]) | posMask(nb[3])) != 0ull;
                         const bool flN = (posMask(nbN[0]) | posMask(nbN[1]) | posMask(nbN[2]) | posMask(nbN[3])) != 0ull;
                         diff = __dsub_rn(factorLogP(ownN, flN, type, P.impTab), factorLogP(own, fl, type, P.impTab));  // :109
                     }
-                    const int cnt = min(32, nSF - fb);
-                    for (int q = 0; q < cnt; ++q) logImpN = __dadd_rn(logImpN, __shfl_sync(kFull, diff, q));
+#pragma unroll
+                    for (int q = 0; q < W; ++q) {   // totalLogProb += ... in stale-factor insertion order
+                        const double dq = __shfl_sync(kFull, diff, q, W);
+                        if (fb + q < nSF) logImpN = __dadd_rn(logImpN, dq);
+                    }
                 }
             }
             // ---- calcRatioOfSums (:276-284) and the Metropolis test (:232-234)
             const double ratio = root / __dadd_rn(root, changeInSum);
             const double acceptance = __dmul_rn(exp(__dsub_rn(logImpN, logImp)), ratio);
-            accept = u2 < acceptance;
-            const int ci = (infeas == 0 ? 2 : 0) + (infN == 0 ? 1 : 0);                 // MCMCStatistics.cpp:12-17
+            accept = act && (u2 < acceptance);
+            const int ci = (infeas == 0 ? 2 : 0) + (infN == 0 ? 1 : 0);                      // MCMCStatistics.cpp:12-17
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                cProp[q] += (q == ci);
-                cAcc[q] += (q == ci && accept);
+                cProp[q] += (act && q == ci);
+                cAcc[q] += (accept && q == ci);
             }
         }
-        if (R.outJ) {
-            if (lane == 0) {
-                const size_t o = (size_t)chain * R.nSteps + s;
-                R.outJ[o] = j;
-                if (R.outAcc) R.outAcc[o] = accept ? 1 : 0;
-                if (R.outInf) R.outInf[o] = infN;
-            }
+        if (R.outJ && act && gl == 0) {
+            const size_t o = (size_t)chain * R.nSteps + s;
+            R.outJ[o] = j;
+            if (R.outAcc) R.outAcc[o] = accept ? 1 : 0;
+            if (R.outInf) R.outInf[o] = infN;
         }
 
+        // ---- applyProposal (:322-336)
         if (accept) {
-            // ---- applyProposal (:322-336)
             logImp = logImpN;
             infeas = infN;
-            if (lane < n) ch.Xb[xoff] = (int8_t)xn;
-            if (lane == 0) ch.delta[j] = (int8_t)(-dj);
-            __syncwarp();
-            // For every changed column u (ascending): currentDE[u] = DE'; tree.set(u, p').  All set() deltas
-            // depend only on pre-commit node values (an update never touches nodes >= its own index before
-            // it runs), so they were computed above; what remains is, per distinct node, the ordered sum of
-            // the deltas of the changed columns below it (MutableCategoricalArray.cpp:18-27).
-            for (int lb = 0; lb < C; lb += 32) {
-                const int l = lb + lane;
-                int u = 0;
-                unsigned ancMask = 0;
-                if (l < C) {
-                    u = sc.U(l);
-                    ch.colRec[u].x = sc.DEn(l);
-                    // own node: base + deltas of later changed columns inside its subtree
-                    const int b = u ? (__ffs(u) - 1) : 31;
-                    double v = sc.Base(l);
-                    for (int q = l + 1; q < C && (sc.U(q) >> b) == (u >> b); ++q) v = __dadd_rn(v, sc.Dl(q));
-                    *ch.node(u) = v;
-                    // ancestors this entry is the first contributor of
-                    const unsigned prev = l ? (unsigned)sc.U(l - 1) : 0u;
-                    const int hbit = l ? (31 - __clz(prev ^ (unsigned)u)) : 31;
-                    const unsigned low = hbit >= 31 ? 0xffffffffu : ((2u << hbit) - 1u);
-                    const unsigned lowbit = (unsigned)u & (0u - (unsigned)u);
-                    ancMask = (unsigned)u & low & ~(lowbit | (lowbit - 1u));
-                    if (l == 0 && u != 0) ancMask |= 0x80000000u;                        // the root
-                }
-                // compact (l, bit) tasks
-                const int cnt = __popc(ancMask);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const int nTasks = __shfl_sync(kFull, incl, 31);
-                int pos = incl - cnt;
-                unsigned mm = ancMask;
-                while (mm) {
-                    const int b = __ffs(mm) - 1;
-                    sc.T(pos++) = (uint16_t)((lane << 5) | b);
-                    mm &= mm - 1;
-                }
-                __syncwarp();
-                for (int t = lane; t < nTasks; t += 32) {
-                    const int tk = sc.T(t);
-                    const int l0 = lb + (tk >> 5), b = tk & 31;
-                    const int u0 = sc.U(l0);
-                    const int a = b == 31 ? 0 : ((u0 >> b) << b);
-                    double *np = ch.node(a);
-                    double v = *np;
-                    for (int q = l0; q < C && (sc.U(q) >> b) == (u0 >> b); ++q) v = __dadd_rn(v, sc.Dl(q));
-                    *np = v;
-                }
-                __syncwarp();
+            if (gl == 0) ch.delta[j] = (int8_t)(-dj);
+        }
+        for (int rb = 0; rb < nW; rb += W) {
+            const int k = rb + gl;
+            if (accept && k < n) ch.Xb[sXoff[k]] = (int8_t)(sXX[k] >> 8);
+        }
+        // For every changed column u (ascending): currentDE[u] = DE'; tree.set(u, p').  Every set() delta
+        // depends only on pre-commit node values (an update never touches nodes at or above its own index
+        // before it runs), so they were computed above.  What remains is, per distinct tree node, the
+        // ORDERED sum of the deltas of the changed columns below it (MutableCategoricalArray.cpp:18-27):
+        // a "task" = (first contributing entry l, tree level b); entries of one node are contiguous in the
+        // ascending list, namely those sharing u >> b.
+        const int Ca = accept ? C : 0;
+        const int CW = warpMax(Ca);
+        int nTasks = 0;
+        for (int lb = 0; lb < CW; lb += W) {
+            const int l = lb + gl;
+            unsigned taskMask = 0;
+            if (l < Ca) {
+                const int u = sU[l];
+                ch.colRec[u].x = scratch[l].x;
+                const unsigned prev = l ? (unsigned)sU[l - 1] : 0u;
+                const int hbit = l ? (31 - __clz(prev ^ (unsigned)u)) : 31;
+                const unsigned low = hbit >= 31 ? 0xffffffffu : ((2u << hbit) - 1u);
+                const unsigned lowbit = (unsigned)u & (0u - (unsigned)u);
+                taskMask = (unsigned)u & low & ~(lowbit | (lowbit - 1u));                    // ancestors first reached here
+                if (l == 0 && u != 0) taskMask |= 0x80000000u;                               // the root
+                taskMask |= u ? lowbit : 0x80000000u;                                        // the column's own node
+            }
+            const int cnt = __popc(taskMask);
+            const int incl = groupInclusiveScan<W>(cnt, gl);
+            int pos = nTasks + incl - cnt;
+            nTasks += __shfl_sync(kFull, incl, W - 1, W);
+            while (taskMask) {
+                const int b = __ffs(taskMask) - 1;
+                sTask[pos++] = (uint16_t)((l << 5) | b);
+                taskMask &= taskMask - 1;
             }
         }
-        ++iter;
+        __syncwarp();
+        {
+            // rounds of W tasks per chain: fetch, ordered sum over the run, store.  Tasks are emitted entry-major,
+            // so the long runs (the ancestors of the first entry) share the first rounds.
+            const int roundsW = warpMax((nTasks + W - 1) / W);
+            for (int rd = 0; rd < roundsW; ++rd) {
+                const int t = rd * W + gl;
+                int q = 0, b = 0, pre = 0;
+                bool have = t < nTasks;
+                double v = 0.0;
+                double *np = nullptr;
+                if (have) {
+                    const int tk = sTask[t];
+                    const int l0 = tk >> 5;
+                    b = tk & 31;
+                    const int u0 = sU[l0];
+                    pre = u0 >> b;
+                    const int a = b == 31 ? 0 : (pre << b);
+                    np = ch.node(a);
+                    const bool own = a == u0;
+                    v = own ? scratch[l0].y : *np;
+                    q = own ? l0 + 1 : l0;
+                }
+                bool more = have && q < Ca && (sU[q] >> b) == pre;
+                while (__any_sync(kFull, more)) {
+                    if (more) {
+                        v = __dadd_rn(v, sDl[q]);
+                        ++q;
+                        more = q < Ca && (sU[q] >> b) == pre;
+                    }
+                }
+                if (have) *np = v;
+            }
+        }
+        __syncwarp();
+        if (act) { ++iter; ++itersDone; }
     }
 
-    if (lane == 0) {
+    if (chainValid && gl == 0) {
         S.logImp[chain] = logImp;
         S.infeas[chain] = infeas;
         S.iter[chain] = iter;
@@ -463,7 +504,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
                 S.counters[(size_t)chain * 8 + 4 + q] += cAcc[q];
             }
         } else if (R.itersOut) {
-            R.itersOut[chain] += s;
+            R.itersOut[chain] += itersDone;
         }
     }
 }
