@@ -16,6 +16,7 @@ SYMBOLS = [
     "abm_chains_find_feasible", "abm_chains_step", "abm_chains_step_traced", "abm_chains_sample",
     "abm_chains_synchronize", "abm_chains_get_state", "abm_chains_get_counters", "abm_chains_get_infeasibility",
     "abm_chains_get_trajectories", "abm_chains_get_statistics", "abm_chains_reset_statistics",
+    "abm_chains_record_series", "abm_chains_get_series",
 ]
 
 
@@ -76,6 +77,8 @@ def load():
     L.abm_chains_get_trajectories.argtypes = [vp, i8p]
     L.abm_chains_get_statistics.argtypes = [vp, i64p, i64p, i64p, i64p, C.c_int]
     L.abm_chains_reset_statistics.argtypes = [vp]
+    L.abm_chains_record_series.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    L.abm_chains_get_series.argtypes = [vp, i32p]
     _lib = L
     return L
 

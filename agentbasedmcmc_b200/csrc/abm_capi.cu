@@ -69,6 +69,8 @@ struct abm_problem {
 };
 
 struct abm_chains {
+    int32_t *series = nullptr;   // thinned synopsis series of the first nSeriesChains chains
+    int nSeriesChains = 0, seriesCap = 0, seriesThin = 1;
     const abm_problem *p = nullptr;
     DevChains d{};
     DeviceArena arena;
@@ -79,6 +81,8 @@ struct abm_chains {
 };
 
 extern "C" {
+
+static int zeroStatistics(abm_chains *c);
 
 const char *abm_last_error(void) { return g_err.c_str(); }
 int abm_version(void) { return 1; }
@@ -172,7 +176,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     }
 
     // lanes per chain: the records are laid out for it (chunks of W coupled columns)
-    int W = 8;
+    int W = 16;
     if (const char *e = getenv("ABM_GROUP_WIDTH")) W = atoi(e);
     if (W != 8 && W != 16 && W != 32) return fail(ABM_ERR_INVALID, "ABM_GROUP_WIDTH must be 8, 16 or 32");
 
@@ -377,6 +381,7 @@ int abm_chains_create(const abm_problem *p, int32_t nChains, uint64_t seed, uint
     al(&d.scratch, n * P.sCap);
     al(&d.endStateSum, size_t(std::max(P.S, 1))); al(&d.synSum, n * std::max(P.nSynopsis, 1));
     al(&d.synSumSq, n * std::max(P.nSynopsis, 1)); al(&d.nSamples, n);
+    al(&d.endOcc, n * std::max(P.S, 1)); al(&d.endStamp, n * std::max(P.S, 1)); al(&d.endAcc, n * std::max(P.S, 1));
     if (e != cudaSuccess) {
         delete c;
         return fail(ABM_ERR_CUDA, std::string("chain allocation: ") + cudaGetErrorString(e));
@@ -389,6 +394,7 @@ int abm_chains_destroy(abm_chains *c) {
     if (!c) return ABM_OK;
     cudaSetDevice(c->p->device);
     cudaStreamSynchronize(c->stream);
+    if (c->series) cudaFree(c->series);
     delete c;
     return ABM_OK;
 }
@@ -418,6 +424,7 @@ int abm_chains_init(abm_chains *c, const int8_t *initEvents, int32_t nInit) {
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, n * 8 * sizeof(long long), c->stream));
     CUDA_TRY(cudaMemsetAsync(d.tier1, 0, n * P.t1Len * sizeof(double), c->stream));
     CUDA_TRY(cudaMemsetAsync(d.tier2, 0, n * P.t2Len * sizeof(double), c->stream));
+    { int rc = zeroStatistics(c); if (rc != ABM_OK) return rc; }
     const int threads = 256;
     dim3 gridC(std::min((P.nCols + threads - 1) / threads, 64), c->n), gridR(std::min((P.nRows + threads - 1) / threads, 64), c->n);
     initDeltaKernel<<<gridC, threads, 0, c->stream>>>(P, d, dInit, nInit);
@@ -450,8 +457,8 @@ template <int MODE>
 static cudaError_t launchStep(const abm_chains *c, const RunParams &r) {
     switch (c->p->d.groupWidth) {
         case 8: return launchStepW<MODE, 8>(c, r);
-        case 16: return launchStepW<MODE, 16>(c, r);
-        default: return launchStepW<MODE, 32>(c, r);
+        case 32: return launchStepW<MODE, 32>(c, r);
+        default: return launchStepW<MODE, 16>(c, r);
     }
 }
 
@@ -559,10 +566,56 @@ int abm_chains_step_traced(abm_chains *c, int64_t nSteps, const double *uniforms
     return ABM_OK;
 }
 
+static int zeroStatistics(abm_chains *c) {
+    const DevProblem &P = c->p->d;
+    const size_t n = size_t(c->n), ns = size_t(std::max(P.nSynopsis, 1));
+    CUDA_TRY(cudaMemsetAsync(c->d.endAcc, 0, n * std::max(P.S, 1) * sizeof(long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d.synSum, 0, n * ns * sizeof(long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d.synSumSq, 0, n * ns * sizeof(long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d.nSamples, 0, n * sizeof(long long), c->stream));
+    if (c->series)
+        CUDA_TRY(cudaMemsetAsync(c->series, 0, size_t(c->nSeriesChains) * c->seriesCap * ns * sizeof(int32_t), c->stream));
+    return ABM_OK;
+}
+
 int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
-    (void)nSamples; (void)maxSteps;
-    if (!c) return fail(ABM_ERR_INVALID, "null chains");
-    return fail(ABM_ERR_STATE, "abm_chains_sample: not implemented yet");
+    if (!c || nSamples < 0) return fail(ABM_ERR_INVALID, "bad argument");
+    if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
+    if (c->p->d.G <= 0) return fail(ABM_ERR_INVALID, "sample statistics need the PredPrey geometry");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    RunParams r = baseParams(c);
+    r.nSteps = maxSteps > 0 ? maxSteps : INT64_MAX;
+    r.nSamples = nSamples;
+    r.series = c->series;
+    r.nSeriesChains = c->nSeriesChains;
+    r.seriesCap = c->seriesCap;
+    r.seriesThin = c->seriesThin;
+    CUDA_TRY(launchStep<MODE_SAMPLE>(c, r));
+    return ABM_OK;
+}
+
+int abm_chains_record_series(abm_chains *c, int32_t nChains, int32_t thin, int32_t capacity) {
+    if (!c || nChains < 0 || nChains > c->n || thin < 1 || capacity < 0) return fail(ABM_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->series) { cudaFree(c->series); c->series = nullptr; }
+    c->nSeriesChains = nChains; c->seriesCap = capacity; c->seriesThin = thin;
+    const size_t count = size_t(nChains) * capacity * std::max(c->p->d.nSynopsis, 1);
+    if (count) {
+        CUDA_TRY(cudaMalloc(&c->series, count * sizeof(int32_t)));
+        CUDA_TRY(cudaMemset(c->series, 0, count * sizeof(int32_t)));
+    }
+    return ABM_OK;
+}
+
+int abm_chains_get_series(abm_chains *c, int32_t *out) {
+    if (!c || !out) return fail(ABM_ERR_INVALID, "null argument");
+    if (!c->series) return fail(ABM_ERR_STATE, "no series is being recorded");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const size_t count = size_t(c->nSeriesChains) * c->seriesCap * std::max(c->p->d.nSynopsis, 1);
+    CUDA_TRY(cudaMemcpy(out, c->series, count * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return ABM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -625,13 +678,31 @@ int abm_chains_get_trajectories(abm_chains *c, int8_t *events) {
     return ABM_OK;
 }
 
-int abm_chains_get_statistics(abm_chains *c, int64_t *, int64_t *, int64_t *, int64_t *, int) {
+int abm_chains_get_statistics(abm_chains *c, int64_t *endStateSum, int64_t *synSum, int64_t *synSumSq, int64_t *nSamples,
+                              int devicePtrs) {
     if (!c) return fail(ABM_ERR_INVALID, "null chains");
-    return fail(ABM_ERR_STATE, "abm_chains_get_statistics: not implemented yet");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const DevProblem &P = c->p->d;
+    const size_t n = size_t(c->n), ns = size_t(P.nSynopsis);
+    const cudaMemcpyKind kind = devicePtrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (endStateSum && P.S > 0) {
+        reduceEndStateKernel<<<(P.S + 127) / 128, 128, 0, c->stream>>>(P, c->d);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(endStateSum, c->d.endStateSum, size_t(P.S) * sizeof(int64_t), kind, c->stream));
+    }
+    if (synSum && ns) CUDA_TRY(cudaMemcpyAsync(synSum, c->d.synSum, n * ns * sizeof(int64_t), kind, c->stream));
+    if (synSumSq && ns) CUDA_TRY(cudaMemcpyAsync(synSumSq, c->d.synSumSq, n * ns * sizeof(int64_t), kind, c->stream));
+    if (nSamples) CUDA_TRY(cudaMemcpyAsync(nSamples, c->d.nSamples, n * sizeof(int64_t), kind, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ABM_OK;
 }
 
 int abm_chains_reset_statistics(abm_chains *c) {
     if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    int rc = zeroStatistics(c);
+    if (rc != ABM_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ABM_OK;
 }
 

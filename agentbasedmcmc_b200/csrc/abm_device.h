@@ -74,6 +74,9 @@ struct DevChains {
     long long *endStateSum;  // [S]   ensemble sum
     long long *synSum, *synSumSq; // [nChains][nSynopsis]
     long long *nSamples;     // [nChains]
+    int32_t *endOcc;         // [nChains][S] current end-state occupancy (valid during a sampling launch)
+    int32_t *endStamp;       // [nChains][S] launch-local sample index at which endOcc last changed
+    long long *endAcc;       // [nChains][S] sum over this chain's samples of the end-state occupancy
 };
 
 }  // namespace abm

@@ -22,7 +22,7 @@ namespace abm {
 constexpr int kWarpsPerCta = 4;
 constexpr unsigned kFull = 0xffffffffu;
 
-enum { MODE_MCMC = 0, MODE_INIT = 1 };
+enum { MODE_MCMC = 0, MODE_INIT = 1, MODE_SAMPLE = 2 };   // SAMPLE = MCMC + per-feasible-sample statistics
 
 struct RunParams {
     long long nSteps;            // Metropolis steps (MCMC) / iteration budget of this launch (INIT)
@@ -35,7 +35,9 @@ struct RunParams {
     int32_t *outInf;
     unsigned long long seed, firstChain;
     long long *itersOut;         // INIT: iterations done, accumulated per chain
-    long long nSamples;          // sample mode: feasible samples wanted per chain (0 = plain stepping)
+    long long nSamples;          // MODE_SAMPLE: feasible samples wanted per chain in this launch
+    int32_t *series;             // MODE_SAMPLE: thinned synopsis series [nSeriesChains][seriesCap][nSynopsis] or null
+    int nSeriesChains, seriesCap, seriesThin;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -144,13 +146,15 @@ __host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap) {
 
 // ------------------------------------------------------------------------------------------------
 // MODE_MCMC: the loop body of nextSampleWithInfeasibleImportance (SparseBasisSampler.h:221-246).
+// MODE_SAMPLE: the same, plus what the reference's statistics pipeline does with every feasible sample
+// (FiguresForPaper.h:93-104): end-state occupancy and synopsis sums, maintained incrementally.
 // MODE_INIT: findInitialFeasibleSolution (:254-263): same proposal, always applied, no importance, no
 // statistics, until the chain is feasible.
 template <int MODE, int W>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P, DevChains S, RunParams R) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     constexpr int NG = 32 / W;
-    constexpr int LW = W == 32 ? 5 : (W == 16 ? 4 : 3);
+    constexpr bool kMC = MODE != MODE_INIT;   // Metropolis test, importance, counters
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (W - 1), g = lane / W;
     const int chain = (blockIdx.x * kWarpsPerCta + warp) * NG + g;
@@ -187,9 +191,52 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
     const double *__restrict__ facVal = P.facVal;
     const int nCols = P.nCols;
 
+    // ---- MODE_SAMPLE state: current end-state occupancy ModelState(traj,T,T) (ModelState.h:27-36 via
+    // State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115), kept
+    // incrementally, with per-state accumulators advanced lazily (occupancy x samples since the last change)
+    long long nSamp = 0, synSum = 0, synSumSq = 0;
+    const long long samplesBefore = (MODE == MODE_SAMPLE && chainValid) ? S.nSamples[chain] : 0;
+    int syn = 0;                        // lane k < nSynopsis: agents inside the k-th nested square (FiguresForPaper.h:245-263)
+    int32_t *endOcc = nullptr, *endStamp = nullptr;
+    long long *endAcc = nullptr;
+    const int lastBase = (P.T - 1) * P.S * kStateBytes;   // Xb offset of the events of the last timestep
+    if (MODE == MODE_SAMPLE) {
+        endOcc = S.endOcc + (size_t)chainC * P.S;
+        endStamp = S.endStamp + (size_t)chainC * P.S;
+        endAcc = S.endAcc + (size_t)chainC * P.S;
+        const int G = P.G, GG = G * G;
+        if (chainValid) {
+            const int8_t *Xl = ch.Xb + lastBase;
+            for (int psi = gl; psi < P.S; psi += W) {
+                const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
+                const int left = tb + (cx + G - 1) % G + G * cy, right = tb + (cx + 1) % G + G * cy;
+                const int up = tb + cx + G * ((cy + 1) % G), down = tb + cx + G * ((cy + G - 1) % G);
+                // incoming events: MOVELEFT from the right neighbour, MOVERIGHT from the left one, MOVEUP from below,
+                // MOVEDOWN from above, GIVEBIRTH from the state itself (parent stays) and from the left neighbour (child)
+                const int occ = Xl[right * kStateBytes + 1] + Xl[left * kStateBytes + 2] + Xl[down * kStateBytes + 3] +
+                                Xl[up * kStateBytes + 4] + Xl[psi * kStateBytes + 5] + Xl[left * kStateBytes + 5];
+                endOcc[psi] = occ;
+                endStamp[psi] = 0;
+            }
+        }
+        __syncwarp();
+        for (int k = 0; k < P.nSynopsis; ++k) {   // group-wide sums, result kept by lane k
+            const int sz = G >> (k + 1), org = G - 2 * sz;
+            int part = 0;
+            if (chainValid)
+                for (int c2 = gl; c2 < 2 * sz * sz; c2 += W) {
+                    const int type = c2 / (sz * sz), cc = c2 - type * sz * sz;
+                    part += endOcc[type * GG + (org + cc % sz) + G * (org + cc / sz)];
+                }
+            part = groupSumInt<W>(part);
+            if (gl == k) syn = part;
+        }
+    }
+
     for (long long s = 0; s < R.nSteps; ++s) {
-        const bool act = chainValid && (MODE == MODE_MCMC || infeas > 0);
-        if (MODE == MODE_INIT && !__any_sync(kFull, act)) break;
+        const bool act = chainValid && (MODE == MODE_MCMC || (MODE == MODE_INIT && infeas > 0) ||
+                                        (MODE == MODE_SAMPLE && nSamp < R.nSamples));
+        if (MODE != MODE_MCMC && !__any_sync(kFull, act)) break;
 
         // ---- uniforms: one Philox block per iteration, or the injected stream
         double u1 = 0.5, u2 = 0.0;
@@ -327,7 +374,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
                 sDl[slot] = __dsub_rn(ssum, nodeOld);                                        // delta of set(), .cpp:17
                 scratch[slot] = make_double2(acc, ssum);
             }
-            if (MODE == MODE_MCMC) {
+            if (kMC) {
                 // changeInSum += ... in ascending column order (:278-281); padding slots carry term == 0 - 0
 #pragma unroll
                 for (int q = 0; q < W; ++q) {
@@ -340,7 +387,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
 
         bool accept = act;
         double logImpN = logImp;
-        if (MODE == MODE_MCMC) {
+        if (kMC) {
             // ---- importance: perturb + refresh (TrajectoryImportance.h:36-54, 90-113)
             const int sfW = warpMax(nSF);
             if (sfW > 0) {
@@ -490,14 +537,77 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
             }
         }
         __syncwarp();
+        if (MODE == MODE_SAMPLE) {
+            // events of the last timestep changed by an accepted proposal move the end state
+            bool touchesEnd = false;
+            for (int rb = 0; rb < nW; rb += W) {
+                const int k = rb + gl;
+                if (accept && k < n) { const int xo = sXoff[k]; touchesEnd |= xo >= lastBase && xo < P.evBytes; }
+            }
+            if (__any_sync(kFull, touchesEnd)) {
+                const int G = P.G, GG = G * G;
+                for (int r = 0; r < nW; ++r) {
+                    if (!(accept && r < n)) continue;
+                    const int xo = sXoff[r];
+                    if (xo < lastBase || xo >= P.evBytes) continue;
+                    const int a = xo & 7, psi = (xo - lastBase) >> 3;
+                    const int xx = sXX[r];
+                    const int dlt = (int)(int8_t)(xx >> 8) - (int)(int8_t)(xx & 0xff);
+                    const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
+                    int tg[2] = {-1, -1};   // consequences(act), PredPreyAgent.h:98-115
+                    if (a == 1) tg[0] = tb + (cx + G - 1) % G + G * cy;
+                    else if (a == 2) tg[0] = tb + (cx + 1) % G + G * cy;
+                    else if (a == 3) tg[0] = tb + cx + G * ((cy + 1) % G);
+                    else if (a == 4) tg[0] = tb + cx + G * ((cy + G - 1) % G);
+                    else if (a == 5) { tg[0] = psi; tg[1] = tb + (cx + 1) % G + G * cy; }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (tg[q] < 0) continue;
+                        if (gl == 0) {   // lazy accumulator: settle the samples taken at the old occupancy
+                            endAcc[tg[q]] += (long long)endOcc[tg[q]] * (long long)(nSamp - endStamp[tg[q]]);
+                            endStamp[tg[q]] = (int32_t)nSamp;
+                            endOcc[tg[q]] += dlt;
+                        }
+                        if (gl < P.nSynopsis) {
+                            const int sz = G >> (gl + 1), org = G - 2 * sz;
+                            const int tc = tg[q] % GG, tx = tc % G, ty = tc / G;
+                            if (tx >= org && tx < org + sz && ty >= org && ty < org + sz) syn += dlt;
+                        }
+                    }
+                }
+            }
+            // the do-while at SparseBasisSampler.h:247 hands out the state whenever it is feasible after a step
+            if (act && infeas == 0) {
+                if (gl < P.nSynopsis) {   // MeanAndVariance::operator(), diagnostics/MeanAndVariance.h:35-45 (exact in int64)
+                    synSum += syn;
+                    synSumSq += (long long)syn * syn;
+                    if (R.series && chain < R.nSeriesChains) {
+                        const long long tot = samplesBefore + nSamp;
+                        if (tot % R.seriesThin == 0 && tot / R.seriesThin < R.seriesCap)
+                            R.series[((size_t)chain * R.seriesCap + tot / R.seriesThin) * P.nSynopsis + gl] = syn;
+                    }
+                }
+                ++nSamp;
+            }
+        }
         if (act) { ++iter; ++itersDone; }
     }
 
+    if (MODE == MODE_SAMPLE && chainValid) {
+        __syncwarp();
+        for (int psi = gl; psi < P.S; psi += W)
+            endAcc[psi] += (long long)endOcc[psi] * (long long)(nSamp - endStamp[psi]);
+        if (gl < P.nSynopsis) {
+            S.synSum[(size_t)chain * P.nSynopsis + gl] += synSum;
+            S.synSumSq[(size_t)chain * P.nSynopsis + gl] += synSumSq;
+        }
+        if (gl == 0) S.nSamples[chain] += nSamp;
+    }
     if (chainValid && gl == 0) {
         S.logImp[chain] = logImp;
         S.infeas[chain] = infeas;
         S.iter[chain] = iter;
-        if (MODE == MODE_MCMC) {
+        if (kMC) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 S.counters[(size_t)chain * 8 + q] += cProp[q];
@@ -601,6 +711,15 @@ __global__ void setStateKernel(DevProblem P, DevChains S) {
         }
     }
     if (lane == 0) S.logImp[chain] = total;
+}
+
+// ensemble end-state sum: out[psi] = sum over chains of endAcc[chain][psi]
+__global__ void reduceEndStateKernel(DevProblem P, DevChains S) {
+    const int psi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (psi >= P.S) return;
+    long long acc = 0;
+    for (int c = 0; c < S.nChains; ++c) acc += S.endAcc[(size_t)c * P.S + psi];
+    S.endStateSum[psi] = acc;
 }
 
 }  // namespace abm

@@ -157,6 +157,40 @@ class SparseBasisSampler:
                                                   _ptr(j, C.c_int32), _ptr(acc, C.c_uint8), _ptr(inf, C.c_int32)))
         return j, acc, inf
 
+    # operator() for every chain + the statistics pipeline of FiguresForPaper.h:93-104
+    def sample(self, n_samples: int, max_steps: int = 0):
+        """Steps every chain until it has visited n_samples further feasible states (asynchronous)."""
+        check(_capi.load().abm_chains_sample(self.h, n_samples, max_steps))
+
+    def statistics(self):
+        """(end_state_sum[S] summed over chains, syn_sum[n_chains][d], syn_sumsq[n_chains][d], n_samples[n_chains])."""
+        P = self.problem
+        S = 2 * P.grid_size ** 2
+        end = np.zeros(S, np.int64)
+        ss = np.zeros((self.n_chains, P.n_synopsis), np.int64)
+        sq = np.zeros((self.n_chains, P.n_synopsis), np.int64)
+        ns = np.zeros(self.n_chains, np.int64)
+        check(_capi.load().abm_chains_get_statistics(self.h, _ptr(end, C.c_int64), _ptr(ss, C.c_int64), _ptr(sq, C.c_int64),
+                                                     _ptr(ns, C.c_int64), 0))
+        return end, ss, sq, ns
+
+    def statistics_into(self, end_ptr: int, syn_sum_ptr: int, syn_sumsq_ptr: int, n_samples_ptr: int):
+        """Same, into DEVICE buffers (raw pointers, e.g. torch tensors' data_ptr()) for an NCCL all-reduce."""
+        vp = lambda p: C.cast(C.c_void_p(p), C.POINTER(C.c_int64)) if p else None
+        check(_capi.load().abm_chains_get_statistics(self.h, vp(end_ptr), vp(syn_sum_ptr), vp(syn_sumsq_ptr), vp(n_samples_ptr), 1))
+
+    def reset_statistics(self):
+        check(_capi.load().abm_chains_reset_statistics(self.h))
+
+    def record_series(self, n_chains: int, thin: int, capacity: int):
+        check(_capi.load().abm_chains_record_series(self.h, n_chains, thin, capacity))
+        self._series_shape = (n_chains, capacity, self.problem.n_synopsis)
+
+    def series(self):
+        out = np.zeros(self._series_shape, np.int32)
+        check(_capi.load().abm_chains_get_series(self.h, _ptr(out, C.c_int32)))
+        return out
+
     def synchronize(self):
         check(_capi.load().abm_chains_synchronize(self.h))
 

@@ -144,6 +144,12 @@ ABM_API int abm_chains_get_trajectories(abm_chains *c, int8_t *events);
 ABM_API int abm_chains_get_statistics(abm_chains *c, int64_t *end_state_sum, int64_t *syn_sum, int64_t *syn_sumsq,
                                       int64_t *n_samples, int device_ptrs);
 ABM_API int abm_chains_reset_statistics(abm_chains *c);
+/* Optional thinned time series of the synopsis statistics (what `save(firstSynopsisSamples)` keeps, FiguresForPaper.h:96),
+ * for the first n_chains chains: every `thin`-th feasible sample, at most `capacity` per chain.  The series feeds the
+ * reference's variogram / effective-sample-size formulas (diagnostics/ChainStats.h:66-79, MultiChainStats.h:81-102).
+ * abm_chains_get_series: host int32 [n_chains][capacity][n_synopsis]. */
+ABM_API int abm_chains_record_series(abm_chains *c, int32_t n_chains, int32_t thin, int32_t capacity);
+ABM_API int abm_chains_get_series(abm_chains *c, int32_t *out);
 ABM_API int abm_problem_n_synopsis(const abm_problem *p); /* floor(log2(G)) - 1 (FiguresForPaper.h:246) */
 
 #ifdef __cplusplus

@@ -64,6 +64,9 @@ def lib():
         L.orc_chain_hash_X.restype = C.c_uint64
         L.orc_chain_hash_X.argtypes = [vp]
         L.orc_chain_end_state.argtypes = [vp, i32p]
+        L.orc_chain_sample_stats.restype = C.c_long
+        L.orc_chain_sample_stats.argtypes = [vp, C.c_long, C.c_long, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                             C.c_long, i32p, C.c_long, C.c_long]
         L.orc_mt_uniforms.argtypes = [C.c_uint32, C.c_long, f64p]
         L.orc_philox_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_long, f64p]
         _LIB = L
@@ -146,6 +149,13 @@ class OracleChain:
 
     def next_sample(self):
         return lib().orc_chain_next_sample(self.h)
+
+    def sample_stats(self, n_samples, max_steps, end_sum, syn_sum, syn_sumsq, sample_base=0, series=None, thin=1):
+        """Accumulates into the int64 arrays; series: int32 [cap][8] (columns beyond n_synopsis unused)."""
+        cap = 0 if series is None else series.shape[0]
+        return lib().orc_chain_sample_stats(self.h, n_samples, max_steps, _p(end_sum, C.c_int64), _p(syn_sum, C.c_int64),
+                                            _p(syn_sumsq, C.c_int64), sample_base,
+                                            None if series is None else _p(series, C.c_int32), cap, thin)
 
     @property
     def X(self):

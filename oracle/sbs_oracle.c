@@ -676,6 +676,43 @@ ORC_API void orc_chain_end_state(const OrcChain *c, int32_t *out) {
         out[right] += Xt[psi * A + 5]; /* ... and the child appears to the right */
     }
 }
+/* The reference's per-sample statistics (FiguresForPaper.h:93-104): for every feasible sample, the end state
+ * ModelState(traj,T,T) is summed (Dataflow Sum) and the synopsis (FiguresForPaper.h:245-263: agents inside nested
+ * squares of side G/2, G/4, ... > 1 along the diagonal) goes through MeanAndVariance (sum, sum of squares).
+ * Steps until nSamples samples were taken or maxSteps steps were made; returns the samples taken.
+ * series (may be NULL): every thin-th sample's synopsis, [cap][nSyn], indexed by global sample number / thin. */
+ORC_API long orc_chain_sample_stats(OrcChain *c, long nSamples, long maxSteps, int64_t *endSum, int64_t *synSum,
+                                    int64_t *synSumSq, long sampleBase, int32_t *series, long cap, long thin) {
+    const OrcProblem *p = c->p;
+    int G = p->G, GG = G * G, S = p->S;
+    int32_t *end = (int32_t *)malloc(sizeof(int32_t) * S);
+    long taken = 0;
+    for (long st = 0; st < maxSteps && taken < nSamples; ++st) {
+        orc_chain_step(c, 1, 0, 0, 0);
+        if (c->infeas != 0) continue;
+        orc_chain_end_state(c, end);
+        for (int k = 0; k < S; ++k) endSum[k] += end[k];
+        int varid = 0, origin = 0;
+        for (int part = G / 2; part > 1; part /= 2) {
+            int64_t occ = 0;
+            for (int x = 0; x < part; ++x)
+                for (int y = 0; y < part; ++y)
+                    occ += end[(origin + x) + G * (origin + y)] + end[(origin + x) + G * (origin + y) + GG];
+            synSum[varid] += occ;
+            synSumSq[varid] += occ * occ;
+            if (series) {
+                long tot = sampleBase + taken;
+                if (tot % thin == 0 && tot / thin < cap) series[(tot / thin) * 8 + varid] = (int32_t)occ;
+            }
+            ++varid;
+            origin += part;
+        }
+        ++taken;
+    }
+    free(end);
+    return taken;
+}
+
 /* bulk uniform generators, exposed so tests can feed the GPU the oracle's exact streams */
 ORC_API void orc_mt_uniforms(uint32_t seed, long n, double *out) {
     Mt19937 g;

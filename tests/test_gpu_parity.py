@@ -126,3 +126,42 @@ def test_async_step_matches_traced_step():
         assert np.array_equal(sa[2], sb[2]) and np.array_equal(sa[3], sb[3]) and sa[4] == sb[4]
     assert np.array_equal(a.counters(), b.counters())
     assert a.stats.nSamples() == 8 * 2000
+
+
+def test_sample_statistics_match_oracle():
+    """abm_chains_sample: every feasible state is a sample (SparseBasisSampler.h:247); end-state occupancy sums and
+    synopsis sums / sums of squares (FiguresForPaper.h:93-104,245-263) are exact integers == the oracle's."""
+    from oracle.oracle import OracleChain, OracleProblem
+    S = _gpu()
+    p = load_golden("pp8-4.abmp.xz")
+    n_chains, seed = 12, 991
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=seed)
+    smp.record_series(4, 3, 400)
+    smp.step(300)                      # burn-in: no statistics
+    smp.sample(700)
+    smp.sample(500, max_steps=450)     # second launch, bounded by steps
+    end, ss, sq, ns = smp.statistics()
+    series = smp.series()
+    OP = OracleProblem(p)
+    nsyn = P.n_synopsis
+    assert nsyn == 2
+    o_end = np.zeros(128, np.int64)
+    for c in range(n_chains):
+        oc = OracleChain(OP)
+        oc.seed_philox(seed, c)
+        oc.find_feasible()
+        oc.step(300)
+        s1, s2 = np.zeros(8, np.int64), np.zeros(8, np.int64)
+        ser = np.zeros((400, 8), np.int32)
+        n1 = oc.sample_stats(700, 10**9, o_end, s1, s2, 0, ser, 3)
+        n2 = oc.sample_stats(500, 450, o_end, s1, s2, n1, ser, 3)
+        assert ns[c] == n1 + n2
+        assert np.array_equal(ss[c], s1[:nsyn]) and np.array_equal(sq[c], s2[:nsyn])
+        assert np.array_equal(smp.state(c)[0], oc.X)
+        if c < 4:
+            assert np.array_equal(series[c], ser[:, :nsyn])
+    assert np.array_equal(end, o_end)
+    smp.reset_statistics()
+    end, ss, sq, ns = smp.statistics()
+    assert end.sum() == 0 and ss.sum() == 0 and ns.sum() == 0
