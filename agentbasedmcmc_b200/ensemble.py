@@ -1,0 +1,75 @@
+"""Ensemble statistics across chains and across GPUs.
+
+Chains are independent, so the only exchange step of the whole sampler is a SUM all-reduce of a few KB of sufficient
+statistics per reporting interval: the end-state occupancy sums, the sample count, and -- per synopsis statistic -- the
+sums over chains of the chain mean, its square, and the chain variance, from which W, B, var+ and R-hat follow
+(diagnostics/MultiChainStats.h:141-181).  `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class EnsembleSummary:
+    n_chains: int
+    n_samples: int                 # feasible samples over all chains
+    end_state_mean: np.ndarray     # [S] posterior mean occupancy of every agent state at t = T
+    synopsis_mean: np.ndarray      # [d]
+    W: np.ndarray
+    B: np.ndarray
+    var_plus: np.ndarray
+    rhat: np.ndarray
+    counters: np.ndarray           # [8] MCMCStatistics nProposals / nAccepted summed over all chains
+
+
+def pack_local(end_state_sum, syn_sum, syn_sumsq, n_samples, counters) -> torch.Tensor:
+    """Per-rank float64 vector [S + 2 + 4 d + 8] that is additive across ranks.  Inputs are this rank's chains."""
+    end = torch.as_tensor(end_state_sum, dtype=torch.float64)
+    s = torch.as_tensor(syn_sum, dtype=torch.float64)
+    sq = torch.as_tensor(syn_sumsq, dtype=torch.float64)
+    n = torch.as_tensor(n_samples, dtype=torch.float64)
+    ok = n > 1
+    nn = torch.where(ok, n, torch.ones_like(n))[:, None]
+    mean = torch.where(ok[:, None], s / nn, torch.zeros_like(s))
+    var = torch.where(ok[:, None], (sq - s * s / nn) / torch.clamp(nn - 1.0, min=1.0), torch.zeros_like(s))
+    head = torch.stack([ok.sum().to(torch.float64), n.sum()])
+    return torch.cat([end.flatten(), head, mean.sum(0), (mean * mean).sum(0), var.sum(0), s.sum(0),
+                      torch.as_tensor(counters, dtype=torch.float64).reshape(-1, 8).sum(0)])
+
+
+def summarize(packed: torch.Tensor, n_states: int, n_syn: int) -> EnsembleSummary:
+    v = packed.detach().cpu().numpy()
+    end, rest = v[:n_states], v[n_states:]
+    m, n_tot = rest[0], rest[1]
+    sm, sm2, sv, ssum = (rest[2 + k * n_syn: 2 + (k + 1) * n_syn] for k in range(4))
+    counters = rest[2 + 4 * n_syn:]
+    nbar = n_tot / max(m, 1.0)
+    W = sv / max(m, 1.0)
+    grand = sm / max(m, 1.0)
+    B = nbar / max(m - 1.0, 1.0) * (sm2 - m * grand * grand)
+    var_plus = W * (nbar - 1.0) / nbar + B / nbar
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rhat = np.sqrt(var_plus / W)
+    return EnsembleSummary(int(m), int(n_tot), end / max(n_tot, 1.0), ssum / max(n_tot, 1.0), W, B, var_plus, rhat,
+                           counters.astype(np.int64))
+
+
+def allreduce_summary(packed: torch.Tensor, n_states: int, n_syn: int, group=None) -> EnsembleSummary:
+    """SUM all-reduce of the packed statistics over the process group (no-op when not initialised), then summary."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return summarize(packed, n_states, n_syn)
+
+
+def sampler_summary(smp, group=None, device=None) -> EnsembleSummary:
+    """Statistics of a `SparseBasisSampler` (all its chains), all-reduced over `group`."""
+    end, ss, sq, ns = smp.statistics()
+    packed = pack_local(end, ss, sq, ns, smp.counters())
+    if device is not None:
+        packed = packed.to(device)
+    return allreduce_summary(packed, end.size, ss.shape[1], group)

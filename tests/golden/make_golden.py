@@ -37,6 +37,10 @@ def main():
         raw = tmp / f"trace_{name}_{s1}.abmp"
         subprocess.run([str(REF), "trace", str(tmp / f"{name}.abmp"), str(s0), str(s1), str(n), str(every), str(raw)], check=True)
         xz(raw, HERE / f"trace_{name}_{s1}.abmp.xz")
+    # long reference chains for posterior marginals (64 chains x 60000 feasible samples after 60000 burn-in)
+    raw = tmp / "marginals_pp8-4.abmp"
+    subprocess.run([str(REF), "marginals", str(tmp / "pp8-4.abmp"), "64", "60000", "60000", str(raw)], check=True)
+    xz(raw, HERE / "marginals_pp8-4.abmp.xz")
 
 
 if __name__ == "__main__":

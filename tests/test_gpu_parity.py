@@ -165,3 +165,32 @@ def test_sample_statistics_match_oracle():
     smp.reset_statistics()
     end, ss, sq, ns = smp.statistics()
     assert end.sum() == 0 and ss.sum() == 0 and ns.sum() == 0
+
+
+def test_posterior_marginals_match_reference_long_run():
+    """Statistical parity (BASELINE.json north_star): end-state marginals of 2048 GPU chains against the reference's own
+    long CPU run (64 chains x 60000 feasible samples after 60000 burn-in, tests/golden/marginals_pp8-4, made by
+    oracle/ref/abm_ref.cpp `marginals`).  Tolerance: 5 standard errors of the reference estimate (from the spread of
+    its 64 chains; two such reference runs differ from each other by up to 4 of these standard errors because a few
+    states mix slowly) plus 0.004 absolute; the expected number of agents to 5 %."""
+    from agentbasedmcmc_b200 import ensemble as E
+    S = _gpu()
+    p = load_golden("pp8-4.abmp.xz")
+    ref = load_golden("marginals_pp8-4.abmp.xz")
+    ref_mean = ref["endstate_sum"] / ref["n_samples"][0]
+    per_chain = ref["perchain_endstate_mean"].reshape(64, -1)
+    se = per_chain.std(axis=0, ddof=1) / np.sqrt(64.0)
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, n_chains=2048, seed=20240)
+    smp.step(80000)     # the first feasible state holds ~80 agents; the chain needs ~5e4 steps to relax to ~9
+    smp.sample(1500)
+    summ = E.sampler_summary(smp)
+    assert summ.n_samples == 2048 * 1500
+    diff = np.abs(summ.end_state_mean - ref_mean)
+    assert np.all(diff <= 5.0 * se + 0.004), f"worst state off by {diff.max():.4f} (se {se[diff.argmax()]:.4f})"
+    assert abs(summ.end_state_mean.sum() / ref_mean.sum() - 1.0) < 0.05
+    # acceptance / infeasibility statistics of the chain itself (BASELINE.md section 2: 83.4 % / 1.7 % at 8x8x4)
+    c = summ.counters
+    acc = c[4:].sum() / c[:4].sum()
+    assert abs(acc - 0.834) < 0.02
+    assert np.all(np.isfinite(summ.rhat)) and np.all(summ.rhat > 0.99)   # 1500 correlated samples per chain: R-hat is well above 1
