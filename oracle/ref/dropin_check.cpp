@@ -1,0 +1,73 @@
+// dropin_check: the reference's own host code (PredPreyProblem, TableauNormMinimiser, factor closures,
+// TrajectoryImportance) drives the GPU sampler through the reference constructor signature, side by side with the
+// unmodified reference SparseBasisSampler on the same Random::gen stream; every returned sample must be identical.
+// TEST INFRASTRUCTURE (built by `make -C oracle dropin` into oracle/_ref/, run by tests/test_gpu_dropin.py).
+#include <boost/serialization/access.hpp>
+#include "Trajectory.h"
+#include "Forecast.h"
+#include "Likelihood.h"
+#include "PredPreyProblem.h"
+#include "SparseBasisSampler.h"
+
+#include "abmcmc_b200/gpu_sampler.hpp"
+
+template <int G>
+int run(int T, int nSamples) {
+    Random::gen.seed(1234);   // FiguresForPaper.h:33
+    std::streambuf *old = std::cout.rdbuf(nullptr);
+    PredPreyProblem<G> problem(T, 0.05, 0.05, 0.05, 1.0, 10.0);
+    std::vector<ABM::occupation_type> init = problem.prior.nextSample(false);
+    Random::gen.seed(77);
+    SparseBasisSampler<ABM::occupation_type> ref(problem.tableau, problem.posterior.factors,
+                                                 problem.posterior.perturbableFunctionFactory(), init, problem.kappa);
+    std::mt19937 genRef = Random::gen;
+    Random::gen.seed(77);
+    abmcmc::GpuSparseBasisSampler<ABM::occupation_type> gpu(problem.tableau, problem.posterior.factors,
+                                                            problem.posterior.perturbableFunctionFactory(), init, problem.kappa);
+    std::mt19937 genGpu = Random::gen;
+    std::cout.rdbuf(old);
+    if (!(genRef == genGpu)) { printf("FAIL: generator position differs after construction\n"); return 1; }
+    if (ref.X != gpu.X) { printf("FAIL: first feasible state differs\n"); return 1; }
+    for (int k = 0; k < nSamples; ++k) {
+        Random::gen = genRef;
+        const std::vector<ABM::occupation_type> &a = ref();
+        genRef = Random::gen;
+        Random::gen = genGpu;
+        const std::vector<ABM::occupation_type> &b = gpu();
+        genGpu = Random::gen;
+        if (a != b || !(genRef == genGpu)) { printf("FAIL: sample %d differs\n", k); return 1; }
+    }
+    bool statsEqual = true;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+            statsEqual = statsEqual && ref.stats.nProposals[a][b] == gpu.stats.nProposals[a][b] && ref.stats.nAccepted[a][b] == gpu.stats.nAccepted[a][b];
+    if (!statsEqual) { printf("FAIL: MCMCStatistics differ\n"); return 1; }
+    // batched mode: many chains, Philox streams; every chain must stay inside the polyhedron (Experiments.cpp:97,142)
+    gpu.batched(64, 99);
+    gpu.step(2000);
+    gpu.sample(50);
+    gpu.synchronize();
+    std::vector<int8_t> ev(size_t(64) * T * PredPreyAgent<G>::domainSize() * 6);
+    abmcmc::detail::check(abm_chains_get_trajectories(gpu.chains(), ev.data()), "get_trajectories");
+    size_t ne = ev.size() / 64;
+    for (int c = 0; c < 64; ++c) {
+        std::vector<ABM::occupation_type> x(ev.begin() + c * ne, ev.begin() + (c + 1) * ne);
+        if (!problem.posterior.constraints.isValidSolution(x)) { printf("FAIL: batched chain %d left the polyhedron\n", c); return 1; }
+    }
+    printf("OK: %d samples identical to the reference SparseBasisSampler (%d Metropolis steps); 64 batched chains feasible\n",
+           nSamples, ref.stats.nSamples());
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    int g = argc > 1 ? atoi(argv[1]) : 8, T = argc > 2 ? atoi(argv[2]) : 4, n = argc > 3 ? atoi(argv[3]) : 300;
+    try {
+        if (g == 8) return run<8>(T, n);
+        if (g == 16) return run<16>(T, n);
+        printf("unsupported grid\n");
+        return 2;
+    } catch (const std::exception &e) {
+        printf("FAIL: %s\n", e.what());
+        return 1;
+    }
+}
