@@ -210,14 +210,20 @@ def bench_ours(args):
     value = steps_done / (total_ms * 1e-3)
 
     # ---- end to end through the host-facing API: step + statistics into host buffers, host clock
+    from agentbasedmcmc_b200 import ensemble as E
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    summary = None
     for k in range(args.steps):
-        smp.step(mh)
+        smp.sample(10 ** 12, max_steps=mh)      # mh Metropolis steps per chain, statistics of every feasible state
+        end, ss, sq, ns = smp.statistics()      # device -> host buffers
         c = smp.counters()
-        inf = smp.infeasibility()
-        d2h = c.nbytes + inf.nbytes
+        d2h = end.nbytes + ss.nbytes + sq.nbytes + ns.nbytes + c.nbytes
+        packed = E.pack_local(end, ss, sq, ns, c)
+        if world > 1:
+            packed = packed.cuda()
+        summary = E.allreduce_summary(packed, end.size, ss.shape[1])   # NCCL sum over ranks (world > 1)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -250,7 +256,12 @@ def bench_ours(args):
                          "algorithmic_bytes_per_chain_step": bytes_per_step, "kernel": "abm::stepKernel<MODE_MCMC>",
                          "kernel_ms_per_launch": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
-                    "what": "abm_chains_step + abm_chains_get_counters + abm_chains_get_infeasibility into host buffers, host clock"},
+                    "what": "abm_chains_sample (steps + on-device end-state/synopsis statistics) + abm_chains_get_statistics + "
+                            "abm_chains_get_counters into host buffers + ensemble all-reduce, host clock; inputs of a step are "
+                            "kernel arguments only (the problem and the chain states are uploaded once, at construction)"},
+            "ensemble": {"chains": summary.n_chains, "feasible_samples": summary.n_samples,
+                         "mean_agents_at_T": float(summary.end_state_mean.sum()),
+                         "rhat_synopsis": [round(float(x), 4) for x in summary.rhat]},
             "gpu_launches": args.steps,
             "clocks": clocks.summary(),
         }
