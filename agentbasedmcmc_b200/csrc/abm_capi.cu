@@ -181,7 +181,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     if (W != 8 && W != 16 && W != 32) return fail(ABM_ERR_INVALID, "ABM_GROUP_WIDTH must be 8, 16 or 32");
 
     // column records (layout: abm_device.h)
-    std::vector<uint32_t> recOff(nCols + 1);
+    std::vector<int4> recIdx(nCols);
     std::vector<int32_t> rec;
     rec.reserve((size_t)nnz * 24);
     int maxCoupled = 1, maxTasks = 1, maxSF = 0;
@@ -192,7 +192,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     std::vector<char> seen(std::max(nStates, 1), 0);
     for (int j = 0; j < nCols; ++j) {
         while (rec.size() % 4) rec.push_back(0);
-        recOff[j] = uint32_t(rec.size() / 4);
+        const uint32_t recStart = uint32_t(rec.size() / 4);
         const int n = colPtr[j + 1] - colPtr[j];
         pairs.clear();
         pairs.push_back({j, -1, 0});   // the proposed column itself (changedDE[j] = -currentDE[j], :294)
@@ -267,12 +267,11 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         if (staleF.size() > 255) return fail(ABM_ERR_INVALID, "too many stale factors for one column");
         maxSF = std::max(maxSF, int(staleF.size()));
         const size_t base = rec.size();
-        const size_t contribWord = 4 + size_t(4) * n + nChunks + slotU.size();
+        const size_t contribWord = size_t(4) * n + nChunks + slotU.size();
         const size_t staleWord = contribWord + (contrib.size() + 1) / 2;
-        rec.push_back(n | (int32_t(staleF.size()) << 8) | (C << 16));
-        rec.push_back(nChunks);
-        rec.push_back(int32_t(contribWord));
-        rec.push_back(int32_t(staleWord));
+        if (staleWord >= 65536) return fail(ABM_ERR_INVALID, "column record too large");
+        recIdx[j] = make_int4(int32_t(recStart), n | (int32_t(staleF.size()) << 8) | (C << 16), nChunks,
+                              int32_t(uint32_t(contribWord) | (uint32_t(staleWord) << 16)));
         for (int k = 0; k < n; ++k) {
             const int i = colRow[colPtr[j] + k];
             const int4 rp = rowParam[i];
@@ -292,7 +291,6 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         if (rec.size() / 4 > 0xfffffff0ull) return fail(ABM_ERR_INVALID, "record table too large");
     }
     while (rec.size() % 4) rec.push_back(0);
-    recOff[nCols] = uint32_t(rec.size() / 4);
     if (maxCoupled > 2040) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2040 others");
 
     std::vector<double> impTab(7 + 24, 0.0);
@@ -325,7 +323,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     std::vector<int32_t> colEvent(desc->nb_col, desc->nb_col + nCols);
     cudaError_t e = cudaSuccess;
     auto up = [&](auto **dst, const auto &v) { if (e == cudaSuccess) e = p->arena.upload(dst, v); };
-    up(&d.recOff, recOff); up(&d.rec, rec); up(&d.facVal, facVal); up(&d.impTab, impTab);
+    up(&d.recIdx, recIdx); up(&d.rec, rec); up(&d.facVal, facVal); up(&d.impTab, impTab);
     up(&d.colPtr, colPtr); up(&d.colRow, colRow); up(&d.colVal, colVal);
     up(&d.rowPtr, rowPtr); up(&d.rowCol, rowCol); up(&d.rowVal, rowVal);
     up(&d.rowF, rowF); up(&d.rowParam, rowParam); up(&d.colEvent, colEvent);

@@ -26,11 +26,10 @@ constexpr int kActs = 6;            // PredPreyAgentBase::actDomainSize(), PredP
 constexpr int kStateBytes = 8;      // bytes reserved per agent state in Xb (6 acts + 2 pad)
 constexpr int kNoContrib = 0xffff;  // empty slot in a contribution plane
 
-// Record of column j (int32 words; W = lanes per chain the problem was built for):
-//   [0] n | nSF << 8 | C << 16     rows in the column; stale factors; coupled columns incl. j itself
-//   [1] nChunks = ceil(C / W)
-//   [2] word offset of the contribution planes (uint16 units start at that word)
-//   [3] word offset of the stale-factor list
+// Record of column j (int32 words; W = lanes per chain the problem was built for).  Its header lives in recIdx[j]:
+//   n | nSF << 8 | C << 16     rows in the column; stale factors; coupled columns incl. j itself
+//   nChunks = ceil(C / W)
+//   word offsets (from the record start) of the contribution planes and of the stale-factor list
 //   rows:     n x {xoff | m << 24, L, U, tabBase}
 //   chunkHdr: nChunks x (maxCnt | contribOffset16 << 8)   maxCnt = most shared rows of a column in the chunk
 //   slotU:    nChunks*W x u, ascending, padded with -1
@@ -47,7 +46,7 @@ struct DevProblem {
     int rowsCap, sCap, tCap;   // per-chain shared-memory capacities: rows, coupled columns, commit tasks
     int nSynopsis;
     double kappa;
-    const uint32_t *recOff; // [nCols+1] record offsets in units of 4 words
+    const int4 *recIdx;     // [nCols] {record offset / 4 words, n | nSF<<8 | C<<16, nChunks, contrib word | stale word << 16}
     const int32_t *rec;
     const double *facVal;   // de-duplicated factor tables
     const double *impTab;   // [7] lgamma table, then [2][2][6] log ratios

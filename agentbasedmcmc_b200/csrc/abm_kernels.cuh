@@ -287,15 +287,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
         if (act && R.injJ) j = R.injJ[(size_t)chain * R.nSteps + s];
 
         // ---- Proposal::Proposal (:288-315): record of column j
-        const int32_t *__restrict__ rec = P.rec + (size_t)P.recOff[act ? j : 0] * 4;
         int4 hdr = make_int4(0, 0, 0, 0);
-        if (act) hdr = __ldg(reinterpret_cast<const int4 *>(rec));
-        const int n = hdr.x & 0xff, nSF = (hdr.x >> 8) & 0xff, C = (hdr.x >> 16) & 0xffff, nChunks = hdr.y;
-        const int4 *__restrict__ recRows = reinterpret_cast<const int4 *>(rec + 4);
-        const int32_t *__restrict__ chunkHdr = rec + 4 + 4 * n;
+        if (act) hdr = __ldg(P.recIdx + j);   // {record offset, n | nSF<<8 | C<<16, nChunks, contrib word | stale word << 16}
+        const int32_t *__restrict__ rec = P.rec + (size_t)(unsigned)hdr.x * 4;
+        const int n = hdr.y & 0xff, nSF = (hdr.y >> 8) & 0xff, C = (hdr.y >> 16) & 0xffff, nChunks = hdr.z;
+        const int4 *__restrict__ recRows = reinterpret_cast<const int4 *>(rec);
+        const int32_t *__restrict__ chunkHdr = rec + 4 * n;
         const int32_t *__restrict__ slotU = chunkHdr + nChunks;
-        const uint16_t *__restrict__ contrib = reinterpret_cast<const uint16_t *>(rec + hdr.z);
-        const int32_t *__restrict__ staleF = rec + hdr.w;
+        const uint16_t *__restrict__ contrib = reinterpret_cast<const uint16_t *>(rec + (hdr.w & 0xffff));
+        const int32_t *__restrict__ staleF = rec + ((unsigned)hdr.w >> 16);
         const int dj = act ? ch.delta[j] : 1;
 
         // rows of the proposed column
@@ -325,17 +325,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
         // row in row order -- the order in which the reference's map accumulation visits them (:305-312).
         double changeInSum = 0.0;
         const int chunksW = warpMax(nChunks);
+        int uNext = -1, chdrNext = 0;
+        if (0 < nChunks) { uNext = __ldg(slotU + gl); chdrNext = __ldg(chunkHdr); }
         for (int c = 0; c < chunksW; ++c) {
-            const bool cv = c < nChunks;
             const int slot = c * W + gl;
-            int u = -1, chdr = 0;
-            if (cv) { u = __ldg(slotU + slot); chdr = __ldg(chunkHdr + c); }
+            const int u = uNext, chdr = chdrNext;
+            uNext = -1; chdrNext = 0;
+            if (c + 1 < nChunks) { uNext = __ldg(slotU + slot + W); chdrNext = __ldg(chunkHdr + c + 1); }   // one chunk ahead
             const bool real = u >= 0, self = real && u == j;
             const int maxCnt = chdr & 0xff;
             const uint16_t *__restrict__ plane = contrib + (chdr >> 8) + gl;
+            // everything this column needs from the chain state, issued together: its record, its delta, and the
+            // nodes get(u) / set(u,.) will read: u + 1, 2, 4, 8, 16 sit in the same 32-record block
+            const int nDesc = real ? (u ? (__ffs(u) - 1) : P.treeDepth) : 0;
             double2 cr = make_double2(0.0, 0.0);
             int du = 0;
+            double dn[5];
             if (real) { cr = ch.colRec[u]; du = ch.delta[u]; }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int d = u + (1 << i);
+                dn[i] = (i < nDesc && d < nCols) ? ch.colRec[d].y : 0.0;
+            }
+            double nodeOld = cr.y;
+            if (real && (u & 31) == 0) nodeOld = *ch.node(u);
             double acc = cr.x;                                                               // try_emplace(u, currentDE[u])
             const int tW = warpMax(maxCnt);
             for (int t = 0; t < tW; ++t) {
@@ -350,22 +363,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
             }
             if (self) acc = -cr.x;                                                           // :294
             // new probability, old leaf value get(u) = tree[u] - descendantSum(u) (MutableCategoricalArray.h:78,
-            // .cpp:30-39), and the sum / delta that set(u, p') will compute (.cpp:10-17)
-            double newP = 0.0, nodeOld = 0.0, dsum = 0.0, ssum = 0.0;
-            int nDesc = 0;
-            if (real) {
-                newP = DEtoBasisProb(acc);
-                nodeOld = (u & 31) ? cr.y : *ch.node(u);
-                ssum = newP;
-                nDesc = u ? (__ffs(u) - 1) : P.treeDepth;
+            // .cpp:30-39), and the sum / delta that set(u, p') will compute (.cpp:10-17).  Absent descendants were
+            // loaded as 0.0 and x + 0.0 == x, so the unconditional adds reproduce the reference's skips.
+            const double newP = real ? DEtoBasisProb(acc) : 0.0;
+            double dsum = 0.0, ssum = newP;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                dsum = __dadd_rn(dsum, dn[i]);
+                ssum = __dadd_rn(ssum, dn[i]);
             }
             const int descW = warpMax(nDesc);
-            for (int i = 0; i < descW; ++i) {
-                const int d = u + (1 << i);
-                if (i < nDesc && d < nCols) {
-                    const double t = *ch.node(d);
-                    dsum = __dadd_rn(dsum, t);
-                    ssum = __dadd_rn(ssum, t);
+            for (int ib = 5; ib < descW; ib += 5) {   // columns with (u & 31) == 0: deeper descendants, five at a time
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const int d = u + (1 << (ib + i));
+                    dn[i] = (ib + i < nDesc && d < nCols) ? *ch.node(d) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    dsum = __dadd_rn(dsum, dn[i]);
+                    ssum = __dadd_rn(ssum, dn[i]);
                 }
             }
             const double term = __dsub_rn(newP, __dsub_rn(nodeOld, dsum));                   // :279-280
@@ -507,24 +524,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
             // rounds of W tasks per chain: fetch, ordered sum over the run, store.  Tasks are emitted entry-major,
             // so the long runs (the ancestors of the first entry) share the first rounds.
             const int roundsW = warpMax((nTasks + W - 1) / W);
-            for (int rd = 0; rd < roundsW; ++rd) {
-                const int t = rd * W + gl;
-                int q = 0, b = 0, pre = 0;
-                bool have = t < nTasks;
-                double v = 0.0;
-                double *np = nullptr;
-                if (have) {
+            // task of the coming round, fetched one round ahead so its node load overlaps the current ordered sum
+            int qN = 0, bN = 0, preN = 0;
+            bool haveN = false;
+            double vN = 0.0;
+            double *npN = nullptr;
+            auto fetch = [&](int t) {
+                haveN = t < nTasks;
+                if (haveN) {
                     const int tk = sTask[t];
                     const int l0 = tk >> 5;
-                    b = tk & 31;
+                    bN = tk & 31;
                     const int u0 = sU[l0];
-                    pre = u0 >> b;
-                    const int a = b == 31 ? 0 : (pre << b);
-                    np = ch.node(a);
+                    preN = u0 >> bN;
+                    const int a = bN == 31 ? 0 : (preN << bN);
+                    npN = ch.node(a);
                     const bool own = a == u0;
-                    v = own ? scratch[l0].y : *np;
-                    q = own ? l0 + 1 : l0;
+                    vN = own ? scratch[l0].y : *npN;
+                    qN = own ? l0 + 1 : l0;
                 }
+            };
+            fetch(gl);
+            for (int rd = 0; rd < roundsW; ++rd) {
+                int q = qN;
+                const int b = bN, pre = preN;
+                const bool have = haveN;
+                double v = vN;
+                double *np = npN;
+                fetch((rd + 1) * W + gl);
                 bool more = have && q < Ca && (sU[q] >> b) == pre;
                 while (__any_sync(kFull, more)) {
                     if (more) {
