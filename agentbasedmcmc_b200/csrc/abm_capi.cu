@@ -184,7 +184,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     std::vector<int4> recIdx(nCols);
     std::vector<int32_t> rec;
     rec.reserve((size_t)nnz * 24);
-    int maxCoupled = 1, maxTasks = 1, maxSF = 0;
+    int maxCoupled = 1, maxTasks = 1, maxSF = 0, maxTA = 1, maxTB = 1, maxTC = 1;
     struct Pair { int u, k, m; };
     std::vector<Pair> pairs;
     std::vector<int32_t> slotU, chunkHdr, staleF, nodes;
@@ -245,7 +245,16 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
             while (a2) { a2 &= a2 - 1; nodes.push_back(a2); }
         }
         std::sort(nodes.begin(), nodes.end());
-        maxTasks = std::max(maxTasks, int(std::unique(nodes.begin(), nodes.end()) - nodes.begin()));
+        {
+            const int nn = int(std::unique(nodes.begin(), nodes.end()) - nodes.begin());
+            int ta = 0, tb = 0, tc = 0;
+            for (int q = 0; q < nn; ++q) {
+                const int z = nodes[q] ? __builtin_ctz(nodes[q]) : 31;
+                (z >= 10 ? ta : (z >= 5 ? tb : tc))++;
+            }
+            maxTasks = std::max(maxTasks, nn);
+            maxTA = std::max(maxTA, ta); maxTB = std::max(maxTB, tb); maxTC = std::max(maxTC, tc);
+        }
         // stale factors in TrajectoryImportance::perturb insertion order (TrajectoryImportance.h:41-53)
         staleF.clear();
         if (G > 0) {
@@ -315,7 +324,10 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.groupWidth = W;
     d.rowsCap = (maxColNnz + 7) & ~7;
     d.sCap = (maxCoupled + 7) & ~7;
-    d.tCap = (maxTasks + 7) & ~7;
+    d.tCapA = (maxTA + 7) & ~7;
+    d.tCapB = (maxTB + 7) & ~7;
+    d.tCap = d.tCapA + d.tCapB + ((maxTC + 7) & ~7);
+    if (maxTA > 1000 || maxTB > 1000 || maxTC > 1000) return fail(ABM_ERR_INVALID, "too many sum-tree nodes touched by one column");
     int nSyn = 0;
     for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
     d.nSynopsis = nSyn;

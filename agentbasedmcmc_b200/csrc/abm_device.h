@@ -44,6 +44,7 @@ struct DevProblem {
     int G, S, T, nStates;   // PredPrey geometry (G == 0: no importance)
     int groupWidth;         // W
     int rowsCap, sCap, tCap;   // per-chain shared-memory capacities: rows, coupled columns, commit tasks
+    int tCapA, tCapB;          // task-list regions: levels >= 10, levels 5..9 (the rest of tCap: levels < 5)
     int nSynopsis;
     double kappa;
     const int4 *recIdx;     // [nCols] {record offset / 4 words, n | nSF<<8 | C<<16, nChunks, contrib word | stale word << 16}

@@ -494,7 +494,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
         // ascending list, namely those sharing u >> b.
         const int Ca = accept ? C : 0;
         const int CW = warpMax(Ca);
-        int nTasks = 0;
+        // Tasks are binned by tree level -- [10, root] (tier2 nodes), [5, 10) (tier1), [0, 5) (in-record nodes) -- because
+        // a node's run length grows with its level: rounds then hold tasks of similar length.  The three per-lane
+        // counts share one prefix scan (10 bits each).
+        int nTA = 0, nTB = 0, nTC = 0;
+        const int baseB = P.tCapA, baseC = P.tCapA + P.tCapB;
         for (int lb = 0; lb < CW; lb += W) {
             const int l = lb + gl;
             unsigned taskMask = 0;
@@ -509,20 +513,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
                 if (l == 0 && u != 0) taskMask |= 0x80000000u;                               // the root
                 taskMask |= u ? lowbit : 0x80000000u;                                        // the column's own node
             }
-            const int cnt = __popc(taskMask);
+            unsigned mA = taskMask & 0xfffffc00u, mB = taskMask & 0x000003e0u, mC = taskMask & 0x0000001fu;
+            const int cnt = __popc(mA) | (__popc(mB) << 10) | (__popc(mC) << 20);
             const int incl = groupInclusiveScan<W>(cnt, gl);
-            int pos = nTasks + incl - cnt;
-            nTasks += __shfl_sync(kFull, incl, W - 1, W);
-            while (taskMask) {
-                const int b = __ffs(taskMask) - 1;
-                sTask[pos++] = (uint16_t)((l << 5) | b);
-                taskMask &= taskMask - 1;
-            }
+            const int excl = incl - cnt, tot = __shfl_sync(kFull, incl, W - 1, W);
+            int pos = nTA + (excl & 1023);
+            while (mA) { sTask[pos++] = (uint16_t)((l << 5) | (__ffs(mA) - 1)); mA &= mA - 1; }
+            pos = baseB + nTB + ((excl >> 10) & 1023);
+            while (mB) { sTask[pos++] = (uint16_t)((l << 5) | (__ffs(mB) - 1)); mB &= mB - 1; }
+            pos = baseC + nTC + (excl >> 20);
+            while (mC) { sTask[pos++] = (uint16_t)((l << 5) | (__ffs(mC) - 1)); mC &= mC - 1; }
+            nTA += tot & 1023;
+            nTB += (tot >> 10) & 1023;
+            nTC += tot >> 20;
         }
+        const int nTasks = nTA + nTB + nTC;
         __syncwarp();
         {
-            // rounds of W tasks per chain: fetch, ordered sum over the run, store.  Tasks are emitted entry-major,
-            // so the long runs (the ancestors of the first entry) share the first rounds.
+            // rounds of W tasks per chain: fetch, ordered sum over the run, store
             const int roundsW = warpMax((nTasks + W - 1) / W);
             // task of the coming round, fetched one round ahead so its node load overlaps the current ordered sum
             int qN = 0, bN = 0, preN = 0;
@@ -532,7 +540,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
             auto fetch = [&](int t) {
                 haveN = t < nTasks;
                 if (haveN) {
-                    const int tk = sTask[t];
+                    const int tk = sTask[t < nTA ? t : (t < nTA + nTB ? baseB + t - nTA : baseC + t - nTA - nTB)];
                     const int l0 = tk >> 5;
                     bN = tk & 31;
                     const int u0 = sU[l0];
