@@ -279,7 +279,12 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         const size_t contribWord = size_t(4) * n + nChunks + slotU.size();
         const size_t staleWord = contribWord + (contrib.size() + 1) / 2;
         if (staleWord >= 65536) return fail(ABM_ERR_INVALID, "column record too large");
-        recIdx[j] = make_int4(int32_t(recStart), n | (int32_t(staleF.size()) << 8) | (C << 16), nChunks,
+        int nEv = 0;
+        for (int k = 0; k < n; ++k) nEv += colRow[colPtr[j] + k] < nEvents;
+        for (int k = 0; k < nEv; ++k)
+            if (colRow[colPtr[j] + k] >= nEvents) return fail(ABM_ERR_INVALID, "internal: event rows are not leading");
+        if (nChunks >= 65536) return fail(ABM_ERR_INVALID, "too many coupled columns");
+        recIdx[j] = make_int4(int32_t(recStart), n | (int32_t(staleF.size()) << 8) | (C << 16), nChunks | (nEv << 16),
                               int32_t(uint32_t(contribWord) | (uint32_t(staleWord) << 16)));
         for (int k = 0; k < n; ++k) {
             const int i = colRow[colPtr[j] + k];

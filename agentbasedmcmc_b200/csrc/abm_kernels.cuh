@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
         int4 hdr = make_int4(0, 0, 0, 0);
         if (act) hdr = __ldg(P.recIdx + j);   // {record offset, n | nSF<<8 | C<<16, nChunks, contrib word | stale word << 16}
         const int32_t *__restrict__ rec = P.rec + (size_t)(unsigned)hdr.x * 4;
-        const int n = hdr.y & 0xff, nSF = (hdr.y >> 8) & 0xff, C = (hdr.y >> 16) & 0xffff, nChunks = hdr.z;
+        const int n = hdr.y & 0xff, nSF = (hdr.y >> 8) & 0xff, C = (hdr.y >> 16) & 0xffff;
+        const int nChunks = hdr.z & 0xffff, nEv = hdr.z >> 16;   // nEv: leading rows that are events (row id < nEvents)
         const int4 *__restrict__ recRows = reinterpret_cast<const int4 *>(rec);
         const int32_t *__restrict__ chunkHdr = rec + 4 * n;
         const int32_t *__restrict__ slotU = chunkHdr + nChunks;
@@ -342,11 +343,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
             int du = 0;
             double dn[5];
             if (real) { cr = ch.colRec[u]; du = ch.delta[u]; }
+            const double *nearBase = &ch.colRec[real ? u : 0].y;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int d = u + (1 << i);
-                dn[i] = (i < nDesc && d < nCols) ? ch.colRec[d].y : 0.0;
-            }
+            for (int i = 0; i < 5; ++i) dn[i] = (i < nDesc && u + (1 << i) < nCols) ? nearBase[2 << i] : 0.0;
             double nodeOld = cr.y;
             if (real && (u & 31) == 0) nodeOld = *ch.node(u);
             double acc = cr.x;                                                               // try_emplace(u, currentDE[u])
@@ -373,16 +372,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
                 ssum = __dadd_rn(ssum, dn[i]);
             }
             const int descW = warpMax(nDesc);
-            for (int ib = 5; ib < descW; ib += 5) {   // columns with (u & 31) == 0: deeper descendants, five at a time
+            if (descW > 5) {
+                // columns with (u & 31) == 0 (one in 32).  Levels 5..9: u + 2^i has its low 5 bits clear and bit i set, so it
+                // is tier1[(u >> 5) + 2^(i-5)]; levels >= 10 likewise are tier2[(u >> 10) + 2^(i-10)].
+                const double *t1 = ch.tier1 + (real ? (u >> 5) : 0);
 #pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    const int d = u + (1 << (ib + i));
-                    dn[i] = (ib + i < nDesc && d < nCols) ? *ch.node(d) : 0.0;
-                }
+                for (int i = 0; i < 5; ++i) dn[i] = (5 + i < nDesc && u + (32 << i) < nCols) ? t1[1 << i] : 0.0;
 #pragma unroll
                 for (int i = 0; i < 5; ++i) {
                     dsum = __dadd_rn(dsum, dn[i]);
                     ssum = __dadd_rn(ssum, dn[i]);
+                }
+                const double *t2 = ch.tier2 + (real ? (u >> 10) : 0);
+                for (int i = 10; i < descW; ++i) {   // one column in 1024
+                    const double t = (i < nDesc && u + (1 << i) < nCols) ? t2[1 << (i - 10)] : 0.0;
+                    dsum = __dadd_rn(dsum, t);
+                    ssum = __dadd_rn(ssum, t);
                 }
             }
             const double term = __dsub_rn(newP, __dsub_rn(nodeOld, dsum));                   // :279-280
@@ -392,12 +397,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
                 scratch[slot] = make_double2(acc, ssum);
             }
             if (kMC) {
-                // changeInSum += ... in ascending column order (:278-281); padding slots carry term == 0 - 0
+                // changeInSum += ... in ascending column order (:278-281), staged through shared memory; padding slots
+                // carry term == +0.0 and x + 0.0 == x
+                sNode[gl] = real ? term : 0.0;
+                __syncwarp();
 #pragma unroll
-                for (int q = 0; q < W; ++q) {
-                    const double tq = __shfl_sync(kFull, term, q, W);
-                    if (c * W + q < C) changeInSum = __dadd_rn(changeInSum, tq);
-                }
+                for (int q = 0; q < W; ++q) changeInSum = __dadd_rn(changeInSum, sNode[q]);
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -407,6 +413,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
         if (kMC) {
             // ---- importance: perturb + refresh (TrajectoryImportance.h:36-54, 90-113)
             const int sfW = warpMax(nSF);
+            const int evW = warpMax(nEv);
             if (sfW > 0) {
                 const int G = P.G, GG = G * G;
                 const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(ch.Xb);
@@ -432,17 +439,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
                     }
                     unsigned long long ownN = own, nbN[4] = {nb[0], nb[1], nb[2], nb[3]};
                     // apply the proposal's event changes (the X swap at :225-228) to the loaded words
-                    for (int r = 0; r < nW; ++r) {
-                        if (fa && r < n) {
+                    for (int r = 0; r < evW; ++r) {   // event rows come first in a column (ascending row ids)
+                        if (fa && r < nEv) {
                             const int xo = sXoff[r];
-                            if (xo < P.evBytes) {
-                                const int rs = xo >> 3, sh = (xo & 7) * 8;
-                                const unsigned long long ins = (unsigned long long)(sXX[r] >> 8) << sh, msk = ~(0xffull << sh);
-                                if (rs == sid) ownN = (ownN & msk) | ins;
+                            const int rs = xo >> 3, sh = (xo & 7) * 8;
+                            const unsigned long long ins = (unsigned long long)(sXX[r] >> 8) << sh, msk = ~(0xffull << sh);
+                            if (rs == sid) ownN = (ownN & msk) | ins;
 #pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    if (rs == ns[q]) nbN[q] = (nbN[q] & msk) | ins;
-                            }
+                            for (int q = 0; q < 4; ++q)
+                                if (rs == ns[q]) nbN[q] = (nbN[q] & msk) | ins;
                         }
                     }
                     double diff = 0.0;
