@@ -151,7 +151,7 @@ __host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap) {
 // MODE_INIT: findInitialFeasibleSolution (:254-263): same proposal, always applied, no importance, no
 // statistics, until the chain is feasible.
 template <int MODE, int W>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P, DevChains S, RunParams R) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P, DevChains S, RunParams R) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     constexpr int NG = 32 / W;
     constexpr bool kMC = MODE != MODE_INIT;   // Metropolis test, importance, counters
@@ -538,39 +538,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 8) stepKernel(DevProblem P,
             // rounds of W tasks per chain: fetch, ordered sum over the run, store
             const int roundsW = warpMax((nTasks + W - 1) / W);
             // task of the coming round, fetched one round ahead so its node load overlaps the current ordered sum
-            int qN = 0, bN = 0, preN = 0;
+            int qN = 0, endN = 0;
             bool haveN = false;
             double vN = 0.0;
             double *npN = nullptr;
             auto fetch = [&](int t) {
                 haveN = t < nTasks;
+                qN = endN = 0;
                 if (haveN) {
                     const int tk = sTask[t < nTA ? t : (t < nTA + nTB ? baseB + t - nTA : baseC + t - nTA - nTB)];
-                    const int l0 = tk >> 5;
-                    bN = tk & 31;
-                    const int u0 = sU[l0];
-                    preN = u0 >> bN;
-                    const int a = bN == 31 ? 0 : (preN << bN);
-                    npN = ch.node(a);
+                    const int l0 = tk >> 5, b = tk & 31;
+                    const unsigned u0 = (unsigned)sU[l0];
+                    const unsigned pre = u0 >> b;
+                    const unsigned a = b == 31 ? 0u : (pre << b);
+                    npN = ch.node((int)a);
                     const bool own = a == u0;
                     vN = own ? scratch[l0].y : *npN;
                     qN = own ? l0 + 1 : l0;
+                    // the run ends at the first entry outside the node's index range [a, a + 2^b): binary search in the
+                    // ascending list (unsigned compare makes the root's key 2^31 exceed every column)
+                    const unsigned key = (pre + 1u) << b;
+                    int lo = qN, hi = Ca;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((unsigned)sU[mid] < key) lo = mid + 1; else hi = mid;
+                    }
+                    endN = lo;
                 }
             };
             fetch(gl);
             for (int rd = 0; rd < roundsW; ++rd) {
                 int q = qN;
-                const int b = bN, pre = preN;
+                const int end = endN;
                 const bool have = haveN;
                 double v = vN;
                 double *np = npN;
                 fetch((rd + 1) * W + gl);
-                bool more = have && q < Ca && (sU[q] >> b) == pre;
-                while (__any_sync(kFull, more)) {
-                    if (more) {
+                while (__any_sync(kFull, q < end)) {
+                    if (q < end) {
                         v = __dadd_rn(v, sDl[q]);
                         ++q;
-                        more = q < Ca && (sU[q] >> b) == pre;
                     }
                 }
                 if (have) *np = v;
