@@ -45,7 +45,7 @@ struct RunParams {
 // constructions as oracle/sbs_oracle.c, so GPU and oracle consume identical uniform streams.
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -76,8 +76,10 @@ __device__ __forceinline__ double energyOf(int x, int L, int U, int tabBase, con
 }
 __device__ __forceinline__ int infeasOf(int x, int L, int U) { return x < L ? L - x : (x > U ? x - U : 0); }
 
+// One out-of-line copy of exp(): the step kernel is bounded by instruction fetch as much as by anything else.
+__device__ __noinline__ double expShared(double x) { return exp(x); }
 // SparseBasisSampler.h:82
-__device__ __forceinline__ double DEtoBasisProb(double DE) { return DE < 0.0 ? exp(DE) : 1.0; }
+__device__ __forceinline__ double DEtoBasisProb(double DE) { return DE < 0.0 ? expShared(DE) : 1.0; }
 
 // ------------------------------------------------------------------------------------------------
 // One chain's HBM state.
@@ -102,7 +104,7 @@ __device__ __forceinline__ unsigned long long posMask(unsigned long long w) {
     return (((w & m7) + m7) & ~w) & m8;
 }
 // newLogP of refresh(): lgamma(occ+1) if occ>1, then += log(pi/pibar) per act with X>0, act order
-__device__ __forceinline__ double factorLogP(unsigned long long own, bool neighbour, int type,
+__device__ __noinline__ double factorLogP(unsigned long long own, bool neighbour, int type,
                                              const double *__restrict__ impTab) {
     unsigned long long pm = posMask(own);
     int occ = __popcll(pm);
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         const int G = P.G, GG = G * G;
         if (chainValid) {
             const int8_t *Xl = ch.Xb + lastBase;
+            #pragma unroll 1
             for (int psi = gl; psi < P.S; psi += W) {
                 const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
                 const int left = tb + (cx + G - 1) % G + G * cy, right = tb + (cx + 1) % G + G * cy;
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
         }
         __syncwarp();
+        #pragma unroll 1
         for (int k = 0; k < P.nSynopsis; ++k) {   // group-wide sums, result kept by lane k
             const int sz = G >> (k + 1), org = G - 2 * sz;
             int part = 0;
@@ -233,6 +237,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         }
     }
 
+    #pragma unroll 1
     for (long long s = 0; s < R.nSteps; ++s) {
         const bool act = chainValid && (MODE == MODE_MCMC || (MODE == MODE_INIT && infeas > 0) ||
                                         (MODE == MODE_SAMPLE && nSamp < R.nSamples));
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         int j = 0;
         {
             double target = __dmul_rn(u1, root);
+            #pragma unroll 1
             for (int hi = P.treeDepth - 1; hi >= 0; hi -= 5) {
                 const int lo = max(hi - 4, 0);
                 const int nl = hi - lo + 1;
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 }
                 __syncwarp();
                 int pref = 0;
+                #pragma unroll 1
                 for (int b = nl - 1; b >= 0; --b) {
                     const int rc = pref | (1 << b);
                     const double vv = sNode[rc];
@@ -302,6 +309,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // rows of the proposed column
         const int nW = warpMax(n);
         int dinf = 0;
+        #pragma unroll 1
         for (int rb = 0; rb < nW; rb += W) {
             const int k = rb + gl;
             if (k < n) {
@@ -328,6 +336,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         const int chunksW = warpMax(nChunks);
         int uNext = -1, chdrNext = 0;
         if (0 < nChunks) { uNext = __ldg(slotU + gl); chdrNext = __ldg(chunkHdr); }
+        #pragma unroll 1
         for (int c = 0; c < chunksW; ++c) {
             const int slot = c * W + gl;
             const int u = uNext, chdr = chdrNext;
@@ -350,6 +359,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             if (real && (u & 31) == 0) nodeOld = *ch.node(u);
             double acc = cr.x;                                                               // try_emplace(u, currentDE[u])
             const int tW = warpMax(maxCnt);
+            #pragma unroll 1
             for (int t = 0; t < tW; ++t) {
                 if (real && t < maxCnt) {
                     const int ct = __ldg(plane + t * W);
@@ -384,6 +394,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     ssum = __dadd_rn(ssum, dn[i]);
                 }
                 const double *t2 = ch.tier2 + (real ? (u >> 10) : 0);
+                #pragma unroll 1
                 for (int i = 10; i < descW; ++i) {   // one column in 1024
                     const double t = (i < nDesc && u + (1 << i) < nCols) ? t2[1 << (i - 10)] : 0.0;
                     dsum = __dadd_rn(dsum, t);
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 // carry term == +0.0 and x + 0.0 == x
                 sNode[gl] = real ? term : 0.0;
                 __syncwarp();
-#pragma unroll
+#pragma unroll 4
                 for (int q = 0; q < W; ++q) changeInSum = __dadd_rn(changeInSum, sNode[q]);
                 __syncwarp();
             }
@@ -417,6 +428,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             if (sfW > 0) {
                 const int G = P.G, GG = G * G;
                 const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(ch.Xb);
+                #pragma unroll 1
                 for (int fb = 0; fb < sfW; fb += W) {
                     const int f = fb + gl;
                     const bool fa = f < nSF;
@@ -439,6 +451,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     }
                     unsigned long long ownN = own, nbN[4] = {nb[0], nb[1], nb[2], nb[3]};
                     // apply the proposal's event changes (the X swap at :225-228) to the loaded words
+                    #pragma unroll 1
                     for (int r = 0; r < evW; ++r) {   // event rows come first in a column (ascending row ids)
                         if (fa && r < nEv) {
                             const int xo = sXoff[r];
@@ -456,7 +469,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                         const bool flN = (posMask(nbN[0]) | posMask(nbN[1]) | posMask(nbN[2]) | posMask(nbN[3])) != 0ull;
                         diff = __dsub_rn(factorLogP(ownN, flN, type, P.impTab), factorLogP(own, fl, type, P.impTab));  // :109
                     }
-#pragma unroll
+#pragma unroll 2
                     for (int q = 0; q < W; ++q) {   // totalLogProb += ... in stale-factor insertion order
                         const double dq = __shfl_sync(kFull, diff, q, W);
                         if (fb + q < nSF) logImpN = __dadd_rn(logImpN, dq);
@@ -465,7 +478,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
             // ---- calcRatioOfSums (:276-284) and the Metropolis test (:232-234)
             const double ratio = root / __dadd_rn(root, changeInSum);
-            const double acceptance = __dmul_rn(exp(__dsub_rn(logImpN, logImp)), ratio);
+            const double acceptance = __dmul_rn(expShared(__dsub_rn(logImpN, logImp)), ratio);
             accept = act && (u2 < acceptance);
             const int ci = (infeas == 0 ? 2 : 0) + (infN == 0 ? 1 : 0);                      // MCMCStatistics.cpp:12-17
 #pragma unroll
@@ -487,6 +500,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             infeas = infN;
             if (gl == 0) ch.delta[j] = (int8_t)(-dj);
         }
+        #pragma unroll 1
         for (int rb = 0; rb < nW; rb += W) {
             const int k = rb + gl;
             if (accept && k < n) ch.Xb[sXoff[k]] = (int8_t)(sXX[k] >> 8);
@@ -504,6 +518,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // counts share one prefix scan (10 bits each).
         int nTA = 0, nTB = 0, nTC = 0;
         const int baseB = P.tCapA, baseC = P.tCapA + P.tCapB;
+        #pragma unroll 1
         for (int lb = 0; lb < CW; lb += W) {
             const int l = lb + gl;
             unsigned taskMask = 0;
@@ -559,6 +574,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     // ascending list (unsigned compare makes the root's key 2^31 exceed every column)
                     const unsigned key = (pre + 1u) << b;
                     int lo = qN, hi = Ca;
+                    #pragma unroll 1
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
                         if ((unsigned)sU[mid] < key) lo = mid + 1; else hi = mid;
@@ -567,6 +583,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 }
             };
             fetch(gl);
+            #pragma unroll 1
             for (int rd = 0; rd < roundsW; ++rd) {
                 int q = qN;
                 const int end = endN;
@@ -574,6 +591,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 double v = vN;
                 double *np = npN;
                 fetch((rd + 1) * W + gl);
+                #pragma unroll 1
                 while (__any_sync(kFull, q < end)) {
                     if (q < end) {
                         v = __dadd_rn(v, sDl[q]);
@@ -587,12 +605,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (MODE == MODE_SAMPLE) {
             // events of the last timestep changed by an accepted proposal move the end state
             bool touchesEnd = false;
+            #pragma unroll 1
             for (int rb = 0; rb < nW; rb += W) {
                 const int k = rb + gl;
                 if (accept && k < n) { const int xo = sXoff[k]; touchesEnd |= xo >= lastBase && xo < P.evBytes; }
             }
             if (__any_sync(kFull, touchesEnd)) {
                 const int G = P.G, GG = G * G;
+                #pragma unroll 1
                 for (int r = 0; r < nW; ++r) {
                     if (!(accept && r < n)) continue;
                     const int xo = sXoff[r];
@@ -642,6 +662,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 
     if (MODE == MODE_SAMPLE && chainValid) {
         __syncwarp();
+        #pragma unroll 1
         for (int psi = gl; psi < P.S; psi += W)
             endAcc[psi] += (long long)endOcc[psi] * (long long)(nSamp - endStamp[psi]);
         if (gl < P.nSynopsis) {
