@@ -357,16 +357,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             for (int i = 0; i < 5; ++i) dn[i] = (i < nDesc && u + (1 << i) < nCols) ? nearBase[2 << i] : 0.0;
             double nodeOld = cr.y;
             if (real && (u & 31) == 0) nodeOld = *ch.node(u);
+            // the column's first four shared-row entries are fetched together with its state (most columns share 1-3
+            // rows with the proposed one); further planes, if any, one by one
+            int ct4[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) ct4[t] = (real && t < maxCnt) ? (int)__ldg(plane + t * W) : kNoContrib;
             double acc = cr.x;                                                               // try_emplace(u, currentDE[u])
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int ct = ct4[t];
+                if (ct != kNoContrib) {
+                    const int k = ct & 0xff, mu = (int)(int8_t)(ct >> 8);
+                    acc = __dadd_rn(acc, sG[2 * k + (mu * du > 0 ? 1 : 0)]);                 // :308-310, unit entries
+                }
+            }
             const int tW = warpMax(maxCnt);
-            #pragma unroll 1
-            for (int t = 0; t < tW; ++t) {
+#pragma unroll 1
+            for (int t = 4; t < tW; ++t) {
                 if (real && t < maxCnt) {
                     const int ct = __ldg(plane + t * W);
                     if (ct != kNoContrib) {
                         const int k = ct & 0xff, mu = (int)(int8_t)(ct >> 8);
-                        const int sft = mu * du;                                             // :308, +-1 (unit entries)
-                        acc = __dadd_rn(acc, sG[2 * k + (sft > 0 ? 1 : 0)]);
+                        acc = __dadd_rn(acc, sG[2 * k + (mu * du > 0 ? 1 : 0)]);
                     }
                 }
             }
