@@ -326,6 +326,8 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.t2Len = (nCols + 1023) / 1024;
     d.evBytes = evBytes;
     d.G = G; d.S = S; d.T = T; d.nStates = nStates;
+    d.gShift = -1;
+    for (int k = 0; k < 30; ++k) if (G == (1 << k)) d.gShift = k;
     d.groupWidth = W;
     d.rowsCap = (maxColNnz + 7) & ~7;
     d.sCap = (maxCoupled + 7) & ~7;
@@ -396,6 +398,7 @@ int abm_chains_create(const abm_problem *p, int32_t nChains, uint64_t seed, uint
     al(&d.scratch, n * P.sCap);
     al(&d.endStateSum, size_t(std::max(P.S, 1))); al(&d.synSum, n * std::max(P.nSynopsis, 1));
     al(&d.synSumSq, n * std::max(P.nSynopsis, 1)); al(&d.nSamples, n);
+    al(&d.synNow, n * std::max(P.nSynopsis, 1)); al(&d.launchSamples, n);
     al(&d.endOcc, n * std::max(P.S, 1)); al(&d.endStamp, n * std::max(P.S, 1)); al(&d.endAcc, n * std::max(P.S, 1));
     if (e != cudaSuccess) {
         delete c;
@@ -605,7 +608,12 @@ int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
     r.nSeriesChains = c->nSeriesChains;
     r.seriesCap = c->seriesCap;
     r.seriesThin = c->seriesThin;
+    const DevProblem &P = c->p->d;
+    sampleBeginKernel<<<(c->n + 3) / 4, 128, 0, c->stream>>>(P, c->d);
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(launchStep<MODE_SAMPLE>(c, r));
+    sampleEndKernel<<<dim3(std::max(1, std::min((P.S + 255) / 256, 8)), c->n), 256, 0, c->stream>>>(P, c->d);
+    CUDA_TRY(cudaGetLastError());
     return ABM_OK;
 }
 
@@ -701,7 +709,8 @@ int abm_chains_get_statistics(abm_chains *c, int64_t *endStateSum, int64_t *synS
     const size_t n = size_t(c->n), ns = size_t(P.nSynopsis);
     const cudaMemcpyKind kind = devicePtrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (endStateSum && P.S > 0) {
-        reduceEndStateKernel<<<(P.S + 127) / 128, 128, 0, c->stream>>>(P, c->d);
+        CUDA_TRY(cudaMemsetAsync(c->d.endStateSum, 0, size_t(P.S) * sizeof(long long), c->stream));
+        reduceEndStateKernel<<<dim3((P.S + 127) / 128, (c->n + kReduceSlice - 1) / kReduceSlice), 128, 0, c->stream>>>(P, c->d);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(endStateSum, c->d.endStateSum, size_t(P.S) * sizeof(int64_t), kind, c->stream));
     }

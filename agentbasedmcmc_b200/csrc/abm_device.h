@@ -42,6 +42,7 @@ struct DevProblem {
     int t1Len, t2Len;
     int evBytes;            // bytes of the padded event region of Xb = nStates * kStateBytes
     int G, S, T, nStates;   // PredPrey geometry (G == 0: no importance)
+    int gShift;             // log2(G) when G is a power of two, else -1
     int groupWidth;         // W
     int rowsCap, sCap, tCap;   // per-chain shared-memory capacities: rows, coupled columns, commit tasks
     int tCapA, tCapB;          // task-list regions: levels >= 10, levels 5..9 (the rest of tCap: levels < 5)
@@ -77,6 +78,8 @@ struct DevChains {
     int32_t *endOcc;         // [nChains][S] current end-state occupancy (valid during a sampling launch)
     int32_t *endStamp;       // [nChains][S] launch-local sample index at which endOcc last changed
     long long *endAcc;       // [nChains][S] sum over this chain's samples of the end-state occupancy
+    int32_t *synNow;         // [nChains][nSynopsis] synopsis of the current state (between sampling launches)
+    long long *launchSamples; // [nChains] samples taken by the last sampling launch
 };
 
 }  // namespace abm

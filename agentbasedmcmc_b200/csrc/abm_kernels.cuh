@@ -118,6 +118,18 @@ __device__ __noinline__ double factorLogP(unsigned long long own, bool neighbour
     return p;
 }
 
+// (type, x, y) of a state id and the base index of the opposite species at the same time, for grids that are not a
+// power of two (cold path; the hot path uses shifts)
+__device__ __noinline__ void stateGeometry(int sid, int S, int G, int &type, int &cx, int &cy, int &ob) {
+    const int GG = G * G;
+    const int t = sid / S, psi = sid - t * S;
+    type = psi / GG;
+    const int cell = psi - type * GG;
+    cy = cell / G;
+    cx = cell - cy * G;
+    ob = t * S + (1 - type) * GG;
+}
+
 __device__ __forceinline__ int warpSumInt(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -143,7 +155,51 @@ __device__ __forceinline__ int warpMax(int v) { return __reduce_max_sync(kFull, 
 
 // Bytes of shared memory one chain (group) needs; must match the carve-up in stepKernel.
 __host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap) {
-    return sCap * 8 + rowsCap * 16 + 32 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7);
+    return sCap * 8 + rowsCap * 16 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7);
+}
+
+// MODE_SAMPLE, rare path (an accepted proposal changed events of the last timestep): move the end-state occupancy
+// ModelState(traj,T,T) and return this lane's synopsis change.  Out of line to keep the step loop's code compact.
+__device__ __noinline__ int endStateUpdate(int G, int evBytes, int nSynopsis, int lastBase, int n, int nW, const int *sXoff,
+                                           const uint16_t *sXX, int32_t *endOcc, int32_t *endStamp, long long *endAcc,
+                                           int nSamp, int gl) {
+    const int GG = G * G;
+    int dsyn = 0;
+    for (int r = 0; r < nW; ++r) {
+        if (r >= n) continue;
+        const int xo = sXoff[r];
+        if (xo < lastBase || xo >= evBytes) continue;
+        const int a = xo & 7, psi = (xo - lastBase) >> 3;
+        const int xx = sXX[r];
+        const int dlt = (int)(int8_t)(xx >> 8) - (int)(int8_t)(xx & 0xff);
+        const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
+        int tg[2] = {-1, -1};   // consequences(act), PredPreyAgent.h:98-115
+        if (a == 1) tg[0] = tb + (cx + G - 1) % G + G * cy;
+        else if (a == 2) tg[0] = tb + (cx + 1) % G + G * cy;
+        else if (a == 3) tg[0] = tb + cx + G * ((cy + 1) % G);
+        else if (a == 4) tg[0] = tb + cx + G * ((cy + G - 1) % G);
+        else if (a == 5) { tg[0] = psi; tg[1] = tb + (cx + 1) % G + G * cy; }
+        for (int q = 0; q < 2; ++q) {
+            if (tg[q] < 0) continue;
+            if (gl == 0) {   // lazy accumulator: settle the samples taken at the old occupancy
+                endAcc[tg[q]] += (long long)endOcc[tg[q]] * (long long)(nSamp - endStamp[tg[q]]);
+                endStamp[tg[q]] = nSamp;
+                endOcc[tg[q]] += dlt;
+            }
+            if (gl < nSynopsis) {
+                const int sz = G >> (gl + 1), org = G - 2 * sz;
+                const int tc = tg[q] % GG, tx = tc % G, ty = tc / G;
+                if (tx >= org && tx < org + sz && ty >= org && ty < org + sz) dsyn += dlt;
+            }
+        }
+    }
+    return dsyn;
+}
+
+__device__ __noinline__ void recordSeries(int32_t *series, int seriesThin, int seriesCap, int nSynopsis, int chain, long long tot,
+                                          int gl, int syn) {
+    if (tot % seriesThin == 0 && tot / seriesThin < seriesCap)
+        series[((size_t)chain * seriesCap + tot / seriesThin) * nSynopsis + gl] = syn;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -170,7 +226,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     double *sG = sDl + P.sCap;                                           // [rowsCap][2] per row: DE' term for a coupled column
                                                                          //   whose flip moves the row by -1 / +1
     double *sNode = sG + 2 * P.rowsCap;                                  // [32] tree nodes of one descent round
-    int *sU = reinterpret_cast<int *>(sNode + 32);                       // [sCap] coupled columns, ascending
+    long long *sSyn = reinterpret_cast<long long *>(sNode + 32);         // [2][8] MODE_SAMPLE: synopsis sum / sum of squares
+    int *sU = reinterpret_cast<int *>(sSyn + 16);                        // [sCap] coupled columns, ascending
     int *sXoff = sU + P.sCap;                                            // [rowsCap] Xb offsets of the rows
     uint16_t *sTask = reinterpret_cast<uint16_t *>(sXoff + P.rowsCap);   // [tCap] commit tasks
     uint16_t *sXX = sTask + P.tCap;                                      // [rowsCap] x | xn << 8 (int8 each)
@@ -196,51 +253,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     // ---- MODE_SAMPLE state: current end-state occupancy ModelState(traj,T,T) (ModelState.h:27-36 via
     // State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115), kept
     // incrementally, with per-state accumulators advanced lazily (occupancy x samples since the last change)
-    long long nSamp = 0, synSum = 0, synSumSq = 0;
-    const long long samplesBefore = (MODE == MODE_SAMPLE && chainValid) ? S.nSamples[chain] : 0;
+    int nSamp = 0;                      // feasible samples taken in this launch
     int syn = 0;                        // lane k < nSynopsis: agents inside the k-th nested square (FiguresForPaper.h:245-263)
-    int32_t *endOcc = nullptr, *endStamp = nullptr;
-    long long *endAcc = nullptr;
     const int lastBase = (P.T - 1) * P.S * kStateBytes;   // Xb offset of the events of the last timestep
-    if (MODE == MODE_SAMPLE) {
-        endOcc = S.endOcc + (size_t)chainC * P.S;
-        endStamp = S.endStamp + (size_t)chainC * P.S;
-        endAcc = S.endAcc + (size_t)chainC * P.S;
-        const int G = P.G, GG = G * G;
-        if (chainValid) {
-            const int8_t *Xl = ch.Xb + lastBase;
-            #pragma unroll 1
-            for (int psi = gl; psi < P.S; psi += W) {
-                const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
-                const int left = tb + (cx + G - 1) % G + G * cy, right = tb + (cx + 1) % G + G * cy;
-                const int up = tb + cx + G * ((cy + 1) % G), down = tb + cx + G * ((cy + G - 1) % G);
-                // incoming events: MOVELEFT from the right neighbour, MOVERIGHT from the left one, MOVEUP from below,
-                // MOVEDOWN from above, GIVEBIRTH from the state itself (parent stays) and from the left neighbour (child)
-                const int occ = Xl[right * kStateBytes + 1] + Xl[left * kStateBytes + 2] + Xl[down * kStateBytes + 3] +
-                                Xl[up * kStateBytes + 4] + Xl[psi * kStateBytes + 5] + Xl[left * kStateBytes + 5];
-                endOcc[psi] = occ;
-                endStamp[psi] = 0;
-            }
-        }
+    if (MODE == MODE_SAMPLE) {   // end-state occupancy and synopsis were prepared by sampleBeginKernel
+        if (chainValid && gl < P.nSynopsis) syn = S.synNow[(size_t)chain * P.nSynopsis + gl];
+        if (gl < 16) sSyn[gl] = 0;
         __syncwarp();
-        #pragma unroll 1
-        for (int k = 0; k < P.nSynopsis; ++k) {   // group-wide sums, result kept by lane k
-            const int sz = G >> (k + 1), org = G - 2 * sz;
-            int part = 0;
-            if (chainValid)
-                for (int c2 = gl; c2 < 2 * sz * sz; c2 += W) {
-                    const int type = c2 / (sz * sz), cc = c2 - type * sz * sz;
-                    part += endOcc[type * GG + (org + cc % sz) + G * (org + cc / sz)];
-                }
-            part = groupSumInt<W>(part);
-            if (gl == k) syn = part;
-        }
     }
 
-    #pragma unroll 1
+#pragma unroll 1
     for (long long s = 0; s < R.nSteps; ++s) {
         const bool act = chainValid && (MODE == MODE_MCMC || (MODE == MODE_INIT && infeas > 0) ||
-                                        (MODE == MODE_SAMPLE && nSamp < R.nSamples));
+                                        (MODE == MODE_SAMPLE && (long long)nSamp < R.nSamples));
         if (MODE != MODE_MCMC && !__any_sync(kFull, act)) break;
 
         // ---- uniforms: one Philox block per iteration, or the injected stream
@@ -319,11 +344,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 const int xn = x + m * dj;                                                  // :299-300
                 sXoff[k] = xoff;
                 sXX[k] = (uint16_t)((x & 0xff) | ((xn & 0xff) << 8));
-                const double dE = __dsub_rn(energyOf(xn, r.y, r.z, r.w, facVal, kappa), energyOf(x, r.y, r.z, r.w, facVal, kappa));  // :302
-                // what this row adds to DE' of a coupled column whose flip would move the row by -1 / +1
-                // (:309-310, unit entries): (energy(x'+s) - energy(x+s)) - dE
-                sG[2 * k] = __dsub_rn(__dsub_rn(energyOf(xn - 1, r.y, r.z, r.w, facVal, kappa), energyOf(x - 1, r.y, r.z, r.w, facVal, kappa)), dE);
-                sG[2 * k + 1] = __dsub_rn(__dsub_rn(energyOf(xn + 1, r.y, r.z, r.w, facVal, kappa), energyOf(x + 1, r.y, r.z, r.w, facVal, kappa)), dE);
+                // dE = energy(x') - energy(x) (:302), and what this row adds to DE' of a coupled column whose flip would move
+                // the row by -1 / +1 (:309-310, unit entries): (energy(x'+s) - energy(x+s)) - dE
+                double dE = 0.0;
+#pragma unroll 1
+                for (int d = 0; d < 3; ++d) {   // shift 0 first (dE itself), then -1 and +1
+                    const int sh = d == 0 ? 0 : 2 * d - 3;
+                    const double e = __dsub_rn(energyOf(xn + sh, r.y, r.z, r.w, facVal, kappa), energyOf(x + sh, r.y, r.z, r.w, facVal, kappa));
+                    if (d == 0) dE = e; else sG[2 * k + d - 1] = __dsub_rn(e, dE);
+                }
                 dinf += infeasOf(xn, r.y, r.z) - infeasOf(x, r.y, r.z);                    // :303
             }
         }
@@ -357,14 +386,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             for (int i = 0; i < 5; ++i) dn[i] = (i < nDesc && u + (1 << i) < nCols) ? nearBase[2 << i] : 0.0;
             double nodeOld = cr.y;
             if (real && (u & 31) == 0) nodeOld = *ch.node(u);
-            // the column's first four shared-row entries are fetched together with its state (most columns share 1-3
+            // the column's first two shared-row entries are fetched together with its state (most columns share 1-3
             // rows with the proposed one); further planes, if any, one by one
-            int ct4[4];
+            int ct4[2];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) ct4[t] = (real && t < maxCnt) ? (int)__ldg(plane + t * W) : kNoContrib;
+            for (int t = 0; t < 2; ++t) ct4[t] = (real && t < maxCnt) ? (int)__ldg(plane + t * W) : kNoContrib;
             double acc = cr.x;                                                               // try_emplace(u, currentDE[u])
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 2; ++t) {
                 const int ct = ct4[t];
                 if (ct != kNoContrib) {
                     const int k = ct & 0xff, mu = (int)(int8_t)(ct >> 8);
@@ -373,7 +402,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
             const int tW = warpMax(maxCnt);
 #pragma unroll 1
-            for (int t = 4; t < tW; ++t) {
+            for (int t = 2; t < tW; ++t) {
                 if (real && t < maxCnt) {
                     const int ct = __ldg(plane + t * W);
                     if (ct != kNoContrib) {
@@ -448,15 +477,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     unsigned long long own = 0ull, nb[4] = {0ull, 0ull, 0ull, 0ull};
                     if (fa) {
                         sid = __ldg(staleF + f);
-                        const int t = sid / P.S, psi = sid - t * P.S;
-                        type = psi / GG;
-                        const int cell = psi - type * GG;
-                        const int cy = cell / G, cx = cell - cy * G;
-                        const int ob = t * P.S + (1 - type) * GG;   // PredPreyAgent.h:199-207: left, right, up, down
-                        ns[0] = ob + (cx + G - 1) % G + G * cy;
-                        ns[1] = ob + (cx + 1) % G + G * cy;
-                        ns[2] = ob + cx + G * ((cy + 1) % G);
-                        ns[3] = ob + cx + G * ((cy + G - 1) % G);
+                        int cx, cy, ob;
+                        if (P.gShift >= 0) {   // power-of-two grids: psi = x + G y + G^2 type (PredPreyAgent.h:59) by shifts
+                            const int psi = sid & (P.S - 1), cell = psi & (GG - 1);
+                            type = psi >> (2 * P.gShift);
+                            cy = cell >> P.gShift; cx = cell & (G - 1);
+                            ob = (sid - psi) + (1 - type) * GG;
+                        } else {
+                            stateGeometry(sid, P.S, G, type, cx, cy, ob);
+                        }
+                        // PredPreyAgent.h:199-207: left, right, up, down, opposite species, torus
+                        const int xl = cx == 0 ? G - 1 : cx - 1, xr = cx == G - 1 ? 0 : cx + 1;
+                        const int yu = cy == G - 1 ? 0 : cy + 1, yd = cy == 0 ? G - 1 : cy - 1;
+                        ns[0] = ob + xl + G * cy;
+                        ns[1] = ob + xr + G * cy;
+                        ns[2] = ob + cx + G * yu;
+                        ns[3] = ob + cx + G * yd;
                         own = X8[sid];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) nb[q] = X8[ns[q]];
@@ -545,16 +581,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 if (l == 0 && u != 0) taskMask |= 0x80000000u;                               // the root
                 taskMask |= u ? lowbit : 0x80000000u;                                        // the column's own node
             }
-            unsigned mA = taskMask & 0xfffffc00u, mB = taskMask & 0x000003e0u, mC = taskMask & 0x0000001fu;
-            const int cnt = __popc(mA) | (__popc(mB) << 10) | (__popc(mC) << 20);
+            const int cnt = __popc(taskMask & 0xfffffc00u) | (__popc(taskMask & 0x000003e0u) << 10) | (__popc(taskMask & 0x0000001fu) << 20);
             const int incl = groupInclusiveScan<W>(cnt, gl);
             const int excl = incl - cnt, tot = __shfl_sync(kFull, incl, W - 1, W);
-            int pos = nTA + (excl & 1023);
-            while (mA) { sTask[pos++] = (uint16_t)((l << 5) | (__ffs(mA) - 1)); mA &= mA - 1; }
-            pos = baseB + nTB + ((excl >> 10) & 1023);
-            while (mB) { sTask[pos++] = (uint16_t)((l << 5) | (__ffs(mB) - 1)); mB &= mB - 1; }
-            pos = baseC + nTC + (excl >> 20);
-            while (mC) { sTask[pos++] = (uint16_t)((l << 5) | (__ffs(mC) - 1)); mC &= mC - 1; }
+            int posA = nTA + (excl & 1023), posB = baseB + nTB + ((excl >> 10) & 1023), posC = baseC + nTC + (excl >> 20);
+#pragma unroll 1
+            while (taskMask) {
+                const int b = __ffs(taskMask) - 1;
+                const int pos = b >= 10 ? posA++ : (b >= 5 ? posB++ : posC++);
+                sTask[pos] = (uint16_t)((l << 5) | b);
+                taskMask &= taskMask - 1;
+            }
             nTA += tot & 1023;
             nTB += (tot >> 10) & 1023;
             nTC += tot >> 20;
@@ -622,49 +659,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 const int k = rb + gl;
                 if (accept && k < n) { const int xo = sXoff[k]; touchesEnd |= xo >= lastBase && xo < P.evBytes; }
             }
-            if (__any_sync(kFull, touchesEnd)) {
-                const int G = P.G, GG = G * G;
-                #pragma unroll 1
-                for (int r = 0; r < nW; ++r) {
-                    if (!(accept && r < n)) continue;
-                    const int xo = sXoff[r];
-                    if (xo < lastBase || xo >= P.evBytes) continue;
-                    const int a = xo & 7, psi = (xo - lastBase) >> 3;
-                    const int xx = sXX[r];
-                    const int dlt = (int)(int8_t)(xx >> 8) - (int)(int8_t)(xx & 0xff);
-                    const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
-                    int tg[2] = {-1, -1};   // consequences(act), PredPreyAgent.h:98-115
-                    if (a == 1) tg[0] = tb + (cx + G - 1) % G + G * cy;
-                    else if (a == 2) tg[0] = tb + (cx + 1) % G + G * cy;
-                    else if (a == 3) tg[0] = tb + cx + G * ((cy + 1) % G);
-                    else if (a == 4) tg[0] = tb + cx + G * ((cy + G - 1) % G);
-                    else if (a == 5) { tg[0] = psi; tg[1] = tb + (cx + 1) % G + G * cy; }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (tg[q] < 0) continue;
-                        if (gl == 0) {   // lazy accumulator: settle the samples taken at the old occupancy
-                            endAcc[tg[q]] += (long long)endOcc[tg[q]] * (long long)(nSamp - endStamp[tg[q]]);
-                            endStamp[tg[q]] = (int32_t)nSamp;
-                            endOcc[tg[q]] += dlt;
-                        }
-                        if (gl < P.nSynopsis) {
-                            const int sz = G >> (gl + 1), org = G - 2 * sz;
-                            const int tc = tg[q] % GG, tx = tc % G, ty = tc / G;
-                            if (tx >= org && tx < org + sz && ty >= org && ty < org + sz) syn += dlt;
-                        }
-                    }
-                }
-            }
+            if (__any_sync(kFull, touchesEnd))
+                syn += endStateUpdate(P.G, P.evBytes, P.nSynopsis, lastBase, accept ? n : 0, nW, sXoff, sXX, S.endOcc + (size_t)chainC * P.S,
+                                      S.endStamp + (size_t)chainC * P.S, S.endAcc + (size_t)chainC * P.S, nSamp, gl);
             // the do-while at SparseBasisSampler.h:247 hands out the state whenever it is feasible after a step
             if (act && infeas == 0) {
                 if (gl < P.nSynopsis) {   // MeanAndVariance::operator(), diagnostics/MeanAndVariance.h:35-45 (exact in int64)
-                    synSum += syn;
-                    synSumSq += (long long)syn * syn;
-                    if (R.series && chain < R.nSeriesChains) {
-                        const long long tot = samplesBefore + nSamp;
-                        if (tot % R.seriesThin == 0 && tot / R.seriesThin < R.seriesCap)
-                            R.series[((size_t)chain * R.seriesCap + tot / R.seriesThin) * P.nSynopsis + gl] = syn;
-                    }
+                    sSyn[gl] += syn;
+                    sSyn[8 + gl] += (long long)syn * syn;
+                    if (R.series && chain < R.nSeriesChains) recordSeries(R.series, R.seriesThin, R.seriesCap, P.nSynopsis, chain, S.nSamples[chain] + nSamp, gl, syn);
                 }
                 ++nSamp;
             }
@@ -672,16 +675,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (act) { ++iter; ++itersDone; }
     }
 
-    if (MODE == MODE_SAMPLE && chainValid) {
-        __syncwarp();
-        #pragma unroll 1
-        for (int psi = gl; psi < P.S; psi += W)
-            endAcc[psi] += (long long)endOcc[psi] * (long long)(nSamp - endStamp[psi]);
+    if (MODE == MODE_SAMPLE && chainValid) {   // the lazy accumulators are settled by sampleEndKernel
         if (gl < P.nSynopsis) {
-            S.synSum[(size_t)chain * P.nSynopsis + gl] += synSum;
-            S.synSumSq[(size_t)chain * P.nSynopsis + gl] += synSumSq;
+            S.synSum[(size_t)chain * P.nSynopsis + gl] += sSyn[gl];
+            S.synSumSq[(size_t)chain * P.nSynopsis + gl] += sSyn[8 + gl];
+            S.synNow[(size_t)chain * P.nSynopsis + gl] = syn;
         }
-        if (gl == 0) S.nSamples[chain] += nSamp;
+        if (gl == 0) S.launchSamples[chain] = nSamp;
     }
     if (chainValid && gl == 0) {
         S.logImp[chain] = logImp;
@@ -793,13 +793,59 @@ __global__ void setStateKernel(DevProblem P, DevChains S) {
     if (lane == 0) S.logImp[chain] = total;
 }
 
-// ensemble end-state sum: out[psi] = sum over chains of endAcc[chain][psi]
+// Before a sampling launch: the current end-state occupancy ModelState(traj,T,T) (ModelState.h:27-36 via
+// State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115) and the synopsis
+// (FiguresForPaper.h:245-263) of every chain, from which stepKernel<MODE_SAMPLE> proceeds incrementally.  One warp per chain.
+__global__ void sampleBeginKernel(DevProblem P, DevChains S) {
+    const int lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (chain >= S.nChains) return;
+    const int G = P.G, GG = G * G;
+    const int8_t *Xl = S.Xb + (size_t)chain * P.xStride + (size_t)(P.T - 1) * P.S * kStateBytes;
+    int32_t *endOcc = S.endOcc + (size_t)chain * P.S, *endStamp = S.endStamp + (size_t)chain * P.S;
+    for (int psi = lane; psi < P.S; psi += 32) {
+        const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
+        const int left = tb + (cx + G - 1) % G + G * cy, right = tb + (cx + 1) % G + G * cy;
+        const int up = tb + cx + G * ((cy + 1) % G), down = tb + cx + G * ((cy + G - 1) % G);
+        // incoming events: MOVELEFT from the right neighbour, MOVERIGHT from the left one, MOVEUP from below,
+        // MOVEDOWN from above, GIVEBIRTH from the state itself (parent stays) and from the left neighbour (child)
+        endOcc[psi] = Xl[right * kStateBytes + 1] + Xl[left * kStateBytes + 2] + Xl[down * kStateBytes + 3] +
+                      Xl[up * kStateBytes + 4] + Xl[psi * kStateBytes + 5] + Xl[left * kStateBytes + 5];
+        endStamp[psi] = 0;
+    }
+    __syncwarp();
+    for (int k = 0; k < P.nSynopsis; ++k) {
+        const int sz = G >> (k + 1), org = G - 2 * sz;   // sizes G/2, G/4, ...; origins 0, G/2, 3G/4, ...
+        int part = 0;
+        for (int c2 = lane; c2 < 2 * sz * sz; c2 += 32) {
+            const int type = c2 / (sz * sz), cc = c2 - type * sz * sz;
+            part += endOcc[type * GG + (org + cc % sz) + G * (org + cc / sz)];
+        }
+        part = warpSumInt(part);
+        if (lane == 0) S.synNow[(size_t)chain * P.nSynopsis + k] = part;
+    }
+}
+
+// After a sampling launch: settle the lazy per-state accumulators and the sample counts.
+__global__ void sampleEndKernel(DevProblem P, DevChains S) {
+    const int chain = blockIdx.y;
+    const long long nSamp = S.launchSamples[chain];
+    for (int psi = blockIdx.x * blockDim.x + threadIdx.x; psi < P.S; psi += gridDim.x * blockDim.x) {
+        const size_t o = (size_t)chain * P.S + psi;
+        S.endAcc[o] += (long long)S.endOcc[o] * (nSamp - S.endStamp[o]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) S.nSamples[chain] += nSamp;
+}
+
+// ensemble end-state sum: out[psi] += sum over a slice of chains of endAcc[chain][psi] (out zeroed by the caller)
+constexpr int kReduceSlice = 64;
 __global__ void reduceEndStateKernel(DevProblem P, DevChains S) {
     const int psi = blockIdx.x * blockDim.x + threadIdx.x;
     if (psi >= P.S) return;
+    const int c0 = blockIdx.y * kReduceSlice, c1 = min(c0 + kReduceSlice, S.nChains);
     long long acc = 0;
-    for (int c = 0; c < S.nChains; ++c) acc += S.endAcc[(size_t)c * P.S + psi];
-    S.endStateSum[psi] = acc;
+    for (int c = c0; c < c1; ++c) acc += S.endAcc[(size_t)c * P.S + psi];
+    atomicAdd(reinterpret_cast<unsigned long long *>(S.endStateSum) + psi, (unsigned long long)acc);
 }
 
 }  // namespace abm
