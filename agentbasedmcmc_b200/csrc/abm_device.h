@@ -40,6 +40,7 @@ struct DevProblem {
     int nRows, nCols, nEvents, xStride;
     int treeDepth;          // D = bit length of nCols-1
     int t1Len, t2Len;
+    int topShift, nTop;     // nodes whose index is a multiple of 2^topShift (<= 32 of them) are held in shared memory by the step kernel
     int evBytes;            // bytes of the padded event region of Xb = nStates * kStateBytes
     int G, S, T, nStates;   // PredPrey geometry (G == 0: no importance)
     int gShift;             // log2(G) when G is a power of two, else -1

@@ -88,10 +88,13 @@ struct Chain {
     double2 *colRec;
     int8_t *delta;
     double *tier1, *tier2;
+    double *top;      // shared-memory copy of the <= 32 highest nodes (index multiple of 2^topShift) while a step kernel runs
+    int topShift;     // construction kernels hold no copy: top = tier2, topShift = 31 (only node 0 qualifies)
     __device__ __forceinline__ double *node(int i) const {
         if (i & 31) return &colRec[i].y;
         if (i & 1023) return &tier1[i >> 5];
-        return &tier2[i >> 10];
+        if (i & ((1 << topShift) - 1)) return &tier2[i >> 10];
+        return &top[i >> topShift];
     }
 };
 
@@ -155,7 +158,7 @@ __device__ __forceinline__ int warpMax(int v) { return __reduce_max_sync(kFull, 
 
 // Bytes of shared memory one chain (group) needs; must match the carve-up in stepKernel.
 __host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap) {
-    return sCap * 8 + rowsCap * 16 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7);
+    return sCap * 8 + rowsCap * 16 + 32 * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7);
 }
 
 // MODE_SAMPLE, rare path (an accepted proposal changed events of the last timestep): move the end-state occupancy
@@ -226,7 +229,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     double *sG = sDl + P.sCap;                                           // [rowsCap][2] per row: DE' term for a coupled column
                                                                          //   whose flip moves the row by -1 / +1
     double *sNode = sG + 2 * P.rowsCap;                                  // [32] tree nodes of one descent round
-    long long *sSyn = reinterpret_cast<long long *>(sNode + 32);         // [2][8] MODE_SAMPLE: synopsis sum / sum of squares
+    double *sTop = sNode + 32;                                           // [32] the chain's highest tree nodes (root = sTop[0])
+    long long *sSyn = reinterpret_cast<long long *>(sTop + 32);          // [2][8] MODE_SAMPLE: synopsis sum / sum of squares
     int *sU = reinterpret_cast<int *>(sSyn + 16);                        // [sCap] coupled columns, ascending
     int *sXoff = sU + P.sCap;                                            // [rowsCap] Xb offsets of the rows
     uint16_t *sTask = reinterpret_cast<uint16_t *>(sXoff + P.rowsCap);   // [tCap] commit tasks
@@ -238,6 +242,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     ch.delta = S.delta + (size_t)chainC * P.nCols;
     ch.tier1 = S.tier1 + (size_t)chainC * P.t1Len;
     ch.tier2 = S.tier2 + (size_t)chainC * P.t2Len;
+    ch.top = sTop;
+    ch.topShift = P.topShift;
+    // the top of the sum tree lives in shared memory for the whole launch: the root, the first descent round and the
+    // longest ordered sums of every commit never touch global memory
+    for (int k = gl; k < 32; k += W) sTop[k] = (chainValid && k < P.nTop) ? ch.tier2[(k << P.topShift) >> 10] : 0.0;
+    __syncwarp();
     double2 *scratch = S.scratch + (size_t)chainC * P.sCap;
 
     double logImp = chainValid ? S.logImp[chain] : 0.0;
@@ -288,7 +298,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // LW tree levels per memory round trip: lane r fetches the node reached by branch pattern r, then the
         // reference's strict comparisons / subtractions are resolved with shuffles.  A child index >= nCols
         // holds 0.0: "0.0 > target" is false and "target - 0.0" is a no-op, which is the reference's skip.
-        const double root = act ? ch.tier2[0] : 1.0;
+        const double root = act ? sTop[0] : 1.0;
         int j = 0;
         {
             double target = __dmul_rn(u1, root);
@@ -425,7 +435,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             const int descW = warpMax(nDesc);
             if (descW > 5) {
                 // columns with (u & 31) == 0 (one in 32).  Levels 5..9: u + 2^i has its low 5 bits clear and bit i set, so it
-                // is tier1[(u >> 5) + 2^(i-5)]; levels >= 10 likewise are tier2[(u >> 10) + 2^(i-10)].
+                // is tier1[(u >> 5) + 2^(i-5)]; levels >= 10 are tier2 / shared-memory top nodes.
                 const double *t1 = ch.tier1 + (real ? (u >> 5) : 0);
 #pragma unroll
                 for (int i = 0; i < 5; ++i) dn[i] = (5 + i < nDesc && u + (32 << i) < nCols) ? t1[1 << i] : 0.0;
@@ -434,10 +444,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     dsum = __dadd_rn(dsum, dn[i]);
                     ssum = __dadd_rn(ssum, dn[i]);
                 }
-                const double *t2 = ch.tier2 + (real ? (u >> 10) : 0);
-                #pragma unroll 1
+#pragma unroll 1
                 for (int i = 10; i < descW; ++i) {   // one column in 1024
-                    const double t = (i < nDesc && u + (1 << i) < nCols) ? t2[1 << (i - 10)] : 0.0;
+                    const double t = (i < nDesc && u + (1 << i) < nCols) ? *ch.node(u + (1 << i)) : 0.0;
                     dsum = __dadd_rn(dsum, t);
                     ssum = __dadd_rn(ssum, t);
                 }
@@ -675,6 +684,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (act) { ++iter; ++itersDone; }
     }
 
+    __syncwarp();
+    for (int k = gl; k < P.nTop; k += W)
+        if (chainValid) ch.tier2[(k << P.topShift) >> 10] = sTop[k];
     if (MODE == MODE_SAMPLE && chainValid) {   // the lazy accumulators are settled by sampleEndKernel
         if (gl < P.nSynopsis) {
             S.synSum[(size_t)chain * P.nSynopsis + gl] += sSyn[gl];
@@ -740,6 +752,8 @@ __global__ void initColsKernel(DevProblem P, DevChains S) {
     ch.colRec = S.colRec + (size_t)chain * P.nCols;
     ch.tier1 = S.tier1 + (size_t)chain * P.t1Len;
     ch.tier2 = S.tier2 + (size_t)chain * P.t2Len;
+    ch.top = ch.tier2;
+    ch.topShift = 31;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.nCols; j += gridDim.x * blockDim.x) {
         const int dj = delta[j];
         double de = 0.0;
