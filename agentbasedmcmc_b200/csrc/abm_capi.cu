@@ -284,7 +284,10 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         for (int k = 0; k < nEv; ++k)
             if (colRow[colPtr[j] + k] >= nEvents) return fail(ABM_ERR_INVALID, "internal: event rows are not leading");
         if (nChunks >= 65536) return fail(ABM_ERR_INVALID, "too many coupled columns");
-        recIdx[j] = make_int4(int32_t(recStart), n | (int32_t(staleF.size()) << 8) | (C << 16), nChunks | (nEv << 16),
+        bool touchesEnd = false;
+        for (int k = 0; k < nEv; ++k) touchesEnd = touchesEnd || colRow[colPtr[j] + k] >= (T - 1) * S * kActs;
+        recIdx[j] = make_int4(int32_t(recStart), n | (int32_t(staleF.size()) << 8) | (C << 16),
+                              int32_t(uint32_t(nChunks) | (uint32_t(nEv) << 16) | (touchesEnd ? 0x80000000u : 0u)),
                               int32_t(uint32_t(contribWord) | (uint32_t(staleWord) << 16)));
         for (int k = 0; k < n; ++k) {
             const int i = colRow[colPtr[j] + k];

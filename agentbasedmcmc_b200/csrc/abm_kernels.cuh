@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (act) hdr = __ldg(P.recIdx + j);   // {record offset, n | nSF<<8 | C<<16, nChunks, contrib word | stale word << 16}
         const int32_t *__restrict__ rec = P.rec + (size_t)(unsigned)hdr.x * 4;
         const int n = hdr.y & 0xff, nSF = (hdr.y >> 8) & 0xff, C = (hdr.y >> 16) & 0xffff;
-        const int nChunks = hdr.z & 0xffff, nEv = hdr.z >> 16;   // nEv: leading rows that are events (row id < nEvents)
+        const int nChunks = hdr.z & 0xffff, nEv = (hdr.z >> 16) & 0xff;   // nEv: leading rows that are events (row id < nEvents)
+        const bool colTouchesEnd = hdr.z < 0;                              // bit 31: the column has an event row in the last timestep
         const int4 *__restrict__ recRows = reinterpret_cast<const int4 *>(rec);
         const int32_t *__restrict__ chunkHdr = rec + 4 * n;
         const int32_t *__restrict__ slotU = chunkHdr + nChunks;
@@ -662,13 +663,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         __syncwarp();
         if (MODE == MODE_SAMPLE) {
             // events of the last timestep changed by an accepted proposal move the end state
-            bool touchesEnd = false;
-            #pragma unroll 1
-            for (int rb = 0; rb < nW; rb += W) {
-                const int k = rb + gl;
-                if (accept && k < n) { const int xo = sXoff[k]; touchesEnd |= xo >= lastBase && xo < P.evBytes; }
-            }
-            if (__any_sync(kFull, touchesEnd))
+            if (__any_sync(kFull, accept && colTouchesEnd))
                 syn += endStateUpdate(P.G, P.evBytes, P.nSynopsis, lastBase, accept ? n : 0, nW, sXoff, sXX, S.endOcc + (size_t)chainC * P.S,
                                       S.endStamp + (size_t)chainC * P.S, S.endAcc + (size_t)chainC * P.S, nSamp, gl);
             // the do-while at SparseBasisSampler.h:247 hands out the state whenever it is feasible after a step
