@@ -240,7 +240,7 @@ def bench_ours(args):
         tp = ROOT / "profiles" / "dram_bytes_per_chain_step.json"
         if tp.exists():
             tj = json.loads(tp.read_text())
-            if args.workload in tj:
+            if args.workload in tj:   # ncu DRAM bytes per chain-step (measured at 8192 chains) x chain-steps per launch
                 traffic = tj[args.workload] * n_chains * mh
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
