@@ -327,7 +327,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.treeDepth = depth;
     d.t1Len = (nCols + 31) / 32;
     d.t2Len = (nCols + 1023) / 1024;
-    d.topShift = std::max(10, depth - 5);
+    d.topShift = std::max(10, ((depth - 1) / 5) * 5);   // the first descent round's levels
     d.nTop = ((nCols - 1) >> d.topShift) + 1;
     if (d.nTop > 32) return fail(ABM_ERR_INVALID, "internal: too many top tree nodes");
     d.evBytes = evBytes;

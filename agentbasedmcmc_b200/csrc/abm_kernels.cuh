@@ -303,8 +303,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         {
             double target = __dmul_rn(u1, root);
             #pragma unroll 1
-            for (int hi = P.treeDepth - 1; hi >= 0; hi -= 5) {
-                const int lo = max(hi - 4, 0);
+            // rounds are aligned with the storage tiers (levels [0,5), [5,10), [10,15), ...): the 31 candidates of a round
+            // are then contiguous in memory, and the first (partial) round reads the shared-memory top
+            for (int hi = P.treeDepth - 1; hi >= 0;) {
+                const int lo = (hi / 5) * 5;
                 const int nl = hi - lo + 1;
 #pragma unroll
                 for (int k = 0; k < NG; ++k) {   // 31 candidate nodes of this round, 32/W per lane
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     if (vv > target) pref = rc; else target = __dsub_rn(target, vv);
                 }
                 j += pref << lo;
+                hi = lo - 1;
                 __syncwarp();
             }
         }
