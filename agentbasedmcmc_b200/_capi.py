@@ -13,7 +13,7 @@ LIB_PATH = _PKG / "libabmcmc_b200.so"
 SYMBOLS = [
     "abm_last_error", "abm_version", "abm_device_count", "abm_problem_create", "abm_problem_destroy",
     "abm_problem_get_info", "abm_problem_n_synopsis", "abm_chains_create", "abm_chains_destroy", "abm_chains_init",
-    "abm_chains_find_feasible", "abm_chains_step", "abm_chains_step_traced", "abm_chains_sample",
+    "abm_chains_init_from_prior", "abm_chains_find_feasible", "abm_chains_step", "abm_chains_step_traced", "abm_chains_sample",
     "abm_chains_synchronize", "abm_chains_get_state", "abm_chains_get_counters", "abm_chains_get_infeasibility",
     "abm_chains_get_trajectories", "abm_chains_get_statistics", "abm_chains_reset_statistics",
     "abm_chains_record_series", "abm_chains_get_series",
@@ -66,6 +66,7 @@ def load():
     L.abm_chains_create.argtypes = [vp, C.c_int32, C.c_uint64, C.c_uint64, vp, vpp]
     L.abm_chains_destroy.argtypes = [vp]
     L.abm_chains_init.argtypes = [vp, i8p, C.c_int32]
+    L.abm_chains_init_from_prior.argtypes = [vp, f64p, C.c_double, C.c_double, C.c_uint64, i8p]
     L.abm_chains_find_feasible.argtypes = [vp, C.c_int64, f64p, C.c_int64, i64p]
     L.abm_chains_step.argtypes = [vp, C.c_int64]
     L.abm_chains_step_traced.argtypes = [vp, C.c_int64, f64p, i32p, i32p, u8p, i32p]

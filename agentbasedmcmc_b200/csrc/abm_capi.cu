@@ -430,17 +430,11 @@ int abm_chains_synchronize(abm_chains *c) {
     return ABM_OK;
 }
 
-int abm_chains_init(abm_chains *c, const int8_t *initEvents, int32_t nInit) {
-    if (!c || nInit < 0 || (nInit > 0 && !initEvents)) return fail(ABM_ERR_INVALID, "bad argument");
-    CUDA_TRY(cudaSetDevice(c->p->device));
+// constructor kernels on a device-resident initial trajectory (dInit may be null when nInit == 0)
+static int initFromDevice(abm_chains *c, const int8_t *dInit, int32_t nInit) {
     const DevProblem &P = c->p->d;
     DevChains &d = c->d;
     const size_t n = size_t(c->n);
-    int8_t *dInit = nullptr;
-    if (nInit > 0) {
-        CUDA_TRY(cudaMalloc(&dInit, n * nInit));
-        CUDA_TRY(cudaMemcpyAsync(dInit, initEvents, n * nInit, cudaMemcpyHostToDevice, c->stream));
-    }
     CUDA_TRY(cudaMemsetAsync(d.Xb, 0, n * P.xStride, c->stream));
     CUDA_TRY(cudaMemsetAsync(d.infeas, 0, n * sizeof(int32_t), c->stream));
     CUDA_TRY(cudaMemsetAsync(d.logImp, 0, n * sizeof(double), c->stream));
@@ -456,10 +450,53 @@ int abm_chains_init(abm_chains *c, const int8_t *initEvents, int32_t nInit) {
     initColsKernel<<<gridC, threads, 0, c->stream>>>(P, d);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (dInit) CUDA_TRY(cudaFree(dInit));
     c->initialised = true;
     c->feasible = false;
     return ABM_OK;
+}
+
+int abm_chains_init(abm_chains *c, const int8_t *initEvents, int32_t nInit) {
+    if (!c || nInit < 0 || (nInit > 0 && !initEvents)) return fail(ABM_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const size_t n = size_t(c->n);
+    int8_t *dInit = nullptr;
+    if (nInit > 0) {
+        CUDA_TRY(cudaMalloc(&dInit, n * nInit));
+        CUDA_TRY(cudaMemcpyAsync(dInit, initEvents, n * nInit, cudaMemcpyHostToDevice, c->stream));
+    }
+    const int rc = initFromDevice(c, dInit, nInit);
+    if (dInit) cudaFree(dInit);
+    return rc;
+}
+
+int abm_chains_init_from_prior(abm_chains *c, const double *actPmf, double pPredator, double pPrey, uint64_t seed,
+                               int8_t *eventsOut) {
+    if (!c || !actPmf) return fail(ABM_ERR_INVALID, "null argument");
+    const DevProblem &P = c->p->d;
+    if (P.G <= 0) return fail(ABM_ERR_INVALID, "prior sampling needs the PredPrey geometry");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const size_t n = size_t(c->n), bytes = n * size_t(P.nEvents);
+    int8_t *dEvents = nullptr;
+    double *dPmf = nullptr;
+    CUDA_TRY(cudaMalloc(&dEvents, bytes));
+    CUDA_TRY(cudaMalloc(&dPmf, 24 * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(dPmf, actPmf, 24 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const size_t smem = size_t(2) * P.S * sizeof(int);
+    cudaError_t e = cudaFuncSetAttribute(priorSampleKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess) {
+        priorSampleKernel<<<c->n, 128, smem, c->stream>>>(P, c->n, seed, c->firstChain, dPmf, pPredator, pPrey, dEvents);
+        e = cudaGetLastError();
+    }
+    int rc = ABM_OK;
+    if (e != cudaSuccess) rc = fail(ABM_ERR_CUDA, std::string("priorSampleKernel: ") + cudaGetErrorString(e));
+    if (rc == ABM_OK && eventsOut) {
+        e = cudaMemcpyAsync(eventsOut, dEvents, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) rc = fail(ABM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc == ABM_OK) rc = initFromDevice(c, dEvents, P.nEvents);
+    cudaFree(dEvents);
+    cudaFree(dPmf);
+    return rc;
 }
 
 }  // extern "C" (templates below need C++ linkage)

@@ -767,6 +767,64 @@ __global__ void initColsKernel(DevProblem P, DevChains S) {
     }
 }
 
+// Per-chain initial trajectories drawn from the prior, on the device: Forecast::nextSample(startState, T, isFermionic =
+// false) (Forecast.h:102-150) with the Bernoulli start state (BernoulliStartState.h:36-47): every agent state is occupied
+// with its start probability; then, timestep by timestep, every agent draws an act from PredPreyAgent::timestep given
+// the opposite-species occupation of its four neighbours (PredPreyAgent.h:124-157) and its consequences populate the next
+// state (:98-115).  One CTA per chain; uniforms from Philox4x32-10 keyed by (seed, chain) with counter (state, time, agent).
+// Only "event count > 0" matters to the sampler's constructor (SparseBasisSampler.h:147), so events are written as 0/1.
+__global__ void priorSampleKernel(DevProblem P, int nChains, unsigned long long seed, unsigned long long firstChain,
+                                  const double *__restrict__ actPmf /* [2][2][6] */, double pPredator, double pPrey,
+                                  int8_t *__restrict__ events /* [nChains][nEvents] */) {
+    extern __shared__ int priorSmem[];
+    int *cur = priorSmem, *nxt = priorSmem + P.S;
+    const int chain = blockIdx.x;
+    if (chain >= nChains) return;
+    const unsigned long long chainId = firstChain + (unsigned long long)chain;
+    const int G = P.G, GG = G * G;
+    int8_t *ev = events + (size_t)chain * P.nEvents;
+    for (int e = threadIdx.x; e < P.nEvents; e += blockDim.x) ev[e] = 0;
+    for (int psi = threadIdx.x; psi < P.S; psi += blockDim.x) {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)psi, 0xffffffffu, (uint32_t)chainId, (uint32_t)(chainId >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), w);
+        cur[psi] = canonical_from_words(w[0], w[1]) < (psi < GG ? pPredator : pPrey) ? 1 : 0;   // type 0 = PREDATOR (PredPreyAgent.h:27-30)
+        nxt[psi] = 0;
+    }
+    __syncthreads();
+    for (int t = 0; t < P.T; ++t) {
+        for (int psi = threadIdx.x; psi < P.S; psi += blockDim.x) {
+            const int nAgents = cur[psi];
+            if (nAgents == 0) continue;
+            const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG, ob = (1 - type) * GG;
+            const int xl = cx == 0 ? G - 1 : cx - 1, xr = cx == G - 1 ? 0 : cx + 1, yu = cy == G - 1 ? 0 : cy + 1, yd = cy == 0 ? G - 1 : cy - 1;
+            const bool nb = cur[ob + xr + G * cy] + cur[ob + xl + G * cy] + cur[ob + cx + G * yu] + cur[ob + cx + G * yd] >= 1;
+            const double *pmf = actPmf + (type * 2 + (nb ? 1 : 0)) * kActs;
+            for (int a = 0; a < nAgents; ++a) {
+                uint32_t w[4];
+                philox4x32_10((uint32_t)psi, (uint32_t)(t * 4096 + a), (uint32_t)chainId, (uint32_t)(chainId >> 32), (uint32_t)seed,
+                              (uint32_t)(seed >> 32), w);
+                const double u = canonical_from_words(w[0], w[1]);
+                int act = kActs - 1;
+                double cum = 0.0;
+                for (int k = 0; k < kActs; ++k) {
+                    cum += pmf[k];
+                    if (u < cum) { act = k; break; }
+                }
+                ev[((size_t)t * P.S + psi) * kActs + act] = 1;
+                // consequences (PredPreyAgent.h:98-115): DIE -> none, moves -> the neighbour cell, GIVEBIRTH -> self + right
+                if (act == 1) atomicAdd(&nxt[tb + xl + G * cy], 1);
+                else if (act == 2) atomicAdd(&nxt[tb + xr + G * cy], 1);
+                else if (act == 3) atomicAdd(&nxt[tb + cx + G * yu], 1);
+                else if (act == 4) atomicAdd(&nxt[tb + cx + G * yd], 1);
+                else if (act == 5) { atomicAdd(&nxt[psi], 1); atomicAdd(&nxt[tb + xr + G * cy], 1); }
+            }
+        }
+        __syncthreads();
+        for (int psi = threadIdx.x; psi < P.S; psi += blockDim.x) { cur[psi] = nxt[psi]; nxt[psi] = 0; }
+        __syncthreads();
+    }
+}
+
 // importanceFunc->setState(X); currentLogImportance = getLogValue(X) (:183-184; TrajectoryImportance.h:116-140):
 // factors are added in (t, psi) order, one warp per chain, 32 states per round.
 __global__ void setStateKernel(DevProblem P, DevChains S) {

@@ -91,7 +91,10 @@ class SparseBasisSampler:
     """``n_chains`` SparseBasisSampler chains on one GPU (reference: one object == one chain)."""
 
     def __init__(self, problem: Problem, initial_states=None, n_chains: int | None = None, seed: int = 0,
-                 first_chain_id: int = 0, stream=None, find_feasible: bool = True):
+                 first_chain_id: int = 0, stream=None, find_feasible: bool = True, prior_init: bool = False,
+                 return_prior_sample: bool = False):
+        """initial_states: [n_chains][n_events] int8 (or one row), or None.  prior_init=True draws one initial
+        trajectory per chain from the prior on the device (`prior.nextSample(false)`, FiguresForPaper.h:56)."""
         L = _capi.load()
         self.problem = problem
         if initial_states is not None:
@@ -108,8 +111,17 @@ class SparseBasisSampler:
         h = C.c_void_p()
         check(L.abm_chains_create(problem.h, n_chains, seed, first_chain_id, C.c_void_p(stream or 0), C.byref(h)))
         self.h = h
-        n_init = 0 if initial_states is None else initial_states.shape[1]
-        check(L.abm_chains_init(self.h, _ptr(initial_states, C.c_int8), n_init))
+        self.prior_sample = None
+        if prior_init:
+            a = problem.abmp
+            pmf = np.ascontiguousarray(a["pp_actpmf"], dtype=np.float64)
+            if return_prior_sample:
+                self.prior_sample = np.zeros((n_chains, problem.n_events), np.int8)
+            check(L.abm_chains_init_from_prior(self.h, _ptr(pmf, C.c_double), float(a["pp_params"][0]), float(a["pp_params"][1]),
+                                               seed ^ 0x5DEECE66D, _ptr(self.prior_sample, C.c_int8)))
+        else:
+            n_init = 0 if initial_states is None else initial_states.shape[1]
+            check(L.abm_chains_init(self.h, _ptr(initial_states, C.c_int8), n_init))
         self.init_iterations = None
         if find_feasible:
             self.findInitialFeasibleSolution()

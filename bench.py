@@ -181,7 +181,9 @@ def bench_ours(args):
     stream = torch.cuda.current_stream()
     t_setup = time.time()
     P = S.Problem(abmp, device=local_rank)
-    smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=args.seed, first_chain_id=rank * n_chains, stream=stream.cuda_stream)
+    # every chain starts from its own prior sample, as FiguresForPaper.h:56 / :162 do (drawn on the device)
+    smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=args.seed, first_chain_id=rank * n_chains, stream=stream.cuda_stream,
+                               prior_init=True)
     setup_s = time.time() - t_setup
 
     def barrier():
@@ -246,7 +248,7 @@ def bench_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "chains_per_gpu": n_chains, "mh_steps_per_launch": mh, "rng": "philox4x32-10",
+            "config": {"workload": desc, "chains_per_gpu": n_chains, "mh_steps_per_launch": mh, "rng": "philox4x32-10", "initial_states": "one prior sample per chain, drawn on the device",
                        "l2_policy": f"per-GPU chain state {P.info.chain_state_bytes * n_chains / 1e9:.1f} GB >> 126 MB L2 (inputs larger than L2)",
                        "problem": "reference generator seed 1234, kappa 10 (tests/golden)", "setup_seconds": round(setup_s, 1),
                        "acceptance": round(st.totalAccepted() / max(st.nSamples(), 1), 4),

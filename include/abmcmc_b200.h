@@ -98,6 +98,14 @@ ABM_API int abm_chains_destroy(abm_chains *c);
  * init_events: host, [n_chains][n_init] int8 (n_init may be 0: all delta = +1). */
 ABM_API int abm_chains_init(abm_chains *c, const int8_t *init_events, int32_t n_init);
 
+/* Same, with one initial trajectory per chain drawn on the device from the prior: Forecast::nextSample(startState, T,
+ * isFermionic = false) with the Bernoulli start state (Forecast.h:102-150, BernoulliStartState.h:36-47), which is what
+ * FiguresForPaper.h:56,162 hands to every chain.  act_pmf = PredPreyAgent::timestep by (type, has opposite-species
+ * neighbour, act) ([2][2][6], ABMP array pp_actpmf); Philox streams keyed by (seed, chain).  events_out (host,
+ * [n_chains][n_events], may be NULL) receives the drawn trajectories as 0/1. */
+ABM_API int abm_chains_init_from_prior(abm_chains *c, const double *act_pmf, double p_predator, double p_prey, uint64_t seed,
+                                       int8_t *events_out);
+
 /* findInitialFeasibleSolution (:254-263) + importanceFunc->setState / getLogValue (:183-184).
  * Uniforms: Philox unless `uniforms` (host, [n_chains][n_uniforms], one per iteration) is given.
  * iterations_out (host, [n_chains], may be NULL) receives the per-chain iteration count. */

@@ -107,7 +107,7 @@ template <class AGENT>
 void flattenPredPreyImportance(AbmpFile &out, int gridSize, int nTimesteps) {
     std::vector<double> lg(AGENT::actDomainSize() + 1, 0.0);
     for (int occ = 0; occ <= AGENT::actDomainSize(); ++occ) lg[occ] = (occ > 1) ? lgamma(occ + 1.0) : 0.0;
-    std::vector<double> ratio(2 * 2 * AGENT::actDomainSize(), 0.0);
+    std::vector<double> ratio(2 * 2 * AGENT::actDomainSize(), 0.0), actPmf(2 * 2 * AGENT::actDomainSize(), 0.0);
     for (int type = 0; type < 2; ++type) {
         AGENT agent(0, 0, typename AGENT::Type(type));
         for (int flag = 0; flag < 2; ++flag) {
@@ -118,6 +118,7 @@ void flattenPredPreyImportance(AbmpFile &out, int gridSize, int nTimesteps) {
                 double r = 0.0;  // "+= 0.0" is what skipping the term amounts to (TrajectoryImportance.h:105)
                 if (pmf[act] > 0.0) r = log(pmf[act] / agent.marginalTimestep(act));
                 ratio[(type * 2 + flag) * AGENT::actDomainSize() + act] = r;
+                actPmf[(type * 2 + flag) * AGENT::actDomainSize() + act] = pmf[act];   // for prior sampling (Forecast.h:102-150)
             }
         }
     }
@@ -125,6 +126,7 @@ void flattenPredPreyImportance(AbmpFile &out, int gridSize, int nTimesteps) {
                           AGENT::domainSize(), AGENT::actDomainSize()};
     out.f64["imp_lgamma"] = lg;
     out.f64["imp_logratio"] = ratio;
+    out.f64["pp_actpmf"] = actPmf;
 }
 
 }  // namespace abmcmc

@@ -522,6 +522,12 @@ static int run(int argc, char **argv) {
         return 2;
     }
     std::string cmd = argv[1];
+    if (cmd == "actpmf") {   // the act pmf table of PredPreyAgent::timestep by (type, has-neighbour, act); grid independent
+        AbmpFile f;
+        abmcmc::flattenPredPreyImportance<PredPreyAgent<8>>(f, 8, 1);
+        for (double v : f.D("pp_actpmf")) printf("%.17g\n", v);
+        return 0;
+    }
     if (cmd == "gen") {
         int g = atoi(argv[2]), T = atoi(argv[3]), seed = atoi(argv[4]);
         double kappa = atof(argv[5]);

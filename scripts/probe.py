@@ -22,7 +22,7 @@ def main():
     print(f"problem: rows={P.n_rows} cols={P.n_cols} maxCoupled={P.info.max_coupled} shared={P.info.shared_bytes/1e6:.1f}MB "
           f"chain={P.info.chain_state_bytes/1e6:.3f}MB build={time.time()-t0:.2f}s", flush=True)
     t0 = time.time()
-    smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=1)
+    smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=1, prior_init="--empty-init" not in sys.argv)
     dt = time.time() - t0
     it = smp.init_iterations
     print(f"init: {dt:.2f}s, iterations mean={it.mean():.0f} max={it.max()} -> {it.sum()/dt/1e6:.2f} M it/s", flush=True)

@@ -37,6 +37,16 @@ def main():
         raw = tmp / f"trace_{name}_{s1}.abmp"
         subprocess.run([str(REF), "trace", str(tmp / f"{name}.abmp"), str(s0), str(s1), str(n), str(every), str(raw)], check=True)
         xz(raw, HERE / f"trace_{name}_{s1}.abmp.xz")
+    # prior samples (prior.nextSample(false), FiguresForPaper.h:56): per (t, type, act) mean of [event > 0] over 20000 draws
+    import numpy as np
+    sys.path.insert(0, str(HERE.parent.parent))
+    from agentbasedmcmc_b200.abmp import write_abmp
+    raw = tmp / "prior8-4.i8"
+    subprocess.run([str(REF), "init", str(tmp / "pp8-4.abmp"), "20000", "4711", str(raw)], check=True)
+    x = np.fromfile(raw, dtype=np.int8).reshape(20000, 4, 2, 64, 6)
+    write_abmp(HERE / "prior_pp8-4.abmp.xz", {"mean_indicator": (x > 0).mean(axis=(0, 3)).ravel(),
+                                              "mean_count": x.astype(np.float64).mean(axis=(0, 3)).ravel(),
+                                              "n": np.array([20000, 64], np.int32)})
     # long reference chains for posterior marginals (64 chains x 60000 feasible samples after 60000 burn-in)
     raw = tmp / "marginals_pp8-4.abmp"
     subprocess.run([str(REF), "marginals", str(tmp / "pp8-4.abmp"), "64", "60000", "60000", str(raw)], check=True)

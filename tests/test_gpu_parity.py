@@ -194,3 +194,30 @@ def test_posterior_marginals_match_reference_long_run():
     acc = c[4:].sum() / c[:4].sum()
     assert abs(acc - 0.834) < 0.02
     assert np.all(np.isfinite(summ.rhat)) and np.all(summ.rhat > 0.99)   # 1500 correlated samples per chain: R-hat is well above 1
+
+
+def test_device_prior_initial_states_match_reference_prior():
+    """abm_chains_init_from_prior draws `prior.nextSample(false)` (Forecast.h:102-150) per chain on the device.  Checked
+    statistically against 20000 draws of the reference (tests/golden/prior_pp8-4, `abm_ref init`): for every
+    (timestep, species, act) the probability that an event is set, within 5 binomial standard errors + 2e-4."""
+    S = _gpu()
+    p, ref = load_golden("pp8-4.abmp.xz"), load_golden("prior_pp8-4.abmp.xz")
+    n_chains = 8192
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=13, prior_init=True, return_prior_sample=True)
+    ev = smp.prior_sample.reshape(n_chains, 4, 2, 64, 6)
+    assert set(np.unique(ev)) <= {0, 1}
+    got = ev.mean(axis=(0, 3)).ravel()
+    want = ref["mean_indicator"]
+    n_ref, n_gpu = 20000 * 64, n_chains * 64
+    se = np.sqrt(want * (1 - want) * (1.0 / n_ref + 1.0 / n_gpu))
+    assert np.all(np.abs(got - want) <= 5 * se + 2e-4), (got - want) / np.maximum(se, 1e-12)
+    # chains start from different trajectories and all reach feasibility
+    assert len({ev[c].tobytes() for c in range(64)}) > 60
+    assert np.all(smp.infeasibility() == 0)
+    # delta reflects the drawn trajectory (SparseBasisSampler.h:147) before the feasibility search moves it: re-init only
+    smp2 = S.SparseBasisSampler(P, n_chains=4, seed=13, prior_init=True, return_prior_sample=True, find_feasible=False)
+    nb_col = p["nb_col"]
+    for c in range(4):
+        delta = smp2.state(c)[1]
+        assert np.array_equal(delta == -1, smp2.prior_sample[c][nb_col] > 0)
