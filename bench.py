@@ -233,6 +233,31 @@ def bench_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = steps_done / float(te.item())
 
+    # ---- ESS/s (the second half of BASELINE.json's metric): reference formula (MultiChainStats::effectiveSamples,
+    # diagnostics/MultiChainStats.h:81-102) on the synopsis series of the first `ess_chains` chains of rank 0, each a
+    # sequence; chains are i.i.d., so the ensemble's effective sample size is the per-chain one times the chain count.
+    ess = None
+    if args.ess_samples > 0 and rank == 0:
+        from agentbasedmcmc_b200 import diagnostics as D
+        k = min(args.ess_chains, n_chains)
+        smp.reset_statistics()
+        smp.record_series(k, 1, args.ess_samples)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        smp.sample(args.ess_samples, max_steps=4 * args.ess_samples)   # bounded: a chain deep in the infeasible region must not stall the batch
+        smp.synchronize()
+        ess_s = time.perf_counter() - t0
+        n_rec = int(min(smp.statistics()[3][:k].min(), args.ess_samples))
+        series = smp.series().astype(np.float64)[:, :n_rec]
+        ms = D.MultiChainStats([D.ChainStats.from_series(series[c], n_lags=200, max_lag_proportion=0.5) for c in range(k)])
+        neff = ms.effective_samples(reference_integer_division=False)
+        per_chain = neff / k
+        ess = {"value": float(per_chain.min() * n_chains * world / ess_s), "unit": "effective samples/s (worst synopsis statistic, all chains)",
+               "n_eff_per_chain": [round(float(x), 2) for x in per_chain], "feasible_samples_per_chain": n_rec,
+               "sequences_analysed": k, "seconds": round(ess_s, 3),
+               "rhat": [round(float(x), 4) for x in ms.potential_scale_reduction(reference_integer_division=False)]}
+    barrier()
+
     st = smp.stats
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -264,6 +289,7 @@ def bench_ours(args):
             "ensemble": {"chains": summary.n_chains, "feasible_samples": summary.n_samples,
                          "mean_agents_at_T": float(summary.end_state_mean.sum()),
                          "rhat_synopsis": [round(float(x), 4) for x in summary.rhat]},
+            "ess": ess,
             "gpu_launches": args.steps,
             "clocks": clocks.summary(),
         }
@@ -286,6 +312,8 @@ def main():
     ap.add_argument("--mh-steps", type=int, default=500, help="Metropolis steps per chain per launch")
     ap.add_argument("--seed", type=int, default=20221)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ess-samples", type=int, default=10000, help="feasible samples per chain for the ESS/s estimate (0 = skip)")
+    ap.add_argument("--ess-chains", type=int, default=64, help="chains whose synopsis series are analysed for ESS/s")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
