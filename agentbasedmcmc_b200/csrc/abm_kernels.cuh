@@ -308,12 +308,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             for (int hi = P.treeDepth - 1; hi >= 0;) {
                 const int lo = (hi / 5) * 5;
                 const int nl = hi - lo + 1;
+                // all candidates of a round live in one storage tier (their lowest set bit is in [lo, lo + 5))
+                const double *base = &ch.colRec[0].y;
+                int sh = 0, mul = 2;
+                if (lo >= P.topShift) { base = sTop; sh = P.topShift; mul = 1; }
+                else if (lo >= 10) { base = ch.tier2; sh = 10; mul = 1; }
+                else if (lo >= 5) { base = ch.tier1; sh = 5; mul = 1; }
 #pragma unroll
                 for (int k = 0; k < NG; ++k) {   // 31 candidate nodes of this round, 32/W per lane
                     const int r = gl + W * k;
                     const int c = j + (r << lo);
                     double v = 0.0;
-                    if (act && r > 0 && r < (1 << nl) && c < nCols) v = *ch.node(c);
+                    if (act && r > 0 && r < (1 << nl) && c < nCols) v = base[(c >> sh) * mul];
                     sNode[r] = v;
                 }
                 __syncwarp();
