@@ -65,7 +65,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.t.start()
@@ -309,7 +309,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pp32-16", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
-    ap.add_argument("--mh-steps", type=int, default=500, help="Metropolis steps per chain per launch")
+    ap.add_argument("--mh-steps", type=int, default=2000, help="Metropolis steps per chain per launch")
     ap.add_argument("--seed", type=int, default=20221)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ess-samples", type=int, default=10000, help="feasible samples per chain for the ESS/s estimate (0 = skip)")

@@ -1,0 +1,92 @@
+"""Edge cases of the C-ABI path on the GPU: ragged chain counts (groups / warps / CTAs only partly filled), a problem
+without importance function, call-order and argument errors, unsupported problems rejected loudly."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _S():
+    from agentbasedmcmc_b200 import sampler
+    return sampler
+
+
+@pytest.mark.parametrize("n_chains", [1, 3, 17, 33])
+def test_ragged_chain_counts_match_oracle(n_chains):
+    from oracle.oracle import OracleChain, OracleProblem
+    S = _S()
+    p = load_golden("pp8-4.abmp.xz")
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=5, first_chain_id=7)
+    j, acc, inf = smp.step_traced(400)
+    OP = OracleProblem(p)
+    for c in sorted({0, n_chains // 2, n_chains - 1}):
+        oc = OracleChain(OP)
+        oc.seed_philox(5, 7 + c)
+        assert oc.find_feasible() == int(smp.init_iterations[c])
+        oj, oacc, oinf = oc.step(400, trace=True)
+        assert np.array_equal(j[c], oj) and np.array_equal(acc[c], oacc) and np.array_equal(inf[c], oinf)
+        assert np.array_equal(smp.state(c)[0], oc.X)
+
+
+def test_without_importance_function():
+    """grid_size == 0: log W == 0 (a plain FactoredConvexDistribution); decisions follow the ratio of sums alone."""
+    from oracle.oracle import OracleChain, OracleProblem
+    S = _S()
+    p = load_golden("pp8-4.abmp.xz")
+    P = S.Problem(p, with_importance=False)
+    smp = S.SparseBasisSampler(P, n_chains=4, seed=11)
+    j, acc, inf = smp.step_traced(1500)
+    OP = OracleProblem(p, with_importance=False)
+    for c in range(4):
+        oc = OracleChain(OP)
+        oc.seed_philox(11, c)
+        oc.find_feasible()
+        oj, oacc, oinf = oc.step(1500, trace=True)
+        assert np.array_equal(j[c], oj) and np.array_equal(acc[c], oacc)
+        assert smp.state(c)[4] == 0.0
+
+
+def test_errors_are_reported_not_swallowed():
+    S = _S()
+    p = load_golden("pp8-4.abmp.xz")
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, n_chains=2, seed=1, find_feasible=False)
+    with pytest.raises(S.AbmError, match="feasible"):
+        smp.step(10)                                    # stepping before findInitialFeasibleSolution
+    with pytest.raises(S.AbmError):
+        smp.state(5)                                    # chain index out of range
+    with pytest.raises(S.AbmError, match="iteration limit"):
+        smp.findInitialFeasibleSolution(max_iterations=3)
+    smp.findInitialFeasibleSolution()                   # and the search can be resumed afterwards
+    assert np.all(smp.infeasibility() == 0)
+    # tableau entries other than +-1 (e.g. the reference's CatMouse agent) are rejected, not mis-sampled
+    bad = dict(p)
+    bad["nb_val"] = p["nb_val"].copy()
+    bad["nb_val"][0] = 2
+    with pytest.raises(S.AbmError, match=r"\+-1"):
+        S.Problem(bad)
+    # a factor table that does not cover its row's reachable range
+    bad = dict(p)
+    bad["ut_off"] = p["ut_off"].copy()
+    bad["ut_off"][1:] -= 1
+    bad["ut_off"] = np.maximum(bad["ut_off"], 0)
+    with pytest.raises(S.AbmError):
+        S.Problem(bad)
+
+
+def test_sample_is_bounded_by_max_steps_and_counts_only_feasible_states():
+    S = _S()
+    p = load_golden("pp16-8.abmp.xz")
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, n_chains=64, seed=2, prior_init=True)
+    smp.sample(10 ** 9, max_steps=300)
+    end, ss, sq, ns = smp.statistics()
+    ctr = smp.counters()
+    assert np.all(ctr[:, :4].sum(axis=1) == 300)        # exactly max_steps Metropolis steps per chain
+    # feasible-ending steps (MCMCStatistics::nFeasibleSamples, MCMCStatistics.cpp:40-42) == samples taken
+    feas = ctr[:, 3] + ctr[:, 4 + 1] + (ctr[:, 2] - ctr[:, 4 + 2])
+    assert np.array_equal(ns, feas)
+    assert end.sum() > 0 and np.all(sq >= 0)
