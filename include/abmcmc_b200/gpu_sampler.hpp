@@ -93,6 +93,7 @@ public:
         nRows_ = info.n_rows;
         nCols_ = info.n_cols;
         init_.assign(initialState.begin(), initialState.end());
+        actPmf_ = f.D("pp_actpmf");
         // the reference constructs one chain here, including findInitialFeasibleSolution() on Random::gen (:181)
         createChains(1, 0, /*exact=*/true);
     }
@@ -134,6 +135,16 @@ public:
 
     // ---- batched use: nChains independent chains from the same initial state on Philox streams (seed, chain)
     void batched(int nChains, uint64_t seed) { createChains(nChains, seed, /*exact=*/false); }
+    // ... or each chain from its own prior sample drawn on the device (what FiguresForPaper.h:56 gives every chain);
+    // pPredator / pPrey are the Bernoulli start-state probabilities of the problem (PredPreyProblem.h:36-37)
+    void batchedFromPrior(int nChains, uint64_t seed, double pPredator, double pPrey) {
+        if (chains_) { abm_chains_destroy(chains_); chains_ = nullptr; }
+        nChains_ = nChains;
+        detail::check(abm_chains_create(problem_, nChains, seed, 0, nullptr, &chains_), "abm_chains_create");
+        detail::check(abm_chains_init_from_prior(chains_, actPmf_.data(), pPredator, pPrey, seed ^ 0x5DEECE66Dull, nullptr), "abm_chains_init_from_prior");
+        detail::check(abm_chains_find_feasible(chains_, 0, nullptr, 0, nullptr), "abm_chains_find_feasible");
+        refresh();
+    }
     void step(int64_t nSteps) { detail::check(abm_chains_step(chains_, nSteps), "abm_chains_step"); }
     void sample(int64_t nSamples, int64_t maxSteps = 0) { detail::check(abm_chains_sample(chains_, nSamples, maxSteps), "abm_chains_sample"); }
     void synchronize() { detail::check(abm_chains_synchronize(chains_), "abm_chains_synchronize"); }
@@ -145,6 +156,7 @@ private:
     abm_chains *chains_ = nullptr;
     int nRows_ = 0, nCols_ = 0, nChains_ = 0;
     std::vector<int8_t> init_;
+    std::vector<double> actPmf_;
 
     void createChains(int nChains, uint64_t seed, bool exact) {
         if (chains_) { abm_chains_destroy(chains_); chains_ = nullptr; }
