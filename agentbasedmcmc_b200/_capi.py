@@ -34,6 +34,7 @@ class ProblemDesc(C.Structure):
         ("ut_val", C.POINTER(C.c_double)), ("kappa", C.c_double),
         ("grid_size", C.c_int32), ("n_timesteps", C.c_int32),
         ("imp_lgamma", C.POINTER(C.c_double)), ("imp_logratio", C.POINTER(C.c_double)),
+        ("sum_tree", C.c_int32),
     ]
 
 

@@ -184,7 +184,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     std::vector<int4> recIdx(nCols);
     std::vector<int32_t> rec;
     rec.reserve((size_t)nnz * 24);
-    int maxCoupled = 1, maxTasks = 1, maxSF = 0, maxTA = 1, maxTB = 1, maxTC = 1;
+    int maxCoupled = 1, maxTasks = 1, maxSF = 0, maxTA = 1, maxTB = 1, maxTC = 1, maxBlkTasks = 1;
     struct Pair { int u, k, m; };
     std::vector<Pair> pairs;
     std::vector<int32_t> slotU, chunkHdr, staleF, nodes;
@@ -215,6 +215,13 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         const int C = int(slotU.size());
         const int nChunks = (C + W - 1) / W;
         maxCoupled = std::max(maxCoupled, C);
+        {
+            int blk = 0;
+            for (int l = 0; l < C; ++l)
+                for (int b = 5; b <= 15; b += 5)
+                    if (l == 0 || (slotU[l - 1] >> b) != (slotU[l] >> b)) ++blk;
+            maxBlkTasks = std::max(maxBlkTasks, blk);
+        }
         slotU.resize(size_t(nChunks) * W, -1);
         chunkHdr.assign(nChunks, 0);
         contrib.clear();
@@ -332,6 +339,9 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     if (d.nTop > 32) return fail(ABM_ERR_INVALID, "internal: too many top tree nodes");
     d.evBytes = evBytes;
     d.G = G; d.S = S; d.T = T; d.nStates = nStates;
+    d.blockedTree = desc->sum_tree == ABM_TREE_REFERENCE ? 0 : 1;
+    if (const char *e = getenv("ABM_TREE")) d.blockedTree = std::string(e) != "reference";
+    if (d.blockedTree && nCols > (1 << 20)) return fail(ABM_ERR_INVALID, "blocked tree supports up to 2^20 columns");
     d.gShift = -1;
     for (int k = 0; k < 30; ++k) if (G == (1 << k)) d.gShift = k;
     d.groupWidth = W;
@@ -340,6 +350,10 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.tCapA = (maxTA + 7) & ~7;
     d.tCapB = (maxTB + 7) & ~7;
     d.tCap = d.tCapA + d.tCapB + ((maxTC + 7) & ~7);
+    if (d.blockedTree) {   // levels 10/15 go to the first region, level 5 to the second; either can hold every task
+        d.tCapA = d.tCapB = (maxBlkTasks + 7) & ~7;
+        d.tCap = std::max(d.tCap, 2 * d.tCapA + 8);
+    }
     if (maxTA > 1000 || maxTB > 1000 || maxTC > 1000) return fail(ABM_ERR_INVALID, "too many sum-tree nodes touched by one column");
     int nSyn = 0;
     for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
@@ -399,7 +413,7 @@ int abm_chains_create(const abm_problem *p, int32_t nChains, uint64_t seed, uint
     cudaError_t e = cudaSuccess;
     auto al = [&](auto **dst, size_t count) { if (e == cudaSuccess) e = c->arena.alloc(dst, count); };
     al(&d.Xb, n * P.xStride); al(&d.colRec, n * P.nCols); al(&d.delta, n * P.nCols);
-    al(&d.tier1, n * P.t1Len); al(&d.tier2, n * P.t2Len);
+    al(&d.tier1, n * P.t1Len); al(&d.tier2, n * P.t2Len); al(&d.tier3, n * 32);
     al(&d.logImp, n); al(&d.infeas, n); al(&d.iter, n); al(&d.counters, n * 8);
     al(&d.scratch, n * P.sCap);
     al(&d.endStateSum, size_t(std::max(P.S, 1))); al(&d.synSum, n * std::max(P.nSynopsis, 1));
@@ -442,6 +456,7 @@ static int initFromDevice(abm_chains *c, const int8_t *dInit, int32_t nInit) {
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, n * 8 * sizeof(long long), c->stream));
     CUDA_TRY(cudaMemsetAsync(d.tier1, 0, n * P.t1Len * sizeof(double), c->stream));
     CUDA_TRY(cudaMemsetAsync(d.tier2, 0, n * P.t2Len * sizeof(double), c->stream));
+    CUDA_TRY(cudaMemsetAsync(d.tier3, 0, n * 32 * sizeof(double), c->stream));
     { int rc = zeroStatistics(c); if (rc != ABM_OK) return rc; }
     const int threads = 256;
     dim3 gridC(std::min((P.nCols + threads - 1) / threads, 64), c->n), gridR(std::min((P.nRows + threads - 1) / threads, 64), c->n);
@@ -501,17 +516,22 @@ int abm_chains_init_from_prior(abm_chains *c, const double *actPmf, double pPred
 
 }  // extern "C" (templates below need C++ linkage)
 
-template <int MODE, int W>
-static cudaError_t launchStepW(const abm_chains *c, const RunParams &r) {
+template <int MODE, int W, bool BLK>
+static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
     const DevProblem &P = c->p->d;
     constexpr int NG = 32 / W;
     const int chainsPerCta = kWarpsPerCta * NG;
     const int grid = (c->n + chainsPerCta - 1) / chainsPerCta;
     const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap);
-    cudaError_t e = cudaFuncSetAttribute(stepKernel<MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(stepKernel<MODE, W, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    stepKernel<MODE, W><<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);
+    stepKernel<MODE, W, BLK><<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);
     return cudaGetLastError();
+}
+
+template <int MODE, int W>
+static cudaError_t launchStepW(const abm_chains *c, const RunParams &r) {
+    return c->p->d.blockedTree ? launchStepWB<MODE, W, true>(c, r) : launchStepWB<MODE, W, false>(c, r);
 }
 
 template <int MODE>
@@ -706,7 +726,17 @@ int abm_chains_get_state(abm_chains *c, int32_t chain, int32_t *X, int8_t *delta
         CUDA_TRY(cudaMemcpy(t2.data(), c->d.tier2 + ch * P.t2Len, sizeof(double) * P.t2Len, cudaMemcpyDeviceToHost));
         for (int j = 0; j < P.nCols; ++j) {
             if (currentDE) currentDE[j] = cr[j].x;
-            if (tree) tree[j] = (j & 31) ? cr[j].y : ((j & 1023) ? t1[j >> 5] : t2[j >> 10]);
+            if (tree && !P.blockedTree) tree[j] = (j & 31) ? cr[j].y : ((j & 1023) ? t1[j >> 5] : t2[j >> 10]);
+        }
+        if (tree && P.blockedTree) {
+            // the blocked tree stores leaves; present them in the reference's node layout (node i = sum of the leaves in
+            // [i, i + lowbit(i)), MutableCategoricalArray.h:9-24), each node summed directly from its leaves
+            for (int j = 0; j < P.nCols; ++j) {
+                const int span = j ? (j & -j) : P.nCols;
+                double v = 0.0;
+                for (int k = std::min(j + span, P.nCols) - 1; k >= j; --k) v += cr[k].y;
+                tree[j] = v;
+            }
         }
     }
     if (logImportance) CUDA_TRY(cudaMemcpy(logImportance, c->d.logImp + ch, sizeof(double), cudaMemcpyDeviceToHost));

@@ -44,6 +44,7 @@ struct DevProblem {
     int evBytes;            // bytes of the padded event region of Xb = nStates * kStateBytes
     int G, S, T, nStates;   // PredPrey geometry (G == 0: no importance)
     int gShift;             // log2(G) when G is a power of two, else -1
+    int blockedTree;        // 1: 32-ary blocked sum tree (colRec.y = leaf p_u), 0: the reference's binary sum tree
     int groupWidth;         // W
     int rowsCap, sCap, tCap;   // per-chain shared-memory capacities: rows, coupled columns, commit tasks
     int tCapA, tCapB;          // task-list regions: levels >= 10, levels 5..9 (the rest of tCap: levels < 5)
@@ -67,6 +68,7 @@ struct DevChains {
     double2 *colRec;
     int8_t *delta;
     double *tier1, *tier2;
+    double *tier3;           // [nChains][32] blocked tree: sums of 32768 leaves
     double *logImp;          // currentLogImportance (:50)
     int32_t *infeas;         // currentInfeasibility (:49)
     unsigned long long *iter;   // Philox counter: iterations (init + MH) done so far

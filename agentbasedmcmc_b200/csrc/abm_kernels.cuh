@@ -156,6 +156,42 @@ __device__ __forceinline__ int groupInclusiveScan(int v, int gl) {
 }
 __device__ __forceinline__ int warpMax(int v) { return __reduce_max_sync(kFull, v); }
 
+// Blocked sum tree: one 32-ary level.  32 entries are spread over the W lanes of a group (lane gl holds entries gl*NG ..
+// gl*NG+NG-1); they are consumed from the highest index down: entry e owns [sum_{e'>e} v, sum_{e'>=e} v).  Returns the
+// entry that owns `target` and rebases target to the start of that entry's interval.
+template <int W>
+__device__ __forceinline__ int selectDescending(const double (&v)[32 / W], double &target, int gl) {
+    constexpr int NG = 32 / W;
+    double own = 0.0;
+#pragma unroll
+    for (int k = NG - 1; k >= 0; --k) own = __dadd_rn(own, v[k]);
+    double sfx = own;   // inclusive suffix sum over lanes >= gl
+#pragma unroll
+    for (int o = 1; o < W; o <<= 1) {
+        const double t = __shfl_down_sync(kFull, sfx, o, W);
+        if (gl + o < W) sfx = __dadd_rn(sfx, t);
+    }
+    const double aboveRaw = __shfl_down_sync(kFull, sfx, 1, W);
+    const double above = gl + 1 < W ? aboveRaw : 0.0;             // entries held by higher lanes
+    const unsigned hits = (__ballot_sync(kFull, target < sfx) >> ((threadIdx.x & 31) & ~(W - 1))) & (W == 32 ? 0xffffffffu : ((1u << W) - 1u));
+    const int winner = hits ? 31 - __clz(hits) : 0;               // highest lane whose suffix exceeds the target
+    int e = gl * NG;                                               // rounding fallback: the lane's lowest entry
+    double start = above;
+    bool found = false;
+#pragma unroll
+    for (int k = NG - 1; k >= 0; --k) {
+        if (!found) {
+            const double next = __dadd_rn(start, v[k]);
+            if (target < next || k == 0) { e = gl * NG + k; found = true; }
+            else start = next;
+        }
+    }
+    e = __shfl_sync(kFull, e, winner, W);
+    start = __shfl_sync(kFull, start, winner, W);
+    target = hits ? fmax(__dsub_rn(target, start), 0.0) : 0.0;
+    return e;
+}
+
 // Bytes of shared memory one chain (group) needs; must match the carve-up in stepKernel.
 __host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap) {
     return sCap * 8 + rowsCap * 16 + 32 * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7);
@@ -211,7 +247,14 @@ __device__ __noinline__ void recordSeries(int32_t *series, int seriesThin, int s
 // (FiguresForPaper.h:93-104): end-state occupancy and synopsis sums, maintained incrementally.
 // MODE_INIT: findInitialFeasibleSolution (:254-263): same proposal, always applied, no importance, no
 // statistics, until the chain is feasible.
-template <int MODE, int W>
+//
+// BLK selects the categorical's storage.  false: the reference's binary sum tree, node for node and add for add (above).
+// true: a 32-ary blocked sum tree -- leaf p_u next to currentDE[u], sums of 32 leaves (tier1), of 1024 (tier2), of 32768
+// (shared-memory top) -- with the reference's cdf order (the descent consumes the HIGH indices first, i.e. column j owns
+// [sum_{i>j} p_i, sum_{i>=j} p_i)).  The same uniform then selects the same column except when it falls within rounding
+// distance (~1e-13 relative) of a boundary; get(u) is the exact leaf instead of the reference's drifting difference of
+// sums.  An update touches 3 nodes instead of 1 + popcount(u), which removes most of the commit work and traffic.
+template <int MODE, int W, bool BLK>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P, DevChains S, RunParams R) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     constexpr int NG = 32 / W;
@@ -246,7 +289,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     ch.topShift = P.topShift;
     // the top of the sum tree lives in shared memory for the whole launch: the root, the first descent round and the
     // longest ordered sums of every commit never touch global memory
-    for (int k = gl; k < 32; k += W) sTop[k] = (chainValid && k < P.nTop) ? ch.tier2[(k << P.topShift) >> 10] : 0.0;
+    double *tier3 = S.tier3 + (size_t)chainC * 32;   // BLK: sums of 32768 leaves (global home of the shared-memory top)
+    const int nTop = BLK ? ((P.nCols - 1) >> 15) + 1 : P.nTop;
+    for (int k = gl; k < 32; k += W) {
+        double v = 0.0;
+        if (chainValid && k < nTop) v = BLK ? tier3[k] : ch.tier2[(k << P.topShift) >> 10];
+        sTop[k] = v;
+    }
     __syncwarp();
     double2 *scratch = S.scratch + (size_t)chainC * P.sCap;
 
@@ -298,8 +347,40 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // LW tree levels per memory round trip: lane r fetches the node reached by branch pattern r, then the
         // reference's strict comparisons / subtractions are resolved with shuffles.  A child index >= nCols
         // holds 0.0: "0.0 > target" is false and "target - 0.0" is a no-op, which is the reference's skip.
-        const double root = act ? sTop[0] : 1.0;
+        double root = 1.0;
         int j = 0;
+        if constexpr (BLK) {
+            // total = sum of the top entries, highest first (the order the selection below subtracts them in)
+            double tot = 0.0;
+#pragma unroll 1
+            for (int k = nTop - 1; k >= 0; --k) tot = __dadd_rn(tot, sTop[k]);
+            if (act) root = tot;
+            double target = __dmul_rn(u1, root);
+            // top level: sequential, from shared memory
+            int sel = 0;
+#pragma unroll 1
+            for (int k = nTop - 1; k >= 0; --k) {
+                const double v = sTop[k];
+                if (target < v || k == 0) { sel = k; break; }
+                target = __dsub_rn(target, v);
+            }
+            // three 32-ary levels: tier2 (1024 leaves each), tier1 (32 leaves), leaves
+#pragma unroll 1
+            for (int lvl = 2; lvl >= 0; --lvl) {
+                const int first = sel * 32;
+                const int count = lvl == 2 ? P.t2Len : (lvl == 1 ? P.t1Len : nCols);
+                double v[NG];
+#pragma unroll
+                for (int k = 0; k < NG; ++k) {
+                    const int e = first + gl * NG + k;
+                    v[k] = 0.0;
+                    if (act && e < count) v[k] = lvl == 2 ? ch.tier2[e] : (lvl == 1 ? ch.tier1[e] : ch.colRec[e].y);
+                }
+                sel = first + selectDescending<W>(v, target, gl);
+            }
+            j = min(sel, nCols - 1);
+        } else {
+            if (act) root = sTop[0];
         {
             double target = __dmul_rn(u1, root);
             #pragma unroll 1
@@ -334,6 +415,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 hi = lo - 1;
                 __syncwarp();
             }
+        }
         }
         if (act && R.injJ) j = R.injJ[(size_t)chain * R.nSteps + s];
 
@@ -394,18 +476,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             const bool real = u >= 0, self = real && u == j;
             const int maxCnt = chdr & 0xff;
             const uint16_t *__restrict__ plane = contrib + (chdr >> 8) + gl;
-            // everything this column needs from the chain state, issued together: its record, its delta, and the
-            // nodes get(u) / set(u,.) will read: u + 1, 2, 4, 8, 16 sit in the same 32-record block
-            const int nDesc = real ? (u ? (__ffs(u) - 1) : P.treeDepth) : 0;
+            // everything this column needs from the chain state, issued together: its record, its delta, and (reference
+            // tree) the nodes get(u) / set(u,.) will read: u + 1, 2, 4, 8, 16 sit in the same 32-record block
+            const int nDesc = (!BLK && real) ? (u ? (__ffs(u) - 1) : P.treeDepth) : 0;
             double2 cr = make_double2(0.0, 0.0);
             int du = 0;
             double dn[5];
             if (real) { cr = ch.colRec[u]; du = ch.delta[u]; }
-            const double *nearBase = &ch.colRec[real ? u : 0].y;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) dn[i] = (i < nDesc && u + (1 << i) < nCols) ? nearBase[2 << i] : 0.0;
             double nodeOld = cr.y;
-            if (real && (u & 31) == 0) nodeOld = *ch.node(u);
+            if constexpr (!BLK) {
+                const double *nearBase = &ch.colRec[real ? u : 0].y;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) dn[i] = (i < nDesc && u + (1 << i) < nCols) ? nearBase[2 << i] : 0.0;
+                if (real && (u & 31) == 0) nodeOld = *ch.node(u);
+            }
             // the column's first two shared-row entries are fetched together with its state (most columns share 1-3
             // rows with the proposed one); further planes, if any, one by one
             int ct4[2];
@@ -436,36 +520,45 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             // .cpp:30-39), and the sum / delta that set(u, p') will compute (.cpp:10-17).  Absent descendants were
             // loaded as 0.0 and x + 0.0 == x, so the unconditional adds reproduce the reference's skips.
             const double newP = real ? DEtoBasisProb(acc) : 0.0;
-            double dsum = 0.0, ssum = newP;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                dsum = __dadd_rn(dsum, dn[i]);
-                ssum = __dadd_rn(ssum, dn[i]);
-            }
-            const int descW = warpMax(nDesc);
-            if (descW > 5) {
-                // columns with (u & 31) == 0 (one in 32).  Levels 5..9: u + 2^i has its low 5 bits clear and bit i set, so it
-                // is tier1[(u >> 5) + 2^(i-5)]; levels >= 10 are tier2 / shared-memory top nodes.
-                const double *t1 = ch.tier1 + (real ? (u >> 5) : 0);
-#pragma unroll
-                for (int i = 0; i < 5; ++i) dn[i] = (5 + i < nDesc && u + (32 << i) < nCols) ? t1[1 << i] : 0.0;
-#pragma unroll
+            double term, dlt, base;
+            if constexpr (BLK) {
+                term = __dsub_rn(newP, nodeOld);   // the leaf itself is stored: get(u) = p_u
+                dlt = term;
+                base = newP;
+            } else {
+                double dsum = 0.0, ssum = newP;
+    #pragma unroll
                 for (int i = 0; i < 5; ++i) {
                     dsum = __dadd_rn(dsum, dn[i]);
                     ssum = __dadd_rn(ssum, dn[i]);
                 }
-#pragma unroll 1
-                for (int i = 10; i < descW; ++i) {   // one column in 1024
-                    const double t = (i < nDesc && u + (1 << i) < nCols) ? *ch.node(u + (1 << i)) : 0.0;
-                    dsum = __dadd_rn(dsum, t);
-                    ssum = __dadd_rn(ssum, t);
+                const int descW = warpMax(nDesc);
+                if (descW > 5) {
+                    // columns with (u & 31) == 0 (one in 32).  Levels 5..9: u + 2^i has its low 5 bits clear and bit i set, so it
+                    // is tier1[(u >> 5) + 2^(i-5)]; levels >= 10 are tier2 / shared-memory top nodes.
+                    const double *t1 = ch.tier1 + (real ? (u >> 5) : 0);
+    #pragma unroll
+                    for (int i = 0; i < 5; ++i) dn[i] = (5 + i < nDesc && u + (32 << i) < nCols) ? t1[1 << i] : 0.0;
+    #pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        dsum = __dadd_rn(dsum, dn[i]);
+                        ssum = __dadd_rn(ssum, dn[i]);
+                    }
+    #pragma unroll 1
+                    for (int i = 10; i < descW; ++i) {   // one column in 1024
+                        const double t = (i < nDesc && u + (1 << i) < nCols) ? *ch.node(u + (1 << i)) : 0.0;
+                        dsum = __dadd_rn(dsum, t);
+                        ssum = __dadd_rn(ssum, t);
+                    }
                 }
+                term = __dsub_rn(newP, __dsub_rn(nodeOld, dsum));                   // :279-280
+                dlt = __dsub_rn(ssum, nodeOld);                                              // delta of set(), .cpp:17
+                base = ssum;
             }
-            const double term = __dsub_rn(newP, __dsub_rn(nodeOld, dsum));                   // :279-280
             if (real) {
                 sU[slot] = u;
-                sDl[slot] = __dsub_rn(ssum, nodeOld);                                        // delta of set(), .cpp:17
-                scratch[slot] = make_double2(acc, ssum);
+                sDl[slot] = dlt;
+                scratch[slot] = make_double2(acc, base);
             }
             if (kMC) {
                 // changeInSum += ... in ascending column order (:278-281), staged through shared memory; padding slots
@@ -591,14 +684,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             unsigned taskMask = 0;
             if (l < Ca) {
                 const int u = sU[l];
-                ch.colRec[u].x = scratch[l].x;
                 const unsigned prev = l ? (unsigned)sU[l - 1] : 0u;
+                if constexpr (BLK) {
+                    // currentDE[u] and the leaf p_u in one 16-byte store; sums of 32 / 1024 / 32768 leaves are updated by
+                    // the first entry of each block (levels 5, 10, 15)
+                    ch.colRec[u] = scratch[l];
+                    if (l == 0 || (prev >> 5) != ((unsigned)u >> 5)) taskMask |= 1u << 5;
+                    if (l == 0 || (prev >> 10) != ((unsigned)u >> 10)) taskMask |= 1u << 10;
+                    if (l == 0 || (prev >> 15) != ((unsigned)u >> 15)) taskMask |= 1u << 15;
+                } else {
+                ch.colRec[u].x = scratch[l].x;
                 const int hbit = l ? (31 - __clz(prev ^ (unsigned)u)) : 31;
                 const unsigned low = hbit >= 31 ? 0xffffffffu : ((2u << hbit) - 1u);
                 const unsigned lowbit = (unsigned)u & (0u - (unsigned)u);
                 taskMask = (unsigned)u & low & ~(lowbit | (lowbit - 1u));                    // ancestors first reached here
                 if (l == 0 && u != 0) taskMask |= 0x80000000u;                               // the root
                 taskMask |= u ? lowbit : 0x80000000u;                                        // the column's own node
+                }
             }
             const int cnt = __popc(taskMask & 0xfffffc00u) | (__popc(taskMask & 0x000003e0u) << 10) | (__popc(taskMask & 0x0000001fu) << 20);
             const int incl = groupInclusiveScan<W>(cnt, gl);
@@ -634,8 +736,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     const unsigned u0 = (unsigned)sU[l0];
                     const unsigned pre = u0 >> b;
                     const unsigned a = b == 31 ? 0u : (pre << b);
-                    npN = ch.node((int)a);
-                    const bool own = a == u0;
+                    bool own = false;
+                    if constexpr (BLK) {
+                        npN = b == 5 ? &ch.tier1[pre] : (b == 10 ? &ch.tier2[pre] : &sTop[pre]);
+                    } else {
+                        npN = ch.node((int)a);
+                        own = a == u0;
+                    }
                     vN = own ? scratch[l0].y : *npN;
                     qN = own ? l0 + 1 : l0;
                     // the run ends at the first entry outside the node's index range [a, a + 2^b): binary search in the
@@ -689,8 +796,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     }
 
     __syncwarp();
-    for (int k = gl; k < P.nTop; k += W)
-        if (chainValid) ch.tier2[(k << P.topShift) >> 10] = sTop[k];
+    for (int k = gl; k < nTop; k += W)
+        if (chainValid) {
+            if (BLK) tier3[k] = sTop[k]; else ch.tier2[(k << P.topShift) >> 10] = sTop[k];
+        }
     if (MODE == MODE_SAMPLE && chainValid) {   // the lazy accumulators are settled by sampleEndKernel
         if (gl < P.nSynopsis) {
             S.synSum[(size_t)chain * P.nSynopsis + gl] += sSyn[gl];
@@ -768,6 +877,13 @@ __global__ void initColsKernel(DevProblem P, DevChains S) {
                                          energyOf(x, rp.y, rp.z, rp.w, P.facVal, P.kappa)));
         }
         ch.colRec[j].x = de;
+        if (P.blockedTree) {   // every leaf 1.0; block sums = number of columns in the block
+            ch.colRec[j].y = 1.0;
+            if ((j & 31) == 0) ch.tier1[j >> 5] = (double)(min(j + 32, P.nCols) - j);
+            if ((j & 1023) == 0) ch.tier2[j >> 10] = (double)(min(j + 1024, P.nCols) - j);
+            if ((j & 32767) == 0) S.tier3[(size_t)chain * 32 + (j >> 15)] = (double)(min(j + 32768, P.nCols) - j);
+            continue;
+        }
         const int span = j ? (j & -j) : P.nCols;
         *ch.node(j) = (double)(min(j + span, P.nCols) - j);
     }

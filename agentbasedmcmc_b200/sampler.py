@@ -26,7 +26,9 @@ class Problem:
     ``TableauNormMinimiser`` + factor closures (SparseBasisSampler.h:107-158).
     """
 
-    def __init__(self, abmp: dict, device: int = 0, with_importance: bool = True):
+    def __init__(self, abmp: dict, device: int = 0, with_importance: bool = True, sum_tree: str = "blocked"):
+        """sum_tree: "blocked" (32-ary tree, default) or "reference" (MutableCategoricalArray's binary tree, node for
+        node); see ABM_TREE_* in include/abmcmc_b200.h."""
         L = _capi.load()
         self.abmp = abmp
         self.device = device
@@ -47,6 +49,8 @@ class Problem:
         d.n_timesteps = int(abmp["pp_meta"][1]) if use_imp else 0
         d.imp_lgamma = _ptr(k["imp_lgamma"], C.c_double)
         d.imp_logratio = _ptr(k["imp_logratio"], C.c_double)
+        d.sum_tree = {"blocked": 0, "reference": 1}[sum_tree]
+        self.sum_tree = sum_tree
         h = C.c_void_p()
         check(L.abm_problem_create(C.byref(d), device, C.byref(h)))
         self.h = h

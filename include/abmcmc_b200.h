@@ -60,7 +60,17 @@ typedef struct {
     int32_t n_timesteps;
     const double *imp_lgamma;   /* [7]  lgamma(occ+1) for occ>1 else 0 (TrajectoryImportance.h:96) */
     const double *imp_logratio; /* [2][2][6] log(pi/pibar) by type, has-neighbour flag, act (:105) */
+    int32_t sum_tree;        /* storage of basisDistribution (MutableCategoricalArray): ABM_TREE_BLOCKED (0, default) or
+                              * ABM_TREE_REFERENCE; the environment variable ABM_TREE=blocked|reference overrides it */
 } abm_problem_desc;
+
+/* ABM_TREE_REFERENCE keeps the reference's binary sum tree node for node and add for add (every double of the tree
+ * reproduces MutableCategoricalArray's, rounding drift included).  ABM_TREE_BLOCKED keeps the same categorical -- same
+ * leaves, same cdf order, so the same uniform selects the same column except within rounding distance (~1e-13) of an
+ * interval boundary -- in a 32-ary blocked tree whose updates touch 3 nodes instead of 1 + popcount(index); get(u) is
+ * then the exact leaf instead of a difference of drifting sums.  Integer state and accept decisions are identical in
+ * both (tests/test_gpu_parity.py runs the golden reference traces through both). */
+enum { ABM_TREE_BLOCKED = 0, ABM_TREE_REFERENCE = 1 };
 
 typedef struct {
     int32_t n_rows, n_cols, nnz, n_events;

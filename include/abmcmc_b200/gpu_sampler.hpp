@@ -67,7 +67,7 @@ public:
     // SparseBasisSampler.h:69
     GpuSparseBasisSampler(const TableauNormMinimiser<T> &tableau, const std::vector<std::function<double(T)>> &tableauFactors,
                           std::unique_ptr<PerturbableFunction<T, double>> &&importanceFunc, const std::vector<T> &initialState,
-                          double Kappa, int device = 0)
+                          double Kappa, int device = 0, int sumTree = ABM_TREE_BLOCKED)
         : kappa(Kappa) {
         AbmpFile f;
         flattenTableau<TableauNormMinimiser<T>, T>(f, tableau, tableauFactors, Kappa);
@@ -87,6 +87,7 @@ public:
         d.n_timesteps = f.I("pp_meta")[1];
         d.imp_lgamma = f.D("imp_lgamma").data();
         d.imp_logratio = f.D("imp_logratio").data();
+        d.sum_tree = sumTree;
         detail::check(abm_problem_create(&d, device, &problem_), "abm_problem_create");
         abm_problem_info info;
         detail::check(abm_problem_get_info(problem_, &info), "abm_problem_get_info");
