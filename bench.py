@@ -238,24 +238,36 @@ def bench_ours(args):
     # sequence; chains are i.i.d., so the ensemble's effective sample size is the per-chain one times the chain count.
     ess = None
     if args.ess_samples > 0 and rank == 0:
-        from agentbasedmcmc_b200 import diagnostics as D
-        k = min(args.ess_chains, n_chains)
-        smp.reset_statistics()
-        smp.record_series(k, 1, args.ess_samples)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        smp.sample(args.ess_samples, max_steps=4 * args.ess_samples)   # bounded: a chain deep in the infeasible region must not stall the batch
-        smp.synchronize()
-        ess_s = time.perf_counter() - t0
-        n_rec = int(min(smp.statistics()[3][:k].min(), args.ess_samples))
-        series = smp.series().astype(np.float64)[:, :n_rec]
-        ms = D.MultiChainStats([D.ChainStats.from_series(series[c], n_lags=200, max_lag_proportion=0.5) for c in range(k)])
-        neff = ms.effective_samples(reference_integer_division=False)
-        per_chain = neff / k
-        ess = {"value": float(per_chain.min() * n_chains * world / ess_s), "unit": "effective samples/s (worst synopsis statistic, all chains)",
-               "n_eff_per_chain": [round(float(x), 2) for x in per_chain], "feasible_samples_per_chain": n_rec,
-               "sequences_analysed": k, "seconds": round(ess_s, 3),
-               "rhat": [round(float(x), 4) for x in ms.potential_scale_reduction(reference_integer_division=False)]}
+        try:
+            from agentbasedmcmc_b200 import diagnostics as D
+            k = min(args.ess_chains, n_chains)
+            burn = 0
+            while burn < args.ess_burnin:       # relaxation from the first feasible state takes ~3e6 steps at 32x32x16
+                smp.step(min(250000, args.ess_burnin - burn))
+                burn += 250000
+            smp.reset_statistics()
+            smp.record_series(k, 1, args.ess_samples)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            smp.sample(args.ess_samples, max_steps=4 * args.ess_samples)   # bounded: a chain deep in the infeasible region must not stall the batch
+            smp.synchronize()
+            ess_s = time.perf_counter() - t0
+            ns_k = smp.statistics()[3][:k]
+            n_rec = int(min(np.percentile(ns_k, 25), args.ess_samples))      # sequences must be equally long: keep the upper 75 %
+            use = [c for c in range(k) if ns_k[c] >= n_rec]
+            if n_rec >= 400 and len(use) >= 4:
+                series = smp.series().astype(np.float64)[use, :n_rec]
+                ms = D.MultiChainStats([D.ChainStats.from_series(x, n_lags=200, max_lag_proportion=0.5) for x in series])
+                per_chain = ms.effective_samples(reference_integer_division=False) / len(use)
+                ess = {"value": float(per_chain.min() * n_chains * world / ess_s),
+                       "unit": "effective samples/s (worst synopsis statistic, all chains)",
+                       "n_eff_per_chain": [round(float(x), 2) for x in per_chain], "feasible_samples_per_chain": n_rec,
+                       "sequences_analysed": len(use), "seconds": round(ess_s, 3), "burnin_steps_per_chain": args.ess_burnin,
+                       "rhat": [round(float(x), 4) for x in ms.potential_scale_reduction(reference_integer_division=False)]}
+            else:
+                ess = {"value": None, "note": f"too few feasible samples in {4 * args.ess_samples} steps (25th percentile {n_rec})"}
+        except Exception as exc:   # the ESS estimate must never take the benchmark line down
+            ess = {"value": None, "note": f"ESS estimate failed: {exc!r}"}
     barrier()
 
     st = smp.stats
@@ -312,7 +324,9 @@ def main():
     ap.add_argument("--mh-steps", type=int, default=2000, help="Metropolis steps per chain per launch")
     ap.add_argument("--seed", type=int, default=20221)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ess-samples", type=int, default=10000, help="feasible samples per chain for the ESS/s estimate (0 = skip)")
+    ap.add_argument("--ess-samples", type=int, default=0,
+                    help="feasible samples per chain for the ESS/s estimate (0 = skip; needs --ess-burnin steps first, ~2 more minutes)")
+    ap.add_argument("--ess-burnin", type=int, default=3000000, help="Metropolis steps per chain before the ESS estimate")
     ap.add_argument("--ess-chains", type=int, default=64, help="chains whose synopsis series are analysed for ESS/s")
     args = ap.parse_args()
     if args.warmup < 3:
