@@ -465,24 +465,45 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // row in row order -- the order in which the reference's map accumulation visits them (:305-312).
         double changeInSum = 0.0;
         const int chunksW = warpMax(nChunks);
-        int uNext = -1, chdrNext = 0;
-        if (0 < nChunks) { uNext = __ldg(slotU + gl); chdrNext = __ldg(chunkHdr); }
+        // Two-deep software pipeline over the chunks: the column list of chunk c+2 and the chain state of chunk c+1 (record,
+        // delta, first shared-row entries) are in flight while chunk c is evaluated.
+        int uB = -1, chdrB = 0, uC = -1, chdrC = 0;                  // chunk c+1, chunk c+2
+        if (0 < nChunks) { uB = __ldg(slotU + gl); chdrB = __ldg(chunkHdr); }
+        if (1 < nChunks) { uC = __ldg(slotU + W + gl); chdrC = __ldg(chunkHdr + 1); }
+        double2 crN = make_double2(0.0, 0.0);
+        int duN = 0, ctN0 = kNoContrib, ctN1 = kNoContrib;
+        if (uB >= 0) {
+            crN = ch.colRec[uB];
+            duN = ch.delta[uB];
+            const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
+            if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
+            if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
+        }
         #pragma unroll 1
         for (int c = 0; c < chunksW; ++c) {
             const int slot = c * W + gl;
-            const int u = uNext, chdr = chdrNext;
-            uNext = -1; chdrNext = 0;
-            if (c + 1 < nChunks) { uNext = __ldg(slotU + slot + W); chdrNext = __ldg(chunkHdr + c + 1); }   // one chunk ahead
+            const int u = uB, chdr = chdrB;
+            const double2 cr = crN;
+            const int du = duN;
+            int ct4[2] = {ctN0, ctN1};
+            uB = uC; chdrB = chdrC;
+            uC = -1; chdrC = 0;
+            if (c + 2 < nChunks) { uC = __ldg(slotU + slot + 2 * W); chdrC = __ldg(chunkHdr + c + 2); }
+            crN = make_double2(0.0, 0.0);
+            duN = 0; ctN0 = kNoContrib; ctN1 = kNoContrib;
+            if (uB >= 0) {
+                crN = ch.colRec[uB];
+                duN = ch.delta[uB];
+                const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
+                if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
+                if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
+            }
             const bool real = u >= 0, self = real && u == j;
             const int maxCnt = chdr & 0xff;
             const uint16_t *__restrict__ plane = contrib + (chdr >> 8) + gl;
-            // everything this column needs from the chain state, issued together: its record, its delta, and (reference
-            // tree) the nodes get(u) / set(u,.) will read: u + 1, 2, 4, 8, 16 sit in the same 32-record block
+            // (reference tree) the nodes get(u) / set(u,.) will read: u + 1, 2, 4, 8, 16 sit in the same 32-record block
             const int nDesc = (!BLK && real) ? (u ? (__ffs(u) - 1) : P.treeDepth) : 0;
-            double2 cr = make_double2(0.0, 0.0);
-            int du = 0;
             double dn[5];
-            if (real) { cr = ch.colRec[u]; du = ch.delta[u]; }
             double nodeOld = cr.y;
             if constexpr (!BLK) {
                 const double *nearBase = &ch.colRec[real ? u : 0].y;
@@ -490,11 +511,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 for (int i = 0; i < 5; ++i) dn[i] = (i < nDesc && u + (1 << i) < nCols) ? nearBase[2 << i] : 0.0;
                 if (real && (u & 31) == 0) nodeOld = *ch.node(u);
             }
-            // the column's first two shared-row entries are fetched together with its state (most columns share 1-3
-            // rows with the proposed one); further planes, if any, one by one
-            int ct4[2];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) ct4[t] = (real && t < maxCnt) ? (int)__ldg(plane + t * W) : kNoContrib;
             double acc = cr.x;                                                               // try_emplace(u, currentDE[u])
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
