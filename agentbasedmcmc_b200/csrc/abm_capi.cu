@@ -531,7 +531,9 @@ static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
 
 template <int MODE, int W>
 static cudaError_t launchStepW(const abm_chains *c, const RunParams &r) {
-    return c->p->d.blockedTree ? launchStepWB<MODE, W, true>(c, r) : launchStepWB<MODE, W, false>(c, r);
+    if (!c->p->d.blockedTree) return launchStepWB<MODE, W, false>(c, r);
+    refreshBlockedTopKernel<<<(c->n + 3) / 4, 128, 0, c->stream>>>(c->p->d, c->d);
+    return launchStepWB<MODE, W, true>(c, r);
 }
 
 template <int MODE>

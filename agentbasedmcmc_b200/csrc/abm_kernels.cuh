@@ -1045,6 +1045,29 @@ __global__ void sampleEndKernel(DevProblem P, DevChains S) {
     if (blockIdx.x == 0 && threadIdx.x == 0) S.nSamples[chain] += nSamp;
 }
 
+// Blocked sum tree, before every launch: the two upper levels are recomputed from the level below (sums of 32 entries,
+// highest index first -- the order the selection consumes them in), so incremental rounding cannot accumulate there across
+// launches.  tier1 (sums of 32 leaves) stays incremental: rebuilding it would read every leaf.  One warp per chain.
+__global__ void refreshBlockedTopKernel(DevProblem P, DevChains S) {
+    const int lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (chain >= S.nChains) return;
+    const double *t1 = S.tier1 + (size_t)chain * P.t1Len;
+    double *t2 = S.tier2 + (size_t)chain * P.t2Len, *t3 = S.tier3 + (size_t)chain * 32;
+    for (int s2 = lane; s2 < P.t2Len; s2 += 32) {
+        double v = 0.0;
+        for (int k = min(32 * s2 + 31, P.t1Len - 1); k >= 32 * s2; --k) v = __dadd_rn(v, t1[k]);
+        t2[s2] = v;
+    }
+    __syncwarp();
+    const int nTop = ((P.nCols - 1) >> 15) + 1;
+    if (lane < nTop) {
+        double v = 0.0;
+        for (int k = min(32 * lane + 31, P.t2Len - 1); k >= 32 * lane; --k) v = __dadd_rn(v, t2[k]);
+        t3[lane] = v;
+    }
+}
+
 // ensemble end-state sum: out[psi] += sum over a slice of chains of endAcc[chain][psi] (out zeroed by the caller)
 constexpr int kReduceSlice = 64;
 __global__ void reduceEndStateKernel(DevProblem P, DevChains S) {
