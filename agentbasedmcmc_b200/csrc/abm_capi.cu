@@ -662,7 +662,7 @@ static int zeroStatistics(abm_chains *c) {
 }
 
 int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
-    if (!c || nSamples < 0) return fail(ABM_ERR_INVALID, "bad argument");
+    if (!c || nSamples < 0 || (nSamples == 0 && maxSteps <= 0)) return fail(ABM_ERR_INVALID, "bad argument");
     if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
     if (c->p->d.G <= 0) return fail(ABM_ERR_INVALID, "sample statistics need the PredPrey geometry");
     CUDA_TRY(cudaSetDevice(c->p->device));
@@ -676,7 +676,9 @@ int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
     const DevProblem &P = c->p->d;
     sampleBeginKernel<<<(c->n + 3) / 4, 128, 0, c->stream>>>(P, c->d);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(launchStep<MODE_SAMPLE>(c, r));
+    // without a quota (n_samples == 0 or beyond what max_steps can yield) every chain simply runs max_steps steps
+    if (maxSteps > 0 && (nSamples == 0 || nSamples >= maxSteps)) CUDA_TRY(launchStep<MODE_SAMPLE_FIXED>(c, r));
+    else CUDA_TRY(launchStep<MODE_SAMPLE>(c, r));
     sampleEndKernel<<<dim3(std::max(1, std::min((P.S + 255) / 256, 8)), c->n), 256, 0, c->stream>>>(P, c->d);
     CUDA_TRY(cudaGetLastError());
     return ABM_OK;

@@ -22,7 +22,9 @@ namespace abm {
 constexpr int kWarpsPerCta = 4;
 constexpr unsigned kFull = 0xffffffffu;
 
-enum { MODE_MCMC = 0, MODE_INIT = 1, MODE_SAMPLE = 2 };   // SAMPLE = MCMC + per-feasible-sample statistics
+enum { MODE_MCMC = 0, MODE_INIT = 1, MODE_SAMPLE = 2, MODE_SAMPLE_FIXED = 3 };
+// SAMPLE = MCMC + per-feasible-sample statistics until a per-chain sample quota; SAMPLE_FIXED = the same for exactly
+// nSteps steps (no quota), which keeps every chain active in every iteration like MODE_MCMC
 
 struct RunParams {
     long long nSteps;            // Metropolis steps (MCMC) / iteration budget of this launch (INIT)
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     extern __shared__ __align__(16) unsigned char smemRaw[];
     constexpr int NG = 32 / W;
     constexpr bool kMC = MODE != MODE_INIT;   // Metropolis test, importance, counters
+    constexpr bool kSample = MODE == MODE_SAMPLE || MODE == MODE_SAMPLE_FIXED;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (W - 1), g = lane / W;
     const int chain = (blockIdx.x * kWarpsPerCta + warp) * NG + g;
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     int nSamp = 0;                      // feasible samples taken in this launch
     int syn = 0;                        // lane k < nSynopsis: agents inside the k-th nested square (FiguresForPaper.h:245-263)
     const int lastBase = (P.T - 1) * P.S * kStateBytes;   // Xb offset of the events of the last timestep
-    if (MODE == MODE_SAMPLE) {   // end-state occupancy and synopsis were prepared by sampleBeginKernel
+    if (kSample) {   // end-state occupancy and synopsis were prepared by sampleBeginKernel
         if (chainValid && gl < P.nSynopsis) syn = S.synNow[(size_t)chain * P.nSynopsis + gl];
         if (gl < 16) sSyn[gl] = 0;
         __syncwarp();
@@ -323,9 +326,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 
 #pragma unroll 1
     for (long long s = 0; s < R.nSteps; ++s) {
-        const bool act = chainValid && (MODE == MODE_MCMC || (MODE == MODE_INIT && infeas > 0) ||
+        const bool act = chainValid && (MODE == MODE_MCMC || MODE == MODE_SAMPLE_FIXED || (MODE == MODE_INIT && infeas > 0) ||
                                         (MODE == MODE_SAMPLE && (long long)nSamp < R.nSamples));
-        if (MODE != MODE_MCMC && !__any_sync(kFull, act)) break;
+        if ((MODE == MODE_INIT || MODE == MODE_SAMPLE) && !__any_sync(kFull, act)) break;
 
         // ---- uniforms: one Philox block per iteration, or the injected stream
         double u1 = 0.5, u2 = 0.0;
@@ -793,7 +796,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
         }
         __syncwarp();
-        if (MODE == MODE_SAMPLE) {
+        if (kSample) {
             // events of the last timestep changed by an accepted proposal move the end state
             if (__any_sync(kFull, accept && colTouchesEnd))
                 syn += endStateUpdate(P.G, P.evBytes, P.nSynopsis, lastBase, accept ? n : 0, nW, sXoff, sXX, S.endOcc + (size_t)chainC * P.S,
@@ -816,7 +819,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (chainValid) {
             if (BLK) tier3[k] = sTop[k]; else ch.tier2[(k << P.topShift) >> 10] = sTop[k];
         }
-    if (MODE == MODE_SAMPLE && chainValid) {   // the lazy accumulators are settled by sampleEndKernel
+    if (kSample && chainValid) {   // the lazy accumulators are settled by sampleEndKernel
         if (gl < P.nSynopsis) {
             S.synSum[(size_t)chain * P.nSynopsis + gl] += sSyn[gl];
             S.synSumSq[(size_t)chain * P.nSynopsis + gl] += sSyn[8 + gl];

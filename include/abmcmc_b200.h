@@ -136,7 +136,8 @@ ABM_API int abm_chains_step_traced(abm_chains *c, int64_t n_steps, const double 
 
 /* operator() (:212-214) for every chain: step until n_samples further feasible states were visited
  * (a feasible state is a sample each time the loop condition :247 sees infeasibility == 0), accumulating
- * the ensemble statistics below after each one.  max_steps bounds the work per chain. */
+ * the ensemble statistics below after each one.  max_steps bounds the work per chain (0 = unbounded); n_samples == 0 with
+ * max_steps > 0 means "sample for exactly max_steps steps". */
 ABM_API int abm_chains_sample(abm_chains *c, int64_t n_samples, int64_t max_steps);
 
 ABM_API int abm_chains_synchronize(abm_chains *c);
