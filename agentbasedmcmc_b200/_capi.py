@@ -7,8 +7,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libabmcmc_b200.so"
+# ABM_LIB names an experimental build of the same library inside the package directory (kernel A/B measurements)
+LIB_PATH = _PKG / os.environ.get("ABM_LIB", "libabmcmc_b200.so")
 
 SYMBOLS = [
     "abm_last_error", "abm_version", "abm_device_count", "abm_problem_create", "abm_problem_destroy",

@@ -17,12 +17,15 @@ NVCC_FLAGS = [
 ]
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path = OUT) -> Path:
+    """``defines``/``out`` build an experimental variant next to the product library (kernel A/B runs select it with
+    the ABM_LIB environment variable, see _capi.py)."""
     sources = [SRC / "abm_capi.cu"]
     deps = list(SRC.glob("*")) + [ROOT / "include" / "abmcmc_b200.h"]
-    if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
-        return OUT
-    cmd = ["nvcc", *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{SRC}", *(str(s) for s in sources), "-o", str(OUT)]
+    if not force and out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return out
+    cmd = ["nvcc", *NVCC_FLAGS, *(f"-D{d}" for d in defines), f"-I{ROOT / 'include'}", f"-I{SRC}", *(str(s) for s in sources),
+           "-o", str(out)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -30,8 +33,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv or bool(defs), verbose="-v" in sys.argv, defines=defs,
+                out=PKG / outs[0] if outs else OUT))

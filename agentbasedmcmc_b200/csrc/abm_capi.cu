@@ -3,6 +3,7 @@
 // compute returns ABM_ERR_CUDA.
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -184,7 +185,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     std::vector<int4> recIdx(nCols);
     std::vector<int32_t> rec;
     rec.reserve((size_t)nnz * 24);
-    int maxCoupled = 1, maxTasks = 1, maxSF = 0, maxTA = 1, maxTB = 1, maxTC = 1, maxBlkTasks = 1;
+    int maxCoupled = 1, maxTasks = 1, maxSF = 0, maxTA = 1, maxTB = 1, maxTC = 1;
     struct Pair { int u, k, m; };
     std::vector<Pair> pairs;
     std::vector<int32_t> slotU, chunkHdr, staleF, nodes;
@@ -215,13 +216,6 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         const int C = int(slotU.size());
         const int nChunks = (C + W - 1) / W;
         maxCoupled = std::max(maxCoupled, C);
-        {
-            int blk = 0;
-            for (int l = 0; l < C; ++l)
-                for (int b = 5; b <= 15; b += 5)
-                    if (l == 0 || (slotU[l - 1] >> b) != (slotU[l] >> b)) ++blk;
-            maxBlkTasks = std::max(maxBlkTasks, blk);
-        }
         slotU.resize(size_t(nChunks) * W, -1);
         chunkHdr.assign(nChunks, 0);
         contrib.clear();
@@ -350,10 +344,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.tCapA = (maxTA + 7) & ~7;
     d.tCapB = (maxTB + 7) & ~7;
     d.tCap = d.tCapA + d.tCapB + ((maxTC + 7) & ~7);
-    if (d.blockedTree) {   // levels 10/15 go to the first region, level 5 to the second; either can hold every task
-        d.tCapA = d.tCapB = (maxBlkTasks + 7) & ~7;
-        d.tCap = std::max(d.tCap, 2 * d.tCapA + 8);
-    }
+    if (d.blockedTree) d.tCap = d.tCapA = d.tCapB = 0;   // the blocked tree's commit keeps no task list
     if (maxTA > 1000 || maxTB > 1000 || maxTC > 1000) return fail(ABM_ERR_INVALID, "too many sum-tree nodes touched by one column");
     int nSyn = 0;
     for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
@@ -721,8 +712,8 @@ int abm_chains_get_state(abm_chains *c, int32_t chain, int32_t *X, int8_t *delta
         CUDA_TRY(cudaMemcpy(xb.data(), c->d.Xb + ch * P.xStride, P.xStride, cudaMemcpyDeviceToHost));
         for (int i = 0; i < P.nRows; ++i) X[i] = xb[c->p->xoff[i]];
     }
-    if (delta) CUDA_TRY(cudaMemcpy(delta, c->d.delta + ch * P.nCols, P.nCols, cudaMemcpyDeviceToHost));
-    if (currentDE || tree) {
+    if (delta && !P.blockedTree) CUDA_TRY(cudaMemcpy(delta, c->d.delta + ch * P.nCols, P.nCols, cudaMemcpyDeviceToHost));
+    if (currentDE || tree || (delta && P.blockedTree)) {
         std::vector<double2> cr(P.nCols);
         std::vector<double> t1(P.t1Len), t2(P.t2Len);
         CUDA_TRY(cudaMemcpy(cr.data(), c->d.colRec + ch * P.nCols, sizeof(double2) * P.nCols, cudaMemcpyDeviceToHost));
@@ -730,6 +721,7 @@ int abm_chains_get_state(abm_chains *c, int32_t chain, int32_t *X, int8_t *delta
         CUDA_TRY(cudaMemcpy(t2.data(), c->d.tier2 + ch * P.t2Len, sizeof(double) * P.t2Len, cudaMemcpyDeviceToHost));
         for (int j = 0; j < P.nCols; ++j) {
             if (currentDE) currentDE[j] = cr[j].x;
+            if (delta && P.blockedTree) delta[j] = std::signbit(cr[j].y) ? -1 : 1;   // the blocked tree's leaf carries delta_j in its sign
             if (tree && !P.blockedTree) tree[j] = (j & 31) ? cr[j].y : ((j & 1023) ? t1[j >> 5] : t2[j >> 10]);
         }
         if (tree && P.blockedTree) {
@@ -738,7 +730,7 @@ int abm_chains_get_state(abm_chains *c, int32_t chain, int32_t *X, int8_t *delta
             for (int j = 0; j < P.nCols; ++j) {
                 const int span = j ? (j & -j) : P.nCols;
                 double v = 0.0;
-                for (int k = std::min(j + span, P.nCols) - 1; k >= j; --k) v += cr[k].y;
+                for (int k = std::min(j + span, P.nCols) - 1; k >= j; --k) v += std::fabs(cr[k].y);
                 tree[j] = v;
             }
         }

@@ -20,6 +20,10 @@
 namespace abm {
 
 constexpr int kWarpsPerCta = 4;
+#ifndef ABM_IMP_EARLY
+#define ABM_IMP_EARLY 0
+#endif
+constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 constexpr unsigned kFull = 0xffffffffu;
 
 enum { MODE_MCMC = 0, MODE_INIT = 1, MODE_SAMPLE = 2, MODE_SAMPLE_FIXED = 3 };
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 for (int k = 0; k < NG; ++k) {
                     const int e = first + gl * NG + k;
                     v[k] = 0.0;
-                    if (act && e < count) v[k] = lvl == 2 ? ch.tier2[e] : (lvl == 1 ? ch.tier1[e] : ch.colRec[e].y);
+                    if (act && e < count) v[k] = lvl == 2 ? __ldcg(ch.tier2 + e) : (lvl == 1 ? __ldcg(ch.tier1 + e) : fabs(ch.colRec[e].y));   // leaf sign = delta_e; the two tiers are updated by L2 reductions
                 }
                 sel = first + selectDescending<W>(v, target, gl);
             }
@@ -434,7 +438,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         const int32_t *__restrict__ slotU = chunkHdr + nChunks;
         const uint16_t *__restrict__ contrib = reinterpret_cast<const uint16_t *>(rec + (hdr.w & 0xffff));
         const int32_t *__restrict__ staleF = rec + ((unsigned)hdr.w >> 16);
-        const int dj = act ? ch.delta[j] : 1;
+        // BLK: delta_u is the sign bit of the stored leaf p_u (p_u >= 0), so a coupled column costs one 16-byte load
+        int dj = 1;
+        if (act) dj = BLK ? (__double2hiint(ch.colRec[j].y) < 0 ? -1 : 1) : (int)ch.delta[j];
 
         // rows of the proposed column
         const int nW = warpMax(n);
@@ -477,17 +483,86 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         int duN = 0, ctN0 = kNoContrib, ctN1 = kNoContrib;
         if (uB >= 0) {
             crN = ch.colRec[uB];
-            duN = ch.delta[uB];
+            if constexpr (!BLK) duN = ch.delta[uB];
             const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
             if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
             if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
         }
+        // The importance change (perturb + refresh) can be evaluated between issuing the first chunk's loads and consuming
+        // them (ABM_IMP_EARLY), so that its own loads of the trajectory overlap with them, or after the chunks.
+        double logImpN = logImp;
+        auto importance = [&]() {
+            // ---- importance: perturb + refresh (TrajectoryImportance.h:36-54, 90-113)
+            const int sfW = warpMax(nSF);
+            const int evW = warpMax(nEv);
+            if (sfW > 0) {
+                const int G = P.G, GG = G * G;
+                const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(ch.Xb);
+                #pragma unroll 1
+                for (int fb = 0; fb < sfW; fb += W) {
+                    const int f = fb + gl;
+                    const bool fa = f < nSF;
+                    int sid = -1, type = 0, ns[4] = {-1, -1, -1, -1};
+                    unsigned long long own = 0ull, nb[4] = {0ull, 0ull, 0ull, 0ull};
+                    if (fa) {
+                        sid = __ldg(staleF + f);
+                        int cx, cy, ob;
+                        if (P.gShift >= 0) {   // power-of-two grids: psi = x + G y + G^2 type (PredPreyAgent.h:59) by shifts
+                            const int psi = sid & (P.S - 1), cell = psi & (GG - 1);
+                            type = psi >> (2 * P.gShift);
+                            cy = cell >> P.gShift; cx = cell & (G - 1);
+                            ob = (sid - psi) + (1 - type) * GG;
+                        } else {
+                            stateGeometry(sid, P.S, G, type, cx, cy, ob);
+                        }
+                        // PredPreyAgent.h:199-207: left, right, up, down, opposite species, torus
+                        const int xl = cx == 0 ? G - 1 : cx - 1, xr = cx == G - 1 ? 0 : cx + 1;
+                        const int yu = cy == G - 1 ? 0 : cy + 1, yd = cy == 0 ? G - 1 : cy - 1;
+                        ns[0] = ob + xl + G * cy;
+                        ns[1] = ob + xr + G * cy;
+                        ns[2] = ob + cx + G * yu;
+                        ns[3] = ob + cx + G * yd;
+                        own = X8[sid];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) nb[q] = X8[ns[q]];
+                    }
+                    unsigned long long ownN = own, nbN[4] = {nb[0], nb[1], nb[2], nb[3]};
+                    // apply the proposal's event changes (the X swap at :225-228) to the loaded words
+                    #pragma unroll 1
+                    for (int r = 0; r < evW; ++r) {   // event rows come first in a column (ascending row ids)
+                        if (fa && r < nEv) {
+                            const int xo = sXoff[r];
+                            const int rs = xo >> 3, sh = (xo & 7) * 8;
+                            const unsigned long long ins = (unsigned long long)(sXX[r] >> 8) << sh, msk = ~(0xffull << sh);
+                            if (rs == sid) ownN = (ownN & msk) | ins;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (rs == ns[q]) nbN[q] = (nbN[q] & msk) | ins;
+                        }
+                    }
+                    double diff = 0.0;
+                    if (fa) {
+                        const bool fl = (posMask(nb[0]) | posMask(nb[1]) | posMask(nb[2]) | posMask(nb[3])) != 0ull;
+                        const bool flN = (posMask(nbN[0]) | posMask(nbN[1]) | posMask(nbN[2]) | posMask(nbN[3])) != 0ull;
+                        diff = __dsub_rn(factorLogP(ownN, flN, type, P.impTab), factorLogP(own, fl, type, P.impTab));  // :109
+                    }
+                    const int qW = min(W, sfW - fb);
+#pragma unroll 1
+                    for (int q = 0; q < qW; ++q) {   // totalLogProb += ... in stale-factor insertion order
+                        const double dq = __shfl_sync(kFull, diff, q, W);
+                        if (fb + q < nSF) logImpN = __dadd_rn(logImpN, dq);
+                    }
+                }
+            }
+        };
+        if (kMC && kImpEarly) importance();
+        double csLane = 0.0;   // BLK: this lane's share of changeInSum
         #pragma unroll 1
         for (int c = 0; c < chunksW; ++c) {
             const int slot = c * W + gl;
             const int u = uB, chdr = chdrB;
             const double2 cr = crN;
-            const int du = duN;
+            const int du = BLK ? (__double2hiint(cr.y) < 0 ? -1 : 1) : duN;
             int ct4[2] = {ctN0, ctN1};
             uB = uC; chdrB = chdrC;
             uC = -1; chdrC = 0;
@@ -496,7 +571,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             duN = 0; ctN0 = kNoContrib; ctN1 = kNoContrib;
             if (uB >= 0) {
                 crN = ch.colRec[uB];
-                duN = ch.delta[uB];
+                if constexpr (!BLK) duN = ch.delta[uB];
                 const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
                 if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
                 if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
@@ -507,7 +582,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             // (reference tree) the nodes get(u) / set(u,.) will read: u + 1, 2, 4, 8, 16 sit in the same 32-record block
             const int nDesc = (!BLK && real) ? (u ? (__ffs(u) - 1) : P.treeDepth) : 0;
             double dn[5];
-            double nodeOld = cr.y;
+            double nodeOld = BLK ? fabs(cr.y) : cr.y;
             if constexpr (!BLK) {
                 const double *nearBase = &ch.colRec[real ? u : 0].y;
 #pragma unroll
@@ -577,84 +652,36 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             if (real) {
                 sU[slot] = u;
                 sDl[slot] = dlt;
+                // BLK: the stored leaf carries delta_u in its sign; the proposed column's flips on acceptance (:334)
+                if constexpr (BLK) base = ((du < 0) != self) ? -base : base;
                 scratch[slot] = make_double2(acc, base);
             }
             if (kMC) {
-                // changeInSum += ... in ascending column order (:278-281), staged through shared memory; padding slots
-                // carry term == +0.0 and x + 0.0 == x
-                sNode[gl] = real ? term : 0.0;
-                __syncwarp();
+                if constexpr (BLK) {
+                    // the blocked tree's get(u) is the exact leaf, so changeInSum already differs from the reference's
+                    // drifting differences of sums in the last bits: a fixed reduction tree replaces the serial order
+                    csLane = __dadd_rn(csLane, real ? term : 0.0);
+                } else {
+                    // changeInSum += ... in ascending column order (:278-281), staged through shared memory; padding
+                    // slots carry term == +0.0 and x + 0.0 == x
+                    sNode[gl] = real ? term : 0.0;
+                    __syncwarp();
 #pragma unroll 4
-                for (int q = 0; q < W; ++q) changeInSum = __dadd_rn(changeInSum, sNode[q]);
-                __syncwarp();
+                    for (int q = 0; q < W; ++q) changeInSum = __dadd_rn(changeInSum, sNode[q]);
+                    __syncwarp();
+                }
             }
+        }
+        if constexpr (BLK && kMC) {
+#pragma unroll
+            for (int o = W / 2; o > 0; o >>= 1) csLane = __dadd_rn(csLane, __shfl_xor_sync(kFull, csLane, o));
+            changeInSum = csLane;
         }
         __syncwarp();
 
         bool accept = act;
-        double logImpN = logImp;
         if (kMC) {
-            // ---- importance: perturb + refresh (TrajectoryImportance.h:36-54, 90-113)
-            const int sfW = warpMax(nSF);
-            const int evW = warpMax(nEv);
-            if (sfW > 0) {
-                const int G = P.G, GG = G * G;
-                const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(ch.Xb);
-                #pragma unroll 1
-                for (int fb = 0; fb < sfW; fb += W) {
-                    const int f = fb + gl;
-                    const bool fa = f < nSF;
-                    int sid = -1, type = 0, ns[4] = {-1, -1, -1, -1};
-                    unsigned long long own = 0ull, nb[4] = {0ull, 0ull, 0ull, 0ull};
-                    if (fa) {
-                        sid = __ldg(staleF + f);
-                        int cx, cy, ob;
-                        if (P.gShift >= 0) {   // power-of-two grids: psi = x + G y + G^2 type (PredPreyAgent.h:59) by shifts
-                            const int psi = sid & (P.S - 1), cell = psi & (GG - 1);
-                            type = psi >> (2 * P.gShift);
-                            cy = cell >> P.gShift; cx = cell & (G - 1);
-                            ob = (sid - psi) + (1 - type) * GG;
-                        } else {
-                            stateGeometry(sid, P.S, G, type, cx, cy, ob);
-                        }
-                        // PredPreyAgent.h:199-207: left, right, up, down, opposite species, torus
-                        const int xl = cx == 0 ? G - 1 : cx - 1, xr = cx == G - 1 ? 0 : cx + 1;
-                        const int yu = cy == G - 1 ? 0 : cy + 1, yd = cy == 0 ? G - 1 : cy - 1;
-                        ns[0] = ob + xl + G * cy;
-                        ns[1] = ob + xr + G * cy;
-                        ns[2] = ob + cx + G * yu;
-                        ns[3] = ob + cx + G * yd;
-                        own = X8[sid];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) nb[q] = X8[ns[q]];
-                    }
-                    unsigned long long ownN = own, nbN[4] = {nb[0], nb[1], nb[2], nb[3]};
-                    // apply the proposal's event changes (the X swap at :225-228) to the loaded words
-                    #pragma unroll 1
-                    for (int r = 0; r < evW; ++r) {   // event rows come first in a column (ascending row ids)
-                        if (fa && r < nEv) {
-                            const int xo = sXoff[r];
-                            const int rs = xo >> 3, sh = (xo & 7) * 8;
-                            const unsigned long long ins = (unsigned long long)(sXX[r] >> 8) << sh, msk = ~(0xffull << sh);
-                            if (rs == sid) ownN = (ownN & msk) | ins;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (rs == ns[q]) nbN[q] = (nbN[q] & msk) | ins;
-                        }
-                    }
-                    double diff = 0.0;
-                    if (fa) {
-                        const bool fl = (posMask(nb[0]) | posMask(nb[1]) | posMask(nb[2]) | posMask(nb[3])) != 0ull;
-                        const bool flN = (posMask(nbN[0]) | posMask(nbN[1]) | posMask(nbN[2]) | posMask(nbN[3])) != 0ull;
-                        diff = __dsub_rn(factorLogP(ownN, flN, type, P.impTab), factorLogP(own, fl, type, P.impTab));  // :109
-                    }
-#pragma unroll 2
-                    for (int q = 0; q < W; ++q) {   // totalLogProb += ... in stale-factor insertion order
-                        const double dq = __shfl_sync(kFull, diff, q, W);
-                        if (fb + q < nSF) logImpN = __dadd_rn(logImpN, dq);
-                    }
-                }
-            }
+            if (!kImpEarly) importance();
             // ---- calcRatioOfSums (:276-284) and the Metropolis test (:232-234)
             const double ratio = root / __dadd_rn(root, changeInSum);
             const double acceptance = __dmul_rn(expShared(__dsub_rn(logImpN, logImp)), ratio);
@@ -677,7 +704,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (accept) {
             logImp = logImpN;
             infeas = infN;
-            if (gl == 0) ch.delta[j] = (int8_t)(-dj);
+            if (!BLK && gl == 0) ch.delta[j] = (int8_t)(-dj);
         }
         #pragma unroll 1
         for (int rb = 0; rb < nW; rb += W) {
@@ -692,107 +719,135 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // ascending list, namely those sharing u >> b.
         const int Ca = accept ? C : 0;
         const int CW = warpMax(Ca);
-        // Tasks are binned by tree level -- [10, root] (tier2 nodes), [5, 10) (tier1), [0, 5) (in-record nodes) -- because
-        // a node's run length grows with its level: rounds then hold tasks of similar length.  The three per-lane
-        // counts share one prefix scan (10 bits each).
-        int nTA = 0, nTB = 0, nTC = 0;
-        const int baseB = P.tCapA, baseC = P.tCapA + P.tCapB;
-        #pragma unroll 1
-        for (int lb = 0; lb < CW; lb += W) {
-            const int l = lb + gl;
-            unsigned taskMask = 0;
-            if (l < Ca) {
-                const int u = sU[l];
-                const unsigned prev = l ? (unsigned)sU[l - 1] : 0u;
-                if constexpr (BLK) {
-                    // currentDE[u] and the leaf p_u in one 16-byte store; sums of 32 / 1024 / 32768 leaves are updated by
-                    // the first entry of each block (levels 5, 10, 15)
-                    ch.colRec[u] = scratch[l];
-                    if (l == 0 || (prev >> 5) != ((unsigned)u >> 5)) taskMask |= 1u << 5;
-                    if (l == 0 || (prev >> 10) != ((unsigned)u >> 10)) taskMask |= 1u << 10;
-                    if (l == 0 || (prev >> 15) != ((unsigned)u >> 15)) taskMask |= 1u << 15;
-                } else {
-                ch.colRec[u].x = scratch[l].x;
-                const int hbit = l ? (31 - __clz(prev ^ (unsigned)u)) : 31;
-                const unsigned low = hbit >= 31 ? 0xffffffffu : ((2u << hbit) - 1u);
-                const unsigned lowbit = (unsigned)u & (0u - (unsigned)u);
-                taskMask = (unsigned)u & low & ~(lowbit | (lowbit - 1u));                    // ancestors first reached here
-                if (l == 0 && u != 0) taskMask |= 0x80000000u;                               // the root
-                taskMask |= u ? lowbit : 0x80000000u;                                        // the column's own node
-                }
-            }
-            const int cnt = __popc(taskMask & 0xfffffc00u) | (__popc(taskMask & 0x000003e0u) << 10) | (__popc(taskMask & 0x0000001fu) << 20);
-            const int incl = groupInclusiveScan<W>(cnt, gl);
-            const int excl = incl - cnt, tot = __shfl_sync(kFull, incl, W - 1, W);
-            int posA = nTA + (excl & 1023), posB = baseB + nTB + ((excl >> 10) & 1023), posC = baseC + nTC + (excl >> 20);
-#pragma unroll 1
-            while (taskMask) {
-                const int b = __ffs(taskMask) - 1;
-                const int pos = b >= 10 ? posA++ : (b >= 5 ? posB++ : posC++);
-                sTask[pos] = (uint16_t)((l << 5) | b);
-                taskMask &= taskMask - 1;
-            }
-            nTA += tot & 1023;
-            nTB += (tot >> 10) & 1023;
-            nTC += tot >> 20;
-        }
-        const int nTasks = nTA + nTB + nTC;
-        __syncwarp();
-        {
-            // rounds of W tasks per chain: fetch, ordered sum over the run, store
-            const int roundsW = warpMax((nTasks + W - 1) / W);
-            // task of the coming round, fetched one round ahead so its node load overlaps the current ordered sum
-            int qN = 0, endN = 0;
-            bool haveN = false;
-            double vN = 0.0;
-            double *npN = nullptr;
-            auto fetch = [&](int t) {
-                haveN = t < nTasks;
-                qN = endN = 0;
-                if (haveN) {
-                    const int tk = sTask[t < nTA ? t : (t < nTA + nTB ? baseB + t - nTA : baseC + t - nTA - nTB)];
-                    const int l0 = tk >> 5, b = tk & 31;
-                    const unsigned u0 = (unsigned)sU[l0];
-                    const unsigned pre = u0 >> b;
-                    const unsigned a = b == 31 ? 0u : (pre << b);
-                    bool own = false;
-                    if constexpr (BLK) {
-                        npN = b == 5 ? &ch.tier1[pre] : (b == 10 ? &ch.tier2[pre] : &sTop[pre]);
-                    } else {
-                        npN = ch.node((int)a);
-                        own = a == u0;
-                    }
-                    vN = own ? scratch[l0].y : *npN;
-                    qN = own ? l0 + 1 : l0;
-                    // the run ends at the first entry outside the node's index range [a, a + 2^b): binary search in the
-                    // ascending list (unsigned compare makes the root's key 2^31 exceed every column)
-                    const unsigned key = (pre + 1u) << b;
-                    int lo = qN, hi = Ca;
-                    #pragma unroll 1
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if ((unsigned)sU[mid] < key) lo = mid + 1; else hi = mid;
-                    }
-                    endN = lo;
-                }
-            };
-            fetch(gl);
+        if constexpr (BLK) {
+            // Blocked tree: currentDE[u] and the signed leaf in one 16-byte store; then every sum of 32 / 1024 / 32768 leaves
+            // that covers changed columns receives the sum of their leaf changes.  The columns are ascending, so the entries
+            // under one sum are consecutive slots: one inclusive prefix sum over the W slots of a round gives every such run
+            // as a difference of two prefix values.  The run's last slot adds it to the sum (fire-and-forget reductions for
+            // the two global tiers: nothing waits on the old value; the top tier is in shared memory).
+            constexpr unsigned gMask = W == 32 ? 0xffffffffu : ((1u << W) - 1u);
+            const int gShiftLane = (threadIdx.x & 31) & ~(W - 1);
             #pragma unroll 1
-            for (int rd = 0; rd < roundsW; ++rd) {
-                int q = qN;
-                const int end = endN;
-                const bool have = haveN;
-                double v = vN;
-                double *np = npN;
-                fetch((rd + 1) * W + gl);
-                #pragma unroll 1
-                while (__any_sync(kFull, q < end)) {
-                    if (q < end) {
-                        v = __dadd_rn(v, sDl[q]);
-                        ++q;
+            for (int lb = 0; lb < CW; lb += W) {
+                const int l = lb + gl;
+                const bool valid = l < Ca;
+                const unsigned u = valid ? (unsigned)sU[l] : 0x7fffffffu;
+                const double dl = valid ? sDl[l] : 0.0;
+                if (valid) ch.colRec[u] = scratch[l];
+                double pin = dl;
+#pragma unroll
+                for (int o = 1; o < W; o <<= 1) {
+                    const double t = __shfl_up_sync(kFull, pin, o, W);
+                    if (gl >= o) pin = __dadd_rn(pin, t);
+                }
+                const double pexRaw = __shfl_up_sync(kFull, pin, 1, W);
+                const double pex = gl ? pexRaw : 0.0;
+                const unsigned prevU = __shfl_up_sync(kFull, u, 1, W), nextU = __shfl_down_sync(kFull, u, 1, W);
+#pragma unroll
+                for (int lv = 5; lv <= 15; lv += 5) {
+                    const bool head = gl == 0 || (prevU >> lv) != (u >> lv);
+                    const bool tail = gl == W - 1 || (nextU >> lv) != (u >> lv);
+                    const unsigned hm = (__ballot_sync(kFull, head) >> gShiftLane) & gMask & ((2u << gl) - 1u);
+                    const int start = 31 - __clz(hm);                          // first slot of this slot's run (bit 0 is always set)
+                    const double basev = __shfl_sync(kFull, pex, start, W);
+                    if (valid && tail) {
+                        const double seg = __dsub_rn(pin, basev);
+                        if (lv == 5) atomicAdd(&ch.tier1[u >> 5], seg);
+                        else if (lv == 10) atomicAdd(&ch.tier2[u >> 10], seg);
+                        else sTop[u >> 15] = __dadd_rn(sTop[u >> 15], seg);
                     }
                 }
-                if (have) *np = v;
+                __syncwarp();   // a run may continue in the next round: its two updates of one sum stay ordered
+            }
+        } else {
+            // Tasks are binned by tree level -- [10, root] (tier2 nodes), [5, 10) (tier1), [0, 5) (in-record nodes) -- because
+            // a node's run length grows with its level: rounds then hold tasks of similar length.  The three per-lane
+            // counts share one prefix scan (10 bits each).
+            int nTA = 0, nTB = 0, nTC = 0;
+            const int baseB = P.tCapA, baseC = P.tCapA + P.tCapB;
+            #pragma unroll 1
+            for (int lb = 0; lb < CW; lb += W) {
+                const int l = lb + gl;
+                unsigned taskMask = 0;
+                if (l < Ca) {
+                    const int u = sU[l];
+                    const unsigned prev = l ? (unsigned)sU[l - 1] : 0u;
+                    ch.colRec[u].x = scratch[l].x;
+                    const int hbit = l ? (31 - __clz(prev ^ (unsigned)u)) : 31;
+                    const unsigned low = hbit >= 31 ? 0xffffffffu : ((2u << hbit) - 1u);
+                    const unsigned lowbit = (unsigned)u & (0u - (unsigned)u);
+                    taskMask = (unsigned)u & low & ~(lowbit | (lowbit - 1u));                    // ancestors first reached here
+                    if (l == 0 && u != 0) taskMask |= 0x80000000u;                               // the root
+                    taskMask |= u ? lowbit : 0x80000000u;                                        // the column's own node
+                }
+                const int cnt = __popc(taskMask & 0xfffffc00u) | (__popc(taskMask & 0x000003e0u) << 10) | (__popc(taskMask & 0x0000001fu) << 20);
+                const int incl = groupInclusiveScan<W>(cnt, gl);
+                const int excl = incl - cnt, tot = __shfl_sync(kFull, incl, W - 1, W);
+                int posA = nTA + (excl & 1023), posB = baseB + nTB + ((excl >> 10) & 1023), posC = baseC + nTC + (excl >> 20);
+    #pragma unroll 1
+                while (taskMask) {
+                    const int b = __ffs(taskMask) - 1;
+                    const int pos = b >= 10 ? posA++ : (b >= 5 ? posB++ : posC++);
+                    sTask[pos] = (uint16_t)((l << 5) | b);
+                    taskMask &= taskMask - 1;
+                }
+                nTA += tot & 1023;
+                nTB += (tot >> 10) & 1023;
+                nTC += tot >> 20;
+            }
+            const int nTasks = nTA + nTB + nTC;
+            __syncwarp();
+            {
+                // rounds of W tasks per chain: fetch, ordered sum over the run, store
+                const int roundsW = warpMax((nTasks + W - 1) / W);
+                // task of the coming round, fetched one round ahead so its node load overlaps the current ordered sum
+                int qN = 0, endN = 0;
+                bool haveN = false;
+                double vN = 0.0;
+                double *npN = nullptr;
+                auto fetch = [&](int t) {
+                    haveN = t < nTasks;
+                    qN = endN = 0;
+                    if (haveN) {
+                        const int tk = sTask[t < nTA ? t : (t < nTA + nTB ? baseB + t - nTA : baseC + t - nTA - nTB)];
+                        const int l0 = tk >> 5, b = tk & 31;
+                        const unsigned u0 = (unsigned)sU[l0];
+                        const unsigned pre = u0 >> b;
+                        const unsigned a = b == 31 ? 0u : (pre << b);
+                        npN = ch.node((int)a);
+                        const bool own = a == u0;
+                        vN = own ? scratch[l0].y : *npN;
+                        qN = own ? l0 + 1 : l0;
+                        // the run ends at the first entry outside the node's index range [a, a + 2^b): binary search in the
+                        // ascending list (unsigned compare makes the root's key 2^31 exceed every column)
+                        const unsigned key = (pre + 1u) << b;
+                        int lo = qN, hi = Ca;
+                        #pragma unroll 1
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if ((unsigned)sU[mid] < key) lo = mid + 1; else hi = mid;
+                        }
+                        endN = lo;
+                    }
+                };
+                fetch(gl);
+                #pragma unroll 1
+                for (int rd = 0; rd < roundsW; ++rd) {
+                    int q = qN;
+                    const int end = endN;
+                    const bool have = haveN;
+                    double v = vN;
+                    double *np = npN;
+                    fetch((rd + 1) * W + gl);
+                    #pragma unroll 1
+                    while (__any_sync(kFull, q < end)) {
+                        if (q < end) {
+                            v = __dadd_rn(v, sDl[q]);
+                            ++q;
+                        }
+                    }
+                    if (have) *np = v;
+                }
             }
         }
         __syncwarp();
@@ -897,7 +952,7 @@ __global__ void initColsKernel(DevProblem P, DevChains S) {
         }
         ch.colRec[j].x = de;
         if (P.blockedTree) {   // every leaf 1.0; block sums = number of columns in the block
-            ch.colRec[j].y = 1.0;
+            ch.colRec[j].y = dj < 0 ? -1.0 : 1.0;   // leaf 1.0 with delta_j in the sign bit
             if ((j & 31) == 0) ch.tier1[j >> 5] = (double)(min(j + 32, P.nCols) - j);
             if ((j & 1023) == 0) ch.tier2[j >> 10] = (double)(min(j + 1024, P.nCols) - j);
             if ((j & 32767) == 0) S.tier3[(size_t)chain * 32 + (j >> 15)] = (double)(min(j + 32768, P.nCols) - j);
