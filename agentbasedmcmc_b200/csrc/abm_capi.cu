@@ -311,10 +311,20 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     while (rec.size() % 4) rec.push_back(0);
     if (maxCoupled > 2040) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2040 others");
 
-    std::vector<double> impTab(7 + 24, 0.0);
+    // [7] lgamma(occ+1), [2][2][6] log(pi/pibar), then the factor log-probability of TrajectoryImportance::refresh
+    // (TrajectoryImportance.h:96-108) for every (type, neighbour flag, set of present acts), summed in the reference's order
+    std::vector<double> impTab(7 + 24 + 4 * 64, 0.0);
     if (G > 0) {
         std::copy(desc->imp_lgamma, desc->imp_lgamma + 7, impTab.begin());
         std::copy(desc->imp_logratio, desc->imp_logratio + 24, impTab.begin() + 7);
+        for (int tn = 0; tn < 4; ++tn)
+            for (int bits = 0; bits < 64; ++bits) {
+                const int occ = __builtin_popcount(bits);
+                volatile double pv = occ > 1 ? impTab[occ] : 0.0;   // volatile: one rounded add per act, no reassociation
+                for (int a2 = 0; a2 < kActs; ++a2)
+                    if ((bits >> a2) & 1) pv = pv + impTab[7 + tn * kActs + a2];
+                impTab[31 + tn * 64 + bits] = pv;
+            }
     }
 
     abm_problem *p = new abm_problem();

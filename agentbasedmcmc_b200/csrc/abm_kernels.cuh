@@ -112,19 +112,17 @@ __device__ __forceinline__ unsigned long long posMask(unsigned long long w) {
     const unsigned long long m7 = 0x00007f7f7f7f7f7full, m8 = 0x0000808080808080ull;
     return (((w & m7) + m7) & ~w) & m8;
 }
-// newLogP of refresh(): lgamma(occ+1) if occ>1, then += log(pi/pibar) per act with X>0, act order
-__device__ __noinline__ double factorLogP(unsigned long long own, bool neighbour, int type,
+// newLogP of refresh() (TrajectoryImportance.h:96-108): lgamma(occ+1) if occ>1, then += log(pi/pibar) per act with X>0, in act
+// order.  It depends only on which of the 6 acts are present, the agent type and the neighbour flag, so the host tabulates
+// it with exactly that summation (abm_problem_create): impTab[31 + ((type*2 + neighbour) << 6) + presentActs].
+__device__ __forceinline__ int presentActs(unsigned long long pm) {   // bit a = (X[act a] > 0), from posMask's bits 8a+7
+    const unsigned lo = (unsigned)(pm >> 7), hi = (unsigned)(pm >> 39);
+    // bits 0,8,16,24 of lo times (1 + 2^7 + 2^14 + 2^21) land, without carries, on bits 21..24
+    return (int)(((lo * 0x00204081u) >> 21) & 15u) | (int)((hi & 1u) << 4) | (int)((hi >> 3) & 32u);
+}
+__device__ __forceinline__ double factorLogP(unsigned long long own, bool neighbour, int type,
                                              const double *__restrict__ impTab) {
-    unsigned long long pm = posMask(own);
-    int occ = __popcll(pm);
-    double p = occ > 1 ? __ldg(impTab + occ) : 0.0;
-    if (occ > 0) {
-        const double *ratio = impTab + 7 + (type * 2 + (neighbour ? 1 : 0)) * kActs;
-#pragma unroll
-        for (int a = 0; a < kActs; ++a)
-            if ((pm >> (8 * a + 7)) & 1ull) p = __dadd_rn(p, __ldg(ratio + a));
-    }
-    return p;
+    return __ldg(impTab + 31 + ((type * 2 + (neighbour ? 1 : 0)) << 6) + presentActs(posMask(own)));
 }
 
 // (type, x, y) of a state id and the base index of the opposite species at the same time, for grids that are not a
@@ -372,7 +370,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 target = __dsub_rn(target, v);
             }
             // three 32-ary levels: tier2 (1024 leaves each), tier1 (32 leaves), leaves
-#pragma unroll 1
+#pragma unroll
             for (int lvl = 2; lvl >= 0; --lvl) {
                 const int first = sel * 32;
                 const int count = lvl == 2 ? P.t2Len : (lvl == 1 ? P.t1Len : nCols);
@@ -727,13 +725,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             // the two global tiers: nothing waits on the old value; the top tier is in shared memory).
             constexpr unsigned gMask = W == 32 ? 0xffffffffu : ((1u << W) - 1u);
             const int gShiftLane = (threadIdx.x & 31) & ~(W - 1);
+            double2 scN = make_double2(0.0, 0.0);   // the staged {DE', signed leaf} of the coming round, one round ahead
+            if (gl < Ca) scN = scratch[gl];
             #pragma unroll 1
             for (int lb = 0; lb < CW; lb += W) {
                 const int l = lb + gl;
                 const bool valid = l < Ca;
                 const unsigned u = valid ? (unsigned)sU[l] : 0x7fffffffu;
                 const double dl = valid ? sDl[l] : 0.0;
-                if (valid) ch.colRec[u] = scratch[l];
+                const double2 sc = scN;
+                if (l + W < Ca) scN = scratch[l + W];
+                if (valid) ch.colRec[u] = sc;
                 double pin = dl;
 #pragma unroll
                 for (int o = 1; o < W; o <<= 1) {
