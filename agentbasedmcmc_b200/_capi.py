@@ -20,6 +20,7 @@ SYMBOLS = [
     "abm_chains_synchronize", "abm_chains_get_state", "abm_chains_get_counters", "abm_chains_get_infeasibility",
     "abm_chains_get_trajectories", "abm_chains_get_statistics", "abm_chains_reset_statistics",
     "abm_chains_record_series", "abm_chains_get_series",
+    "abm_basis_minimise", "abm_basis_destroy", "abm_basis_get_dims", "abm_basis_get", "abm_basis_get_rows",
 ]
 
 
@@ -70,7 +71,7 @@ def load():
     L.abm_chains_create.argtypes = [vp, C.c_int32, C.c_uint64, C.c_uint64, vp, vpp]
     L.abm_chains_destroy.argtypes = [vp]
     L.abm_chains_init.argtypes = [vp, i8p, C.c_int32]
-    L.abm_chains_init_from_prior.argtypes = [vp, f64p, C.c_double, C.c_double, C.c_uint64, i8p]
+    L.abm_chains_init_from_prior.argtypes = [vp, f64p, C.c_double, C.c_double, C.c_uint64, i8p, C.c_int32]
     L.abm_chains_find_feasible.argtypes = [vp, C.c_int64, f64p, C.c_int64, i64p]
     L.abm_chains_step.argtypes = [vp, C.c_int64]
     L.abm_chains_step_traced.argtypes = [vp, C.c_int64, f64p, i32p, i32p, u8p, i32p]
@@ -84,6 +85,11 @@ def load():
     L.abm_chains_reset_statistics.argtypes = [vp]
     L.abm_chains_record_series.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.abm_chains_get_series.argtypes = [vp, i32p]
+    L.abm_basis_minimise.argtypes = [C.c_int32, i32p, i32p, i32p, i32p, i32p, vpp]
+    L.abm_basis_destroy.argtypes = [vp]
+    L.abm_basis_get_dims.argtypes = [vp, i32p, i32p, i32p, i32p, i64p, i64p]
+    L.abm_basis_get.argtypes = [vp, i32p, i32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p]
+    L.abm_basis_get_rows.argtypes = [vp, i64p, i32p, i32p]
     _lib = L
     return L
 

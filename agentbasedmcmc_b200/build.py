@@ -20,7 +20,7 @@ NVCC_FLAGS = [
 def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path = OUT) -> Path:
     """``defines``/``out`` build an experimental variant next to the product library (kernel A/B runs select it with
     the ABM_LIB environment variable, see _capi.py)."""
-    sources = [SRC / "abm_capi.cu"]
+    sources = [SRC / "abm_capi.cu", SRC / "abm_basis.cpp"]
     deps = list(SRC.glob("*")) + [ROOT / "include" / "abmcmc_b200.h"]
     if not force and out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return out

@@ -15,6 +15,8 @@
 
 using namespace abm;
 
+int abmSetError(int code, const std::string &msg);   // shared with abm_basis.cpp
+
 namespace {
 
 thread_local std::string g_err;
@@ -23,6 +25,11 @@ int fail(int code, const std::string &msg) {
     g_err = msg;
     return code;
 }
+}  // namespace
+
+int abmSetError(int code, const std::string &msg) { return fail(code, msg); }
+
+namespace {
 
 #define CUDA_TRY(expr)                                                                             \
     do {                                                                                           \
@@ -486,8 +493,9 @@ int abm_chains_init(abm_chains *c, const int8_t *initEvents, int32_t nInit) {
 }
 
 int abm_chains_init_from_prior(abm_chains *c, const double *actPmf, double pPredator, double pPrey, uint64_t seed,
-                               int8_t *eventsOut) {
+                               int8_t *eventsOut, int32_t startKind) {
     if (!c || !actPmf) return fail(ABM_ERR_INVALID, "null argument");
+    if (startKind != ABM_START_BERNOULLI && startKind != ABM_START_POISSON) return fail(ABM_ERR_INVALID, "unknown start state kind");
     const DevProblem &P = c->p->d;
     if (P.G <= 0) return fail(ABM_ERR_INVALID, "prior sampling needs the PredPrey geometry");
     CUDA_TRY(cudaSetDevice(c->p->device));
@@ -500,7 +508,7 @@ int abm_chains_init_from_prior(abm_chains *c, const double *actPmf, double pPred
     const size_t smem = size_t(2) * P.S * sizeof(int);
     cudaError_t e = cudaFuncSetAttribute(priorSampleKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e == cudaSuccess) {
-        priorSampleKernel<<<c->n, 128, smem, c->stream>>>(P, c->n, seed, c->firstChain, dPmf, pPredator, pPrey, dEvents);
+        priorSampleKernel<<<c->n, 128, smem, c->stream>>>(P, c->n, seed, c->firstChain, dPmf, pPredator, pPrey, startKind, dEvents);
         e = cudaGetLastError();
     }
     int rc = ABM_OK;

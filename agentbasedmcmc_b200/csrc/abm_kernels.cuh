@@ -967,13 +967,13 @@ __global__ void initColsKernel(DevProblem P, DevChains S) {
 
 // Per-chain initial trajectories drawn from the prior, on the device: Forecast::nextSample(startState, T, isFermionic =
 // false) (Forecast.h:102-150) with the Bernoulli start state (BernoulliStartState.h:36-47): every agent state is occupied
-// with its start probability; then, timestep by timestep, every agent draws an act from PredPreyAgent::timestep given
+// with its start probability (or, startKind 1, by a Poisson number of agents: PoissonStartState.h:38-44); then, timestep by timestep, every agent draws an act from PredPreyAgent::timestep given
 // the opposite-species occupation of its four neighbours (PredPreyAgent.h:124-157) and its consequences populate the next
 // state (:98-115).  One CTA per chain; uniforms from Philox4x32-10 keyed by (seed, chain) with counter (state, time, agent).
 // Only "event count > 0" matters to the sampler's constructor (SparseBasisSampler.h:147), so events are written as 0/1.
 __global__ void priorSampleKernel(DevProblem P, int nChains, unsigned long long seed, unsigned long long firstChain,
                                   const double *__restrict__ actPmf /* [2][2][6] */, double pPredator, double pPrey,
-                                  int8_t *__restrict__ events /* [nChains][nEvents] */) {
+                                  int startKind, int8_t *__restrict__ events /* [nChains][nEvents] */) {
     extern __shared__ int priorSmem[];
     int *cur = priorSmem, *nxt = priorSmem + P.S;
     const int chain = blockIdx.x;
@@ -985,7 +985,14 @@ __global__ void priorSampleKernel(DevProblem P, int nChains, unsigned long long 
     for (int psi = threadIdx.x; psi < P.S; psi += blockDim.x) {
         uint32_t w[4];
         philox4x32_10((uint32_t)psi, 0xffffffffu, (uint32_t)chainId, (uint32_t)(chainId >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), w);
-        cur[psi] = canonical_from_words(w[0], w[1]) < (psi < GG ? pPredator : pPrey) ? 1 : 0;   // type 0 = PREDATOR (PredPreyAgent.h:27-30)
+        const double u0 = canonical_from_words(w[0], w[1]), rate = psi < GG ? pPredator : pPrey;   // type 0 = PREDATOR (PredPreyAgent.h:27-30)
+        int n0 = u0 < rate ? 1 : 0;
+        if (startKind == 1) {   // PoissonStartState::nextSample (PoissonStartState.h:38-44): Poisson(rate) by inversion
+            double pk = exp(-rate), cum = pk;
+            n0 = 0;
+            while (u0 >= cum && n0 < 64) { ++n0; pk *= rate / n0; cum += pk; }
+        }
+        cur[psi] = n0;
         nxt[psi] = 0;
     }
     __syncthreads();

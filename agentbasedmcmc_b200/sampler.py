@@ -122,7 +122,8 @@ class SparseBasisSampler:
             if return_prior_sample:
                 self.prior_sample = np.zeros((n_chains, problem.n_events), np.int8)
             check(L.abm_chains_init_from_prior(self.h, _ptr(pmf, C.c_double), float(a["pp_params"][0]), float(a["pp_params"][1]),
-                                               seed ^ 0x5DEECE66D, _ptr(self.prior_sample, C.c_int8)))
+                                               seed ^ 0x5DEECE66D, _ptr(self.prior_sample, C.c_int8),
+                                               int(a["start_kind"][0]) if "start_kind" in a else 0))
         else:
             n_init = 0 if initial_states is None else initial_states.shape[1]
             check(L.abm_chains_init(self.h, _ptr(initial_states, C.c_int8), n_init))

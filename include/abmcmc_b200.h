@@ -112,9 +112,13 @@ ABM_API int abm_chains_init(abm_chains *c, const int8_t *init_events, int32_t n_
  * isFermionic = false) with the Bernoulli start state (Forecast.h:102-150, BernoulliStartState.h:36-47), which is what
  * FiguresForPaper.h:56,162 hands to every chain.  act_pmf = PredPreyAgent::timestep by (type, has opposite-species
  * neighbour, act) ([2][2][6], ABMP array pp_actpmf); Philox streams keyed by (seed, chain).  events_out (host,
- * [n_chains][n_events], may be NULL) receives the drawn trajectories as 0/1. */
+ * [n_chains][n_events], may be NULL) receives the drawn trajectories as 0/1.  start_kind selects the start state
+ * distribution: ABM_START_BERNOULLI (the one PredPreyProblem.h:64-66 uses) or ABM_START_POISSON (its commented-out
+ * alternative, PredPreyProblem.h:60-62 / PoissonStartState.h:38-44: a Poisson(p) number of agents per state). */
+#define ABM_START_BERNOULLI 0
+#define ABM_START_POISSON 1
 ABM_API int abm_chains_init_from_prior(abm_chains *c, const double *act_pmf, double p_predator, double p_prey, uint64_t seed,
-                                       int8_t *events_out);
+                                       int8_t *events_out, int32_t start_kind);
 
 /* findInitialFeasibleSolution (:254-263) + importanceFunc->setState / getLogValue (:183-184).
  * Uniforms: Philox unless `uniforms` (host, [n_chains][n_uniforms], one per iteration) is given.
@@ -170,6 +174,27 @@ ABM_API int abm_chains_reset_statistics(abm_chains *c);
 ABM_API int abm_chains_record_series(abm_chains *c, int32_t n_chains, int32_t thin, int32_t capacity);
 ABM_API int abm_chains_get_series(abm_chains *c, int32_t *out);
 ABM_API int abm_problem_n_synopsis(const abm_problem *p); /* floor(log2(G)) - 1 (FiguresForPaper.h:246) */
+
+/* ---- basis builder (host code, no device needed): the step BEFORE the sampler, SURVEY.md section 8(f)2.
+ * abm_basis_minimise = TableauNormMinimiser<T>::TableauNormMinimiser(const ConvexPolyhedron<T>&) followed by
+ * findMinimalBasis() (TableauNormMinimiser.h:201-256): constraints lower[i] <= sum_k val[k] X[idx[k]] <= upper[i]
+ * (CSR, con_ptr[n_constraints + 1]; equality where lower == upper) become a tableau with one auxiliary variable per
+ * inequality, and every equality row is eliminated by the reference's Markowitz pivoting (:258-335) -- the same pivots in
+ * the same order, hence the same basis entry for entry; only the search skips ineligible rows/columns without walking
+ * them (the reference's quadratic cost).  Outputs, in the layout reference_flatten.hpp writes to ABMP files:
+ *   L, U, F, basis [n_rows]; col_is_basic [n_cols]; the non-basic columns as CSR by column over the NON-REDUCED rows
+ *   (nb_col [n_nonbasic], nb_ptr [n_nonbasic + 1], nb_row / nb_val [nnz_nonbasic], rows ascending) -- what
+ *   SparseBasisSampler's constructor reads (:121-158); abm_basis_get_rows gives every tableau row in full
+ *   (row_ptr [n_rows + 1], ascending columns), from which a TableauNormMinimiser object can be re-assembled. */
+typedef struct abm_basis abm_basis;
+ABM_API int abm_basis_minimise(int32_t n_constraints, const int32_t *con_ptr, const int32_t *con_idx, const int32_t *con_val,
+                               const int32_t *lower, const int32_t *upper, abm_basis **out);
+ABM_API int abm_basis_destroy(abm_basis *b);
+ABM_API int abm_basis_get_dims(const abm_basis *b, int32_t *n_rows, int32_t *n_cols, int32_t *n_aux, int32_t *n_nonbasic,
+                               int64_t *nnz_nonbasic, int64_t *nnz_rows);
+ABM_API int abm_basis_get(const abm_basis *b, int32_t *L, int32_t *U, int32_t *F, int32_t *basis, uint8_t *col_is_basic,
+                          int32_t *nb_col, int32_t *nb_ptr, int32_t *nb_row, int32_t *nb_val);
+ABM_API int abm_basis_get_rows(const abm_basis *b, int64_t *row_ptr, int32_t *col_idx, int32_t *val);
 
 #ifdef __cplusplus
 }

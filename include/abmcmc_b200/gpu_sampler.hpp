@@ -137,12 +137,12 @@ public:
     // ---- batched use: nChains independent chains from the same initial state on Philox streams (seed, chain)
     void batched(int nChains, uint64_t seed) { createChains(nChains, seed, /*exact=*/false); }
     // ... or each chain from its own prior sample drawn on the device (what FiguresForPaper.h:56 gives every chain);
-    // pPredator / pPrey are the Bernoulli start-state probabilities of the problem (PredPreyProblem.h:36-37)
-    void batchedFromPrior(int nChains, uint64_t seed, double pPredator, double pPrey) {
+    // pPredator / pPrey are the start-state probabilities (Bernoulli) or rates (Poisson) of the problem (PredPreyProblem.h:36-37)
+    void batchedFromPrior(int nChains, uint64_t seed, double pPredator, double pPrey, int startKind = ABM_START_BERNOULLI) {
         if (chains_) { abm_chains_destroy(chains_); chains_ = nullptr; }
         nChains_ = nChains;
         detail::check(abm_chains_create(problem_, nChains, seed, 0, nullptr, &chains_), "abm_chains_create");
-        detail::check(abm_chains_init_from_prior(chains_, actPmf_.data(), pPredator, pPrey, seed ^ 0x5DEECE66Dull, nullptr), "abm_chains_init_from_prior");
+        detail::check(abm_chains_init_from_prior(chains_, actPmf_.data(), pPredator, pPrey, seed ^ 0x5DEECE66Dull, nullptr, startKind), "abm_chains_init_from_prior");
         detail::check(abm_chains_find_feasible(chains_, 0, nullptr, 0, nullptr), "abm_chains_find_feasible");
         refresh();
     }

@@ -85,14 +85,26 @@ static uint64_t bitsOf(double d) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Start-state prior of a problem: the Bernoulli one PredPreyProblem hard-wires (PredPreyProblem.h:64-66), or the Poisson
+// alternative the reference keeps commented out next to it (:60-62, PoissonStartState.h:18-31) with the same per-type
+// rates.  startKind: 0 = Bernoulli, 1 = Poisson.
 template <int G>
-AbmpFile exportProblem(const PredPreyProblem<G> &problem, int seed, double pMakeObs, double pObsIfPresent) {
+Prior<PredPreyAgent<G>> makePrior(int T, int startKind, double pPred, double pPrey) {
+    typedef PredPreyAgent<G> Agent;
+    auto rate = [pPred, pPrey](Agent agent) { return agent.type() == Agent::PREDATOR ? pPred : pPrey; };
+    if (startKind == 1) return Prior<Agent>(T, PoissonStartState<Agent>(rate));
+    return Prior<Agent>(T, BernoulliStartState<Agent>(rate));
+}
+
+template <int G>
+AbmpFile exportProblem(const PredPreyProblem<G> &problem, int seed, double pMakeObs, double pObsIfPresent, int startKind = 0) {
     typedef PredPreyAgent<G> Agent;
     AbmpFile f;
     abmcmc::flattenTableau<TableauNormMinimiser<occ_t>, occ_t>(f, problem.tableau, problem.posterior.factors, problem.kappa);
     abmcmc::flattenPredPreyImportance<Agent>(f, G, problem.nTimesteps());
     f.f64["pp_params"] = {problem.pPredator, problem.pPrey, pMakeObs, pObsIfPresent};
     f.i32["gen_seed"] = {seed};
+    f.i32["start_kind"] = {startKind};
     std::vector<int32_t> rtIdx, rtVal;
     const std::vector<occ_t> &rt = problem.realTrajectory;
     for (size_t e = 0; e < rt.size(); ++e)
@@ -138,7 +150,8 @@ PredPreyProblem<G> importProblem(const AbmpFile &f) {
     const auto &op = f.D("obs_p");
     for (size_t k = 0; k < ot.size(); ++k)
         observations.emplace_back(State<Agent>(ot[k], Agent(oa[k])), on[k], op[k]);
-    p.prior = Prior<Agent>(T, p.startStatePrior());
+    const int startKind = f.i32.count("start_kind") ? f.I("start_kind")[0] : 0;
+    p.prior = makePrior<G>(T, startKind, p.pPredator, p.pPrey);
     p.likelihood = Likelihood<Agent>(observations);
     p.posterior = p.likelihood * p.prior;
 
@@ -171,12 +184,23 @@ std::vector<occ_t> priorSample(const PredPreyProblem<G> &problem) {
 // ---------------------------------------------------------------------------------------------
 template <int G>
 int cmdGen(int T, int seed, double kappa, const std::string &out, double pPred, double pPrey, double pMakeObs,
-           double pObsIfPresent) {
+           double pObsIfPresent, int startKind) {
     auto t0 = std::chrono::steady_clock::now();
     Random::gen.seed(seed);  // FiguresForPaper.h:33
-    PredPreyProblem<G> problem(T, pPred, pPrey, pMakeObs, pObsIfPresent, kappa);
+    // the member-by-member assembly of PredPreyProblem's constructor (PredPreyProblem.h:46-56), so that the start state can
+    // be either of the two the reference provides; with startKind 0 it draws the same random numbers in the same order
+    PredPreyProblem<G> problem;
+    problem.pPredator = pPred;
+    problem.pPrey = pPrey;
+    problem.kappa = kappa;
+    problem.prior = makePrior<G>(T, startKind, pPred, pPrey);
+    problem.realTrajectory = problem.prior.nextSample(true);
+    problem.likelihood = Likelihood<PredPreyAgent<G>>(problem.realTrajectory, pMakeObs, pObsIfPresent);
+    problem.posterior = problem.likelihood * problem.prior;
+    problem.tableau = TableauNormMinimiser<occ_t>(problem.posterior.constraints);
+    problem.tableau.findMinimalBasis();
     auto t1 = std::chrono::steady_clock::now();
-    AbmpFile f = exportProblem<G>(problem, seed, pMakeObs, pObsIfPresent);
+    AbmpFile f = exportProblem<G>(problem, seed, pMakeObs, pObsIfPresent, startKind);
     f.f64["gen_seconds"] = {std::chrono::duration<double>(t1 - t0).count()};
     f.write(out);
     const auto &d = f.I("dims");
@@ -497,6 +521,105 @@ int cmdMarginals(const AbmpFile &f, int nThreads, long nSamples, long burnin, co
     return 0;
 }
 
+// Synopsis series of long reference chains (the window sweep's CPU arm): per thread one chain from its own prior sample,
+// `burnin` calls of sampler(), then nSamples calls, each mapped to the synopsis of its end state exactly as
+// FiguresForPaper.h:93-104 does (TrajectoryToModelState(T,T) then synopsis(), :245-263: agents inside nested squares of
+// side G/2, G/4, ... > 1 along the diagonal).  Output: series i32[nThreads][nSamples][nSyn], seconds of the sampling part
+// (max over threads), Metropolis steps.
+template <int G>
+int cmdSeries(const AbmpFile &f, int nThreads, long nSamples, long burnin, const std::string &out) {
+    typedef PredPreyAgent<G> Agent;
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    const int T = problem.nTimesteps();
+    int nSyn = 0;
+    for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;
+    Random::gen.seed(2468);
+    std::vector<std::vector<occ_t>> inits;
+    for (int t = 0; t < nThreads; ++t) inits.push_back(priorSample<G>(problem));
+    struct Res { std::vector<int32_t> series; double seconds = 0; long steps = 0; };
+    std::vector<std::future<Res>> fut;
+    {
+        SilenceStdout quiet;
+        for (int t = 0; t < nThreads; ++t)
+            fut.push_back(std::async(std::launch::async, [&problem, &inits, t, T, nSyn, nSamples, burnin]() {
+                Random::gen.seed(7000 + t);
+                SparseBasisSampler<occ_t> sampler(problem.tableau, problem.posterior.factors,
+                                                  problem.posterior.perturbableFunctionFactory(), inits[t], problem.kappa);
+                for (long b = 0; b < burnin; ++b) sampler();
+                Res r;
+                r.series.reserve(size_t(nSamples) * nSyn);
+                const long s0 = sampler.stats.nSamples();
+                auto t0 = std::chrono::steady_clock::now();
+                for (long n = 0; n < nSamples; ++n) {
+                    const std::vector<occ_t> &x = sampler();
+                    ModelState<Agent> endState(x, T, T);
+                    int origin = 0;
+                    for (int ps = G / 2; ps > 1; ps /= 2) {
+                        double occ = 0.0;
+                        for (int xx = 0; xx < ps; ++xx)
+                            for (int yy = 0; yy < ps; ++yy)
+                                occ += endState[Agent(origin + xx, origin + yy, Agent::PREDATOR)] +
+                                       endState[Agent(origin + xx, origin + yy, Agent::PREY)];
+                        r.series.push_back(int32_t(occ));
+                        origin += ps;
+                    }
+                }
+                r.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                r.steps = sampler.stats.nSamples() - s0;
+                return r;
+            }));
+        for (auto &x : fut) x.wait();
+    }
+    AbmpFile o;
+    std::vector<int32_t> all;
+    double sec = 0, steps = 0;
+    for (auto &x : fut) {
+        Res r = x.get();
+        all.insert(all.end(), r.series.begin(), r.series.end());
+        sec = std::max(sec, r.seconds);
+        steps += r.steps;
+    }
+    o.i32["series"] = all;
+    o.i32["shape"] = {nThreads, int32_t(nSamples), nSyn};
+    o.f64["timing"] = {sec, steps, double(burnin)};
+    o.write(out);
+    return 0;
+}
+
+// The input of TableauNormMinimiser: posterior.constraints (a ConvexPolyhedron, one Constraint per factor:
+// lowerBound <= coefficients . X <= upperBound), exported as CSR in the reference's own entry order, plus the tableau the
+// unmodified TableauNormMinimiser makes of it (timed).  Feeds the parity test of the own basis builder (abm_basis_*).
+template <int G>
+int cmdConstraints(const AbmpFile &f, const std::string &out, int rebuild) {
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    AbmpFile o;
+    std::vector<int32_t> ptr{0}, idx, val, lo, up;
+    for (const auto &c : problem.posterior.constraints) {
+        for (int k = 0; k < c.coefficients.sparseSize(); ++k) {
+            idx.push_back(c.coefficients.indices[k]);
+            val.push_back(int32_t(c.coefficients.values[k]));
+        }
+        ptr.push_back(int32_t(idx.size()));
+        lo.push_back(int32_t(c.lowerBound));
+        up.push_back(int32_t(c.upperBound));
+    }
+    o.i32["con_ptr"] = ptr;
+    o.i32["con_idx"] = idx;
+    o.i32["con_val"] = val;
+    o.i32["con_lower"] = lo;
+    o.i32["con_upper"] = up;
+    if (rebuild) {   // the reference's own constructor + findMinimalBasis, timed, for the speed comparison
+        SilenceStdout quiet;
+        auto t0 = std::chrono::steady_clock::now();
+        TableauNormMinimiser<occ_t> tab(problem.posterior.constraints);
+        o.f64["reference_seconds"] = {std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()};
+        if (tab.rows.size() != problem.tableau.rows.size()) throw std::runtime_error("constraints: rebuilt tableau differs");
+    }
+    o.write(out);
+    fprintf(stderr, "constraints: %zu constraints, %zu coefficients\n", lo.size(), idx.size());
+    return 0;
+}
+
 #define DISPATCH_G(G_, CALL)                                   \
     switch (G_) {                                              \
         case 3: { constexpr int G = 3; return CALL; }          \
@@ -512,13 +635,15 @@ static int run(int argc, char **argv) {
     if (argc < 2) {
         fprintf(stderr,
                 "usage:\n"
-                "  abm_ref gen G T seed kappa out.abmp [pPred pPrey pMakeObs pObsIfPresent]\n"
+                "  abm_ref gen G T seed kappa out.abmp [pPred pPrey pMakeObs pObsIfPresent [bernoulli|poisson]]\n"
                 "  abm_ref init in.abmp nChains seed out.i8\n"
                 "  abm_ref trace in.abmp initSeed chainSeed nSteps checkpointEvery out.abmp\n"
                 "  abm_ref selfcheck in.abmp nSamples\n"
                 "  abm_ref time in.abmp nThreads nSamplesPerThread [maxSeconds]\n"
                 "  abm_ref bench in.abmp nThreads samplesPerStep warmup steps\n"
-                "  abm_ref marginals in.abmp nThreads nSamples burnin out.abmp\n");
+                "  abm_ref marginals in.abmp nThreads nSamples burnin out.abmp\n"
+                "  abm_ref series in.abmp nThreads nSamples burnin out.abmp\n"
+                "  abm_ref constraints in.abmp out.abmp [rebuild: 1 = also time the reference TableauNormMinimiser on them]\n");
         return 2;
     }
     std::string cmd = argv[1];
@@ -534,7 +659,8 @@ static int run(int argc, char **argv) {
         std::string out = argv[6];
         double pPred = argc > 7 ? atof(argv[7]) : 0.05, pPrey = argc > 8 ? atof(argv[8]) : 0.05;
         double pObs = argc > 9 ? atof(argv[9]) : 0.05, pObsIf = argc > 10 ? atof(argv[10]) : 1.0;
-        DISPATCH_G(g, cmdGen<G>(T, seed, kappa, out, pPred, pPrey, pObs, pObsIf));
+        const int startKind = argc > 11 && std::string(argv[11]) == "poisson" ? 1 : 0;
+        DISPATCH_G(g, cmdGen<G>(T, seed, kappa, out, pPred, pPrey, pObs, pObsIf, startKind));
     }
     AbmpFile f = AbmpFile::read(argv[2]);
     int g = f.I("pp_meta")[0];
@@ -544,6 +670,8 @@ static int run(int argc, char **argv) {
     if (cmd == "time") { DISPATCH_G(g, cmdTime<G>(f, atoi(argv[3]), atol(argv[4]), argc > 5 ? atof(argv[5]) : 0.0)); }
     if (cmd == "bench") { DISPATCH_G(g, cmdBench<G>(f, atoi(argv[3]), atol(argv[4]), atoi(argv[5]), atoi(argv[6]))); }
     if (cmd == "marginals") { DISPATCH_G(g, cmdMarginals<G>(f, atoi(argv[3]), atol(argv[4]), atol(argv[5]), argv[6])); }
+    if (cmd == "constraints") { DISPATCH_G(g, cmdConstraints<G>(f, argv[3], argc > 4 ? atoi(argv[4]) : 0)); }
+    if (cmd == "series") { DISPATCH_G(g, cmdSeries<G>(f, atoi(argv[3]), atol(argv[4]), atol(argv[5]), argv[6])); }
     fprintf(stderr, "unknown command %s\n", cmd.c_str());
     return 2;
 }

@@ -4,21 +4,24 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-src = (ROOT / "agentbasedmcmc_b200/csrc/abm_kernels.cuh").read_text().split("\n")
+# section marks come from the source the profiled library was built from: argv[4], else the working tree
+srcPath = Path(sys.argv[4]) if len(sys.argv) > 4 else ROOT / "agentbasedmcmc_b200/csrc/abm_kernels.cuh"
+src = dict(enumerate(srcPath.read_text().split("\n"), start=1))
+rows = list(csv.reader(open(sys.argv[1])))
 
 
 def find(pat):
-    for i, l in enumerate(src):
-        if pat in l:
-            return i + 1
+    for i in sorted(src):
+        if pat in src[i]:
+            return i
     raise KeyError(pat)
 
 
 marks = [("rng", find("for (long long s = 0")), ("descent", find("column draw")), ("record+rows", find("Proposal::Proposal (:288")),
-         ("columns", find("coupled columns, one per lane")), ("importance", find("importance: perturb")),
-         ("ratio/accept", find("calcRatioOfSums (:276")), ("apply X/delta", find("applyProposal (:322")),
-         ("task build", find("const int Ca = accept")), ("task exec", find("rounds of W tasks")), ("end", find("if (act) { ++iter"))]
-rows = list(csv.reader(open(sys.argv[1])))
+         ("columns: prefetch", find("coupled columns, one per lane")), ("importance", find("auto importance = [&]")),
+         ("columns: chunks", find("double csLane = 0.0")), ("ratio/accept", find("calcRatioOfSums (:276")),
+         ("apply X/delta", find("applyProposal (:322")), ("commit", find("const int Ca = accept")),
+         ("sample stats", find("events of the last timestep changed")), ("end", find("if (act) { ++iter"))]
 steps = float(sys.argv[2])
 hdr = rows[2]
 ci = {h: i for i, h in enumerate(hdr)}

@@ -2,7 +2,10 @@
 """Regenerates the golden fixtures in this directory from the UNMODIFIED reference.
 
 Needs /root/reference (read-only) and a host compiler; run from the repository root:
-    make -C oracle ref && python tests/golden/make_golden.py [--with-32]
+    make -C oracle ref && python tests/golden/make_golden.py [--with-32] [--with-sweep]
+--with-32 adds the paper-scale problem (32x32, T = 16; ~4 minutes of TableauNormMinimiser), --with-sweep the window sweep's
+problems (32x32, T = 4, 8, 32; T = 32 at density 0.02 because the reference cannot draw an act-Fermionic real trajectory of
+32 steps at 0.05, Forecast.h:145-147; ~20 minutes).
 Problems: FiguresForPaper::generateStandardProblemFile protocol (FiguresForPaper.h:25-37): seed 1234,
 pPredator = pPrey = 0.05, pMakeObservation = 0.05, pObserveIfPresent = 1.0, kappa = 10.
 Traces: oracle/ref/abm_ref.cpp `trace` (initial state = prior.nextSample(false) under initSeed; sampler
@@ -31,8 +34,20 @@ def main():
         raw = tmp / f"pp{g}-{t}.abmp"
         subprocess.run([str(REF), "gen", str(g), str(t), "1234", "10.0", str(raw)], check=True, stdout=subprocess.DEVNULL)
         xz(raw, HERE / f"pp{g}-{t}.abmp.xz")
+    if "--with-sweep" in sys.argv:
+        for t, dens in ((4, 0.05), (8, 0.05), (32, 0.02)):
+            raw = tmp / f"pp32-{t}.abmp"
+            subprocess.run([str(REF), "gen", "32", str(t), "1234", "10.0", str(raw), str(dens), str(dens)], check=True, stdout=subprocess.DEVNULL)
+            xz(raw, HERE / f"pp32-{t}.abmp.xz")
+    # Poisson start state (PoissonStartState.h; PredPreyProblem.h:60-62 keeps it as the commented-out alternative)
+    for g, t in ((8, 4), (16, 8)):
+        raw = tmp / f"pp{g}-{t}-poisson.abmp"
+        subprocess.run([str(REF), "gen", str(g), str(t), "1234", "10.0", str(raw), "0.05", "0.05", "0.05", "1.0", "poisson"], check=True,
+                       stdout=subprocess.DEVNULL)
+        xz(raw, HERE / f"pp{g}-{t}-poisson.abmp.xz")
     # (problem, initSeed, chainSeed, nSteps, checkpointEvery)
-    traces = [("pp8-4", 11, 101, 20000, 500), ("pp8-4", 12, 102, 20000, 500), ("pp16-8", 12, 202, 20000, 500)]
+    traces = [("pp8-4", 11, 101, 20000, 500), ("pp8-4", 12, 102, 20000, 500), ("pp16-8", 12, 202, 20000, 500),
+              ("pp8-4-poisson", 11, 103, 20000, 500)]
     for name, s0, s1, n, every in traces:
         raw = tmp / f"trace_{name}_{s1}.abmp"
         subprocess.run([str(REF), "trace", str(tmp / f"{name}.abmp"), str(s0), str(s1), str(n), str(every), str(raw)], check=True)
@@ -41,12 +56,15 @@ def main():
     import numpy as np
     sys.path.insert(0, str(HERE.parent.parent))
     from agentbasedmcmc_b200.abmp import write_abmp
-    raw = tmp / "prior8-4.i8"
-    subprocess.run([str(REF), "init", str(tmp / "pp8-4.abmp"), "20000", "4711", str(raw)], check=True)
-    x = np.fromfile(raw, dtype=np.int8).reshape(20000, 4, 2, 64, 6)
-    write_abmp(HERE / "prior_pp8-4.abmp.xz", {"mean_indicator": (x > 0).mean(axis=(0, 3)).ravel(),
-                                              "mean_count": x.astype(np.float64).mean(axis=(0, 3)).ravel(),
-                                              "n": np.array([20000, 64], np.int32)})
+    for name in ("pp8-4", "pp8-4-poisson"):
+        raw = tmp / f"prior_{name}.i8"
+        subprocess.run([str(REF), "init", str(tmp / f"{name}.abmp"), "20000", "4711", str(raw)], check=True)
+        x = np.fromfile(raw, dtype=np.int8).reshape(20000, 4, 2, 64, 6)
+        write_abmp(HERE / f"prior_{name}.abmp.xz", {"mean_indicator": (x > 0).mean(axis=(0, 3)).ravel(),
+                                                    "mean_count": x.astype(np.float64).mean(axis=(0, 3)).ravel(),
+                                                    "n": np.array([20000, 64], np.int32),
+                                                    # start states holding two agents that chose different acts (Poisson only)
+                                                    "multi_act_t0": np.array([((x[:, 0] > 0).sum(axis=-1) >= 2).mean()])})
     # long reference chains for posterior marginals (64 chains x 60000 feasible samples after 60000 burn-in)
     raw = tmp / "marginals_pp8-4.abmp"
     subprocess.run([str(REF), "marginals", str(tmp / "pp8-4.abmp"), "64", "60000", "60000", str(raw)], check=True)

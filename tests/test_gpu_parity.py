@@ -28,7 +28,8 @@ TREES = ["blocked", "reference"]   # ABM_TREE_BLOCKED (default, fast) and ABM_TR
 @pytest.mark.parametrize("tree", TREES)
 @pytest.mark.parametrize("prob,trace,n_steps", [("pp8-4.abmp.xz", "trace_pp8-4_101.abmp.xz", 20000),
                                                 ("pp8-4.abmp.xz", "trace_pp8-4_102.abmp.xz", 20000),
-                                                ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz", 20000)])
+                                                ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz", 20000),
+                                                ("pp8-4-poisson.abmp.xz", "trace_pp8-4-poisson_103.abmp.xz", 20000)])
 def test_reference_golden_trace(prob, trace, n_steps, tree):
     """Same mt19937 uniform stream as the reference run -> same columns, decisions, infeasibilities and X, in both
     sum-tree storages.  The blocked tree holds exact leaves, the reference's get(u) is a difference of drifting sums
@@ -66,7 +67,8 @@ def test_reference_golden_trace(prob, trace, n_steps, tree):
 
 
 @pytest.mark.parametrize("tree", TREES)
-@pytest.mark.parametrize("prob,n_chains,n_steps", [("pp8-4.abmp.xz", 16, 4000), ("pp16-8.abmp.xz", 6, 3000)])
+@pytest.mark.parametrize("prob,n_chains,n_steps", [("pp8-4.abmp.xz", 16, 4000), ("pp16-8.abmp.xz", 6, 3000),
+                                                   ("pp16-8-poisson.abmp.xz", 4, 3000)])
 def test_philox_free_running_matches_oracle(prob, n_chains, n_steps, tree):
     """Free-running mode: device Philox4x32-10 streams keyed by (seed, chain) == the oracle's; many chains per launch."""
     from oracle.oracle import OracleChain, OracleProblem
@@ -204,12 +206,15 @@ def test_posterior_marginals_match_reference_long_run():
     assert np.all(np.isfinite(summ.rhat)) and np.all(summ.rhat > 0.99)   # 1500 correlated samples per chain: R-hat is well above 1
 
 
-def test_device_prior_initial_states_match_reference_prior():
-    """abm_chains_init_from_prior draws `prior.nextSample(false)` (Forecast.h:102-150) per chain on the device.  Checked
-    statistically against 20000 draws of the reference (tests/golden/prior_pp8-4, `abm_ref init`): for every
-    (timestep, species, act) the probability that an event is set, within 5 binomial standard errors + 2e-4."""
+@pytest.mark.parametrize("name", ["pp8-4", "pp8-4-poisson"])
+def test_device_prior_initial_states_match_reference_prior(name):
+    """abm_chains_init_from_prior draws `prior.nextSample(false)` (Forecast.h:102-150) per chain on the device, from the
+    Bernoulli or the Poisson start state.  Checked statistically against 20000 draws of the reference
+    (tests/golden/prior_*, `abm_ref init`): for every (timestep, species, act) the probability that an event is set,
+    within 5 binomial standard errors + 2e-4; for the Poisson start state also the share of start states that hold two
+    agents with different acts (impossible under the Bernoulli one)."""
     S = _gpu()
-    p, ref = load_golden("pp8-4.abmp.xz"), load_golden("prior_pp8-4.abmp.xz")
+    p, ref = load_golden(f"{name}.abmp.xz"), load_golden(f"prior_{name}.abmp.xz")
     n_chains = 8192
     P = S.Problem(p)
     smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=13, prior_init=True, return_prior_sample=True)
@@ -220,6 +225,12 @@ def test_device_prior_initial_states_match_reference_prior():
     n_ref, n_gpu = 20000 * 64, n_chains * 64
     se = np.sqrt(want * (1 - want) * (1.0 / n_ref + 1.0 / n_gpu))
     assert np.all(np.abs(got - want) <= 5 * se + 2e-4), (got - want) / np.maximum(se, 1e-12)
+    multi = (ev[:, 0].sum(axis=-1) >= 2).mean()
+    if name.endswith("poisson"):
+        want_multi = float(ref["multi_act_t0"][0])
+        assert abs(multi - want_multi) <= 5 * np.sqrt(want_multi * (1.0 / (20000 * 128) + 1.0 / (n_chains * 128))) + 1e-5
+    else:
+        assert multi == 0.0
     # chains start from different trajectories and all reach feasibility
     assert len({ev[c].tobytes() for c in range(64)}) > 60
     assert np.all(smp.infeasibility() == 0)

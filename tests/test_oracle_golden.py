@@ -8,7 +8,9 @@ from conftest import load_golden
 from oracle.oracle import OracleChain, OracleProblem, mt_uniforms
 
 TRACES = [("pp8-4.abmp.xz", "trace_pp8-4_101.abmp.xz"), ("pp8-4.abmp.xz", "trace_pp8-4_102.abmp.xz"),
-          ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz")]
+          ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz"),
+          # Poisson start state (PoissonStartState.h:18-31: unbounded occupation rows, lgamma factors), SURVEY 8(f)4
+          ("pp8-4-poisson.abmp.xz", "trace_pp8-4-poisson_103.abmp.xz")]
 
 
 def bits(a):
