@@ -20,7 +20,7 @@ SYMBOLS = [
     "abm_chains_synchronize", "abm_chains_get_state", "abm_chains_get_counters", "abm_chains_get_infeasibility",
     "abm_chains_get_trajectories", "abm_chains_get_statistics", "abm_chains_reset_statistics",
     "abm_chains_record_series", "abm_chains_get_series",
-    "abm_basis_minimise", "abm_basis_destroy", "abm_basis_get_dims", "abm_basis_get", "abm_basis_get_rows",
+    "abm_chains_last_launch_ms", "abm_basis_minimise", "abm_basis_destroy", "abm_basis_get_dims", "abm_basis_get", "abm_basis_get_rows",
 ]
 
 
@@ -85,6 +85,7 @@ def load():
     L.abm_chains_reset_statistics.argtypes = [vp]
     L.abm_chains_record_series.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.abm_chains_get_series.argtypes = [vp, i32p]
+    L.abm_chains_last_launch_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.abm_basis_minimise.argtypes = [C.c_int32, i32p, i32p, i32p, i32p, i32p, vpp]
     L.abm_basis_destroy.argtypes = [vp]
     L.abm_basis_get_dims.argtypes = [vp, i32p, i32p, i32p, i32p, i64p, i64p]

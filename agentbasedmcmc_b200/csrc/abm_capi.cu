@@ -86,7 +86,20 @@ struct abm_chains {
     uint64_t seed = 0, firstChain = 0;
     cudaStream_t stream = nullptr;
     bool initialised = false, feasible = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the last step / sample launch (abm_chains_last_launch_ms)
+    bool timed = false;
 };
+
+// CUDA events on the chains' stream around a step kernel, so a caller can time the kernel itself
+static cudaError_t markLaunch(abm_chains *c, bool begin) {
+    if (!c->ev0) {
+        cudaError_t e = cudaEventCreate(&c->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+        if (e != cudaSuccess) return e;
+    }
+    if (!begin) c->timed = true;
+    return cudaEventRecord(begin ? c->ev0 : c->ev1, c->stream);
+}
 
 extern "C" {
 
@@ -441,6 +454,7 @@ int abm_chains_destroy(abm_chains *c) {
     cudaSetDevice(c->p->device);
     cudaStreamSynchronize(c->stream);
     if (c->series) cudaFree(c->series);
+    if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     delete c;
     return ABM_OK;
 }
@@ -619,7 +633,18 @@ int abm_chains_step(abm_chains *c, int64_t nSteps) {
     CUDA_TRY(cudaSetDevice(c->p->device));
     RunParams r = baseParams(c);
     r.nSteps = nSteps;
+    CUDA_TRY(markLaunch(c, true));
     CUDA_TRY(launchStep<MODE_MCMC>(c, r));
+    CUDA_TRY(markLaunch(c, false));
+    return ABM_OK;
+}
+
+int abm_chains_last_launch_ms(abm_chains *c, float *ms) {
+    if (!c || !ms) return fail(ABM_ERR_INVALID, "null argument");
+    if (!c->timed) return fail(ABM_ERR_STATE, "no step has been launched yet");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
     return ABM_OK;
 }
 
@@ -650,7 +675,9 @@ int abm_chains_step_traced(abm_chains *c, int64_t nSteps, const double *uniforms
     CUDA_TRY(tmp.alloc(&dOutAcc, n * ns));
     CUDA_TRY(tmp.alloc(&dOutInf, n * ns));
     r.outJ = dOutJ; r.outAcc = dOutAcc; r.outInf = dOutInf;
+    CUDA_TRY(markLaunch(c, true));
     CUDA_TRY(launchStep<MODE_MCMC>(c, r));
+    CUDA_TRY(markLaunch(c, false));
     if (outJ) CUDA_TRY(cudaMemcpyAsync(outJ, dOutJ, n * ns * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     if (outAcc) CUDA_TRY(cudaMemcpyAsync(outAcc, dOutAcc, n * ns, cudaMemcpyDeviceToHost, c->stream));
     if (outInf) CUDA_TRY(cudaMemcpyAsync(outInf, dOutInf, n * ns * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -686,8 +713,10 @@ int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
     sampleBeginKernel<<<(c->n + 3) / 4, 128, 0, c->stream>>>(P, c->d);
     CUDA_TRY(cudaGetLastError());
     // without a quota (n_samples == 0 or beyond what max_steps can yield) every chain simply runs max_steps steps
+    CUDA_TRY(markLaunch(c, true));
     if (maxSteps > 0 && (nSamples == 0 || nSamples >= maxSteps)) CUDA_TRY(launchStep<MODE_SAMPLE_FIXED>(c, r));
     else CUDA_TRY(launchStep<MODE_SAMPLE>(c, r));
+    CUDA_TRY(markLaunch(c, false));
     sampleEndKernel<<<dim3(std::max(1, std::min((P.S + 255) / 256, 8)), c->n), 256, 0, c->stream>>>(P, c->d);
     CUDA_TRY(cudaGetLastError());
     return ABM_OK;

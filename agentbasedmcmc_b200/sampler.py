@@ -208,6 +208,12 @@ class SparseBasisSampler:
         check(_capi.load().abm_chains_get_series(self.h, _ptr(out, C.c_int32)))
         return out
 
+    def last_launch_ms(self) -> float:
+        """Device time of the last step / step_traced / sample launch (waits for it)."""
+        ms = C.c_float()
+        check(_capi.load().abm_chains_last_launch_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def synchronize(self):
         check(_capi.load().abm_chains_synchronize(self.h))
 

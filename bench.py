@@ -302,7 +302,8 @@ def bench_ours(args):
                          "mean_agents_at_T": float(summary.end_state_mean.sum()),
                          "rhat_synopsis": [round(float(x), 4) for x in summary.rhat]},
             "ess": ess,
-            "gpu_launches": args.steps,
+            # per bench step: refreshBlockedTopKernel (0.16 ms) + stepKernel<MODE_MCMC> (profiles/*_bench_launches.csv)
+            "gpu_launches": 2 * args.steps,
             "clocks": clocks.summary(),
         }
         if not args.no_cpu_baseline and world == 1:

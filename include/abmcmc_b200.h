@@ -175,6 +175,10 @@ ABM_API int abm_chains_record_series(abm_chains *c, int32_t n_chains, int32_t th
 ABM_API int abm_chains_get_series(abm_chains *c, int32_t *out);
 ABM_API int abm_problem_n_synopsis(const abm_problem *p); /* floor(log2(G)) - 1 (FiguresForPaper.h:246) */
 
+/* Device time of the last abm_chains_step / _step_traced / _sample launch (CUDA events on the chains' stream around the
+ * step kernel; waits for it to finish).  For measurements: the traced variant's host copies are outside. */
+ABM_API int abm_chains_last_launch_ms(abm_chains *c, float *ms);
+
 /* ---- basis builder (host code, no device needed): the step BEFORE the sampler, SURVEY.md section 8(f)2.
  * abm_basis_minimise = TableauNormMinimiser<T>::TableauNormMinimiser(const ConvexPolyhedron<T>&) followed by
  * findMinimalBasis() (TableauNormMinimiser.h:201-256): constraints lower[i] <= sum_k val[k] X[idx[k]] <= upper[i]

@@ -22,6 +22,9 @@
 
 #include "abmcmc_b200/abmp_io.hpp"
 #include "abmcmc_b200/reference_flatten.hpp"
+#ifdef ABM_WITH_BASIS_ADAPTOR   // the abm_ref_fast build (oracle/Makefile `fast`): `gen ... fastbasis` builds the basis with the
+#include "abmcmc_b200/basis_adaptor.hpp"   // drop-in (proven equal to the reference's, tests/test_basis_*.py) for sizes where
+#endif                                     // the reference's own TableauNormMinimiser takes hours (64x64x16)
 
 using abmcmc::AbmpFile;
 typedef ABM::occupation_type occ_t;
@@ -184,7 +187,7 @@ std::vector<occ_t> priorSample(const PredPreyProblem<G> &problem) {
 // ---------------------------------------------------------------------------------------------
 template <int G>
 int cmdGen(int T, int seed, double kappa, const std::string &out, double pPred, double pPrey, double pMakeObs,
-           double pObsIfPresent, int startKind) {
+           double pObsIfPresent, int startKind, bool fastBasis) {
     auto t0 = std::chrono::steady_clock::now();
     Random::gen.seed(seed);  // FiguresForPaper.h:33
     // the member-by-member assembly of PredPreyProblem's constructor (PredPreyProblem.h:46-56), so that the start state can
@@ -197,8 +200,16 @@ int cmdGen(int T, int seed, double kappa, const std::string &out, double pPred, 
     problem.realTrajectory = problem.prior.nextSample(true);
     problem.likelihood = Likelihood<PredPreyAgent<G>>(problem.realTrajectory, pMakeObs, pObsIfPresent);
     problem.posterior = problem.likelihood * problem.prior;
-    problem.tableau = TableauNormMinimiser<occ_t>(problem.posterior.constraints);
-    problem.tableau.findMinimalBasis();
+    if (fastBasis) {
+#ifdef ABM_WITH_BASIS_ADAPTOR
+        problem.tableau = abmcmc::minimiseBasis(problem.posterior.constraints);
+#else
+        throw std::runtime_error("gen: fastbasis needs the abm_ref_fast build");
+#endif
+    } else {
+        problem.tableau = TableauNormMinimiser<occ_t>(problem.posterior.constraints);
+        problem.tableau.findMinimalBasis();
+    }
     auto t1 = std::chrono::steady_clock::now();
     AbmpFile f = exportProblem<G>(problem, seed, pMakeObs, pObsIfPresent, startKind);
     f.f64["gen_seconds"] = {std::chrono::duration<double>(t1 - t0).count()};
@@ -635,7 +646,7 @@ static int run(int argc, char **argv) {
     if (argc < 2) {
         fprintf(stderr,
                 "usage:\n"
-                "  abm_ref gen G T seed kappa out.abmp [pPred pPrey pMakeObs pObsIfPresent [bernoulli|poisson]]\n"
+                "  abm_ref gen G T seed kappa out.abmp [pPred pPrey pMakeObs pObsIfPresent [bernoulli|poisson [fastbasis]]]\n"
                 "  abm_ref init in.abmp nChains seed out.i8\n"
                 "  abm_ref trace in.abmp initSeed chainSeed nSteps checkpointEvery out.abmp\n"
                 "  abm_ref selfcheck in.abmp nSamples\n"
@@ -660,7 +671,8 @@ static int run(int argc, char **argv) {
         double pPred = argc > 7 ? atof(argv[7]) : 0.05, pPrey = argc > 8 ? atof(argv[8]) : 0.05;
         double pObs = argc > 9 ? atof(argv[9]) : 0.05, pObsIf = argc > 10 ? atof(argv[10]) : 1.0;
         const int startKind = argc > 11 && std::string(argv[11]) == "poisson" ? 1 : 0;
-        DISPATCH_G(g, cmdGen<G>(T, seed, kappa, out, pPred, pPrey, pObs, pObsIf, startKind));
+        const bool fastBasis = argc > 12 && std::string(argv[12]) == "fastbasis";
+        DISPATCH_G(g, cmdGen<G>(T, seed, kappa, out, pPred, pPrey, pObs, pObsIf, startKind, fastBasis));
     }
     AbmpFile f = AbmpFile::read(argv[2]);
     int g = f.I("pp_meta")[0];
