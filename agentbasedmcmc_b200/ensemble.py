@@ -29,17 +29,17 @@ class EnsembleSummary:
 
 def pack_local(end_state_sum, syn_sum, syn_sumsq, n_samples, counters) -> torch.Tensor:
     """Per-rank float64 vector [S + 2 + 4 d + 8] that is additive across ranks.  Inputs are this rank's chains."""
-    end = torch.as_tensor(end_state_sum, dtype=torch.float64)
-    s = torch.as_tensor(syn_sum, dtype=torch.float64)
-    sq = torch.as_tensor(syn_sumsq, dtype=torch.float64)
-    n = torch.as_tensor(n_samples, dtype=torch.float64)
+    end = np.asarray(end_state_sum, dtype=np.float64).ravel()
+    s = np.asarray(syn_sum, dtype=np.float64)
+    sq = np.asarray(syn_sumsq, dtype=np.float64)
+    n = np.asarray(n_samples, dtype=np.float64)
     ok = n > 1
-    nn = torch.where(ok, n, torch.ones_like(n))[:, None]
-    mean = torch.where(ok[:, None], s / nn, torch.zeros_like(s))
-    var = torch.where(ok[:, None], (sq - s * s / nn) / torch.clamp(nn - 1.0, min=1.0), torch.zeros_like(s))
-    head = torch.stack([ok.sum().to(torch.float64), n.sum()])
-    return torch.cat([end.flatten(), head, mean.sum(0), (mean * mean).sum(0), var.sum(0), s.sum(0),
-                      torch.as_tensor(counters, dtype=torch.float64).reshape(-1, 8).sum(0)])
+    nn = np.where(ok, n, 1.0)[:, None]
+    mean = np.where(ok[:, None], s / nn, 0.0)
+    var = np.where(ok[:, None], (sq - s * s / nn) / np.maximum(nn - 1.0, 1.0), 0.0)
+    head = np.array([float(ok.sum()), n.sum()])
+    ctr = np.asarray(counters, dtype=np.float64).reshape(-1, 8).sum(0)
+    return torch.from_numpy(np.concatenate([end, head, mean.sum(0), (mean * mean).sum(0), var.sum(0), s.sum(0), ctr]))
 
 
 def summarize(packed: torch.Tensor, n_states: int, n_syn: int) -> EnsembleSummary:

@@ -217,10 +217,12 @@ def bench_ours(args):
     t0 = time.perf_counter()
     d2h = 0
     summary = None
+    smp.sample(10 ** 12, max_steps=mh)          # mh Metropolis steps per chain, statistics of every feasible state
     for k in range(args.steps):
-        smp.sample(10 ** 12, max_steps=mh)      # mh Metropolis steps per chain, statistics of every feasible state
-        end, ss, sq, ns = smp.statistics()      # device -> host buffers
+        end, ss, sq, ns = smp.statistics()      # device -> host buffers (waits for launch k)
         c = smp.counters()
+        if k + 1 < args.steps:                  # launch k+1 runs while the host reduces the statistics of launch k
+            smp.sample(10 ** 12, max_steps=mh)
         d2h = end.nbytes + ss.nbytes + sq.nbytes + ns.nbytes + c.nbytes
         packed = E.pack_local(end, ss, sq, ns, c)
         if world > 1:
@@ -296,7 +298,8 @@ def bench_ours(args):
                          "kernel_ms_per_launch": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
                     "what": "abm_chains_sample (steps + on-device end-state/synopsis statistics) + abm_chains_get_statistics + "
-                            "abm_chains_get_counters into host buffers + ensemble all-reduce, host clock; inputs of a step are "
+                            "abm_chains_get_counters into host buffers + ensemble all-reduce, host clock, every step; the next launch is "
+                            "issued before the host reduces the statistics just read; inputs of a step are "
                             "kernel arguments only (the problem and the chain states are uploaded once, at construction)"},
             "ensemble": {"chains": summary.n_chains, "feasible_samples": summary.n_samples,
                          "mean_agents_at_T": float(summary.end_state_mean.sum()),
