@@ -119,6 +119,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     *out = nullptr;
     if (abm_device_count() <= device || device < 0) return fail(ABM_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");
     CUDA_TRY(cudaSetDevice(device));
+    if (const char *e = getenv("ABM_L2_FETCH")) CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(e))));   // experiment: 32 / 64 / 128
     const int nTab = desc->n_tab_rows, nCols = desc->n_nonbasic;
     if (nTab <= 0 || nCols <= 0) return fail(ABM_ERR_INVALID, "empty problem");
 
@@ -375,6 +376,16 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.tCapB = (maxTB + 7) & ~7;
     d.tCap = d.tCapA + d.tCapB + ((maxTC + 7) & ~7);
     if (d.blockedTree) d.tCap = d.tCapA = d.tCapB = 0;   // the blocked tree's commit keeps no task list
+    d.scrCap = 0;
+#if ABM_SMEM_SCRATCH
+    if (d.blockedTree) {
+        // what 7 resident CTAs per SM leave to one chain (228 KB per SM, 1 KB reserved per CTA), after the fixed arrays
+        const int chainsPerCta = kWarpsPerCta * (32 / W);
+        const int budget = (((228 * 1024) / 7 - 1024) / chainsPerCta) & ~15;
+        const int room = (budget - groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0)) / 16;
+        d.scrCap = std::max(0, std::min(room, d.sCap + W - 1) / W * W);
+    }
+#endif
     if (maxTA > 1000 || maxTB > 1000 || maxTC > 1000) return fail(ABM_ERR_INVALID, "too many sum-tree nodes touched by one column");
     int nSyn = 0;
     for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
@@ -545,7 +556,7 @@ static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
     constexpr int NG = 32 / W;
     const int chainsPerCta = kWarpsPerCta * NG;
     const int grid = (c->n + chainsPerCta - 1) / chainsPerCta;
-    const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap);
+    const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap);
     cudaError_t e = cudaFuncSetAttribute(stepKernel<MODE, W, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     stepKernel<MODE, W, BLK><<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);

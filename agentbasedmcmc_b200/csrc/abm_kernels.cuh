@@ -24,6 +24,22 @@ constexpr int kWarpsPerCta = 4;
 #define ABM_IMP_EARLY 0
 #endif
 constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
+// ABM_PHILOX_BLOCK: the lanes of a group draw the Philox blocks of the chain's next min(W,16) iterations at once (one
+// iteration per lane) instead of every lane repeating the block of the current one; same counters, same uniforms.
+#ifndef ABM_PHILOX_BLOCK
+#define ABM_PHILOX_BLOCK 0
+#endif
+// ABM_PREFETCH: the first coupled-column chunks' lists (1) and the first stale factors (2) are requested together with
+// the column's rows, so these record reads share one memory round trip instead of following each other.
+#ifndef ABM_PREFETCH
+#define ABM_PREFETCH 2
+#endif
+// ABM_SMEM_SCRATCH: blocked tree: the {DE', leaf} pairs a step stages for its commit stay in shared memory for as many
+// leading coupled columns as 7 resident CTAs per SM leave room for (abm_problem_create sizes it); the rest goes through
+// S.scratch as before.
+#ifndef ABM_SMEM_SCRATCH
+#define ABM_SMEM_SCRATCH 0
+#endif
 constexpr unsigned kFull = 0xffffffffu;
 
 enum { MODE_MCMC = 0, MODE_INIT = 1, MODE_SAMPLE = 2, MODE_SAMPLE_FIXED = 3 };
@@ -81,6 +97,8 @@ __device__ __forceinline__ double energyOf(int x, int L, int U, int tabBase, con
     return __dsub_rn(f, __dmul_rn(kappa, (double)dist));
 }
 __device__ __forceinline__ int infeasOf(int x, int L, int U) { return x < L ? L - x : (x > U ? x - U : 0); }
+
+__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // One out-of-line copy of exp(): the step kernel is bounded by instruction fetch as much as by anything else.
 __device__ __noinline__ double expShared(double x) { return exp(x); }
@@ -197,8 +215,8 @@ __device__ __forceinline__ int selectDescending(const double (&v)[32 / W], doubl
 }
 
 // Bytes of shared memory one chain (group) needs; must match the carve-up in stepKernel.
-__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap) {
-    return sCap * 8 + rowsCap * 16 + 32 * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7);
+__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap) {
+    return (scrCap * 16 + sCap * 8 + rowsCap * 16 + 32 * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
 }
 
 // MODE_SAMPLE, rare path (an accepted proposal changed events of the last timestep): move the end-state occupancy
@@ -271,9 +289,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     const int chainC = chainValid ? chain : 0;   // pointer arithmetic only; every access is predicated
 
     // ---- per-chain shared memory
-    const int gBytes = groupSmemBytes(P.rowsCap, P.sCap, P.tCap);
+    const int gBytes = groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap);
     unsigned char *gs = smemRaw + (size_t)(warp * NG + g) * gBytes;
-    double *sDl = reinterpret_cast<double *>(gs);                        // [sCap] delta of set() per coupled column
+    double2 *sScr = reinterpret_cast<double2 *>(gs);                     // [scrCap] blocked tree: {DE', signed leaf} of the first
+                                                                         //   coupled columns of a step (the rest: S.scratch)
+    double *sDl = reinterpret_cast<double *>(sScr + P.scrCap);           // [sCap] delta of set() per coupled column
     double *sG = sDl + P.sCap;                                           // [rowsCap][2] per row: DE' term for a coupled column
                                                                          //   whose flip moves the row by -1 / +1
     double *sNode = sG + 2 * P.rowsCap;                                  // [32] tree nodes of one descent round
@@ -303,6 +323,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     }
     __syncwarp();
     double2 *scratch = S.scratch + (size_t)chainC * P.sCap;
+    const int scrChunks = BLK ? P.scrCap / W : 0;   // chunks of coupled columns whose staged values stay in shared memory
 
     double logImp = chainValid ? S.logImp[chain] : 0.0;
     int infeas = chainValid ? S.infeas[chain] : 0;
@@ -313,6 +334,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     const double kappa = P.kappa;
     const double *__restrict__ facVal = P.facVal;
     const int nCols = P.nCols;
+    constexpr bool kPhBlk = ABM_PHILOX_BLOCK != 0 && BLK;   // the blocked tree leaves sNode free to hold the drawn block
+    constexpr int PB = W < 16 ? W : 16;
+    int phIdx = PB;                     // next unread iteration of the drawn Philox block (PB: none left)
 
     // ---- MODE_SAMPLE state: current end-state occupancy ModelState(traj,T,T) (ModelState.h:27-36 via
     // State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115), kept
@@ -339,12 +363,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 const double *up = R.injU + (size_t)chain * R.uStride + R.uOffset;
                 if (MODE == MODE_INIT) u1 = up[s];
                 else { u1 = up[2 * s]; u2 = up[2 * s + 1]; }
-            } else {
+            } else if constexpr (!kPhBlk) {
                 uint32_t w[4];
                 philox4x32_10((uint32_t)iter, (uint32_t)(iter >> 32), (uint32_t)chainId, (uint32_t)(chainId >> 32),
                               (uint32_t)R.seed, (uint32_t)(R.seed >> 32), w);
                 u1 = canonical_from_words(w[0], w[1]);
                 u2 = canonical_from_words(w[2], w[3]);
+            }
+        }
+        if constexpr (kPhBlk) {
+            if (!R.injU) {
+                const bool need = act && phIdx >= PB;
+                if (__any_sync(kFull, need)) {
+                    if (need && gl < PB) {   // lane gl: the block of iteration iter + gl
+                        const unsigned long long it = iter + (unsigned long long)gl;
+                        uint32_t w[4];
+                        philox4x32_10((uint32_t)it, (uint32_t)(it >> 32), (uint32_t)chainId, (uint32_t)(chainId >> 32),
+                                      (uint32_t)R.seed, (uint32_t)(R.seed >> 32), w);
+                        sNode[2 * gl] = canonical_from_words(w[0], w[1]);
+                        sNode[2 * gl + 1] = canonical_from_words(w[2], w[3]);
+                    }
+                    if (need) phIdx = 0;
+                    __syncwarp();
+                }
+                if (act) {
+                    u1 = sNode[2 * phIdx];
+                    u2 = sNode[2 * phIdx + 1];
+                    ++phIdx;
+                }
             }
         }
 
@@ -440,16 +486,63 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         int dj = 1;
         if (act) dj = BLK ? (__double2hiint(ch.colRec[j].y) < 0 ? -1 : 1) : (int)ch.delta[j];
 
+        // Two-deep software pipeline over the chunks of coupled columns (below): chunk c+1 in uB/chdrB, chunk c+2 in uC/chdrC
+        int uB = -1, chdrB = 0, uC = -1, chdrC = 0;
+        int sidPre = -1;                                              // first stale factor of this lane (ABM_PREFETCH 2)
+        if constexpr (ABM_PREFETCH >= 1) {
+            if (0 < nChunks) { uB = __ldg(slotU + gl); chdrB = __ldg(chunkHdr); }
+            if (1 < nChunks) { uC = __ldg(slotU + W + gl); chdrC = __ldg(chunkHdr + 1); }
+        }
+        if constexpr (ABM_PREFETCH >= 2 && kMC) {
+            if (gl < nSF) sidPre = __ldg(staleF + gl);
+        }
+
         // rows of the proposed column
         const int nW = warpMax(n);
         int dinf = 0;
+        // ABM_PREFETCH 3: the first W rows and their X are requested, then the chain state of the first chunk of coupled
+        // columns, and only then are the rows evaluated: one memory round trip instead of two in a row
+        int4 r0 = make_int4(0, 0, 0, 0);
+        int x0 = 0;
+        double2 crN = make_double2(0.0, 0.0);
+        int duN = 0, ctN0 = kNoContrib, ctN1 = kNoContrib;
+        if constexpr (ABM_PREFETCH >= 3) {
+            if (gl < n) {
+                r0 = __ldg(recRows + gl);
+                x0 = ch.Xb[r0.x & 0xffffff];
+            }
+            if (uB >= 0) {
+                crN = ch.colRec[uB];
+                if constexpr (!BLK) duN = ch.delta[uB];
+                const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
+                if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
+                if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
+            }
+        }
+        if constexpr (ABM_PREFETCH >= 4 && kMC) {
+            // the trajectory words the importance change will read (own state and the four neighbours of the first stale
+            // factors) are pulled into L2 now; the reads themselves follow the coupled columns
+            if (sidPre >= 0 && P.gShift >= 0) {
+                const int G = P.G, GG = G * G;
+                const int psi = sidPre & (P.S - 1), cell = psi & (GG - 1), type = psi >> (2 * P.gShift);
+                const int cy = cell >> P.gShift, cx = cell & (G - 1), ob = (sidPre - psi) + (1 - type) * GG;
+                const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(ch.Xb);
+                prefetchL2(X8 + sidPre);
+                prefetchL2(X8 + ob + ((cx - 1) & (G - 1)) + G * cy);
+                prefetchL2(X8 + ob + ((cx + 1) & (G - 1)) + G * cy);
+                prefetchL2(X8 + ob + cx + G * ((cy + 1) & (G - 1)));
+                prefetchL2(X8 + ob + cx + G * ((cy - 1) & (G - 1)));
+            }
+        }
         #pragma unroll 1
         for (int rb = 0; rb < nW; rb += W) {
             const int k = rb + gl;
             if (k < n) {
-                const int4 r = __ldg(recRows + k);
+                int4 r;
+                int x;
+                if (ABM_PREFETCH >= 3 && rb == 0) { r = r0; x = x0; }
+                else { r = __ldg(recRows + k); x = ch.Xb[r.x & 0xffffff]; }
                 const int xoff = r.x & 0xffffff, m = r.x >> 24;
-                const int x = ch.Xb[xoff];
                 const int xn = x + m * dj;                                                  // :299-300
                 sXoff[k] = xoff;
                 sXX[k] = (uint16_t)((x & 0xff) | ((xn & 0xff) << 8));
@@ -474,17 +567,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         const int chunksW = warpMax(nChunks);
         // Two-deep software pipeline over the chunks: the column list of chunk c+2 and the chain state of chunk c+1 (record,
         // delta, first shared-row entries) are in flight while chunk c is evaluated.
-        int uB = -1, chdrB = 0, uC = -1, chdrC = 0;                  // chunk c+1, chunk c+2
-        if (0 < nChunks) { uB = __ldg(slotU + gl); chdrB = __ldg(chunkHdr); }
-        if (1 < nChunks) { uC = __ldg(slotU + W + gl); chdrC = __ldg(chunkHdr + 1); }
-        double2 crN = make_double2(0.0, 0.0);
-        int duN = 0, ctN0 = kNoContrib, ctN1 = kNoContrib;
-        if (uB >= 0) {
-            crN = ch.colRec[uB];
-            if constexpr (!BLK) duN = ch.delta[uB];
-            const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
-            if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
-            if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
+        if constexpr (ABM_PREFETCH < 1) {
+            if (0 < nChunks) { uB = __ldg(slotU + gl); chdrB = __ldg(chunkHdr); }
+            if (1 < nChunks) { uC = __ldg(slotU + W + gl); chdrC = __ldg(chunkHdr + 1); }
+        }
+        if constexpr (ABM_PREFETCH < 3) {
+            if (uB >= 0) {
+                crN = ch.colRec[uB];
+                if constexpr (!BLK) duN = ch.delta[uB];
+                const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
+                if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
+                if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
+            }
         }
         // The importance change (perturb + refresh) can be evaluated between issuing the first chunk's loads and consuming
         // them (ABM_IMP_EARLY), so that its own loads of the trajectory overlap with them, or after the chunks.
@@ -503,7 +597,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     int sid = -1, type = 0, ns[4] = {-1, -1, -1, -1};
                     unsigned long long own = 0ull, nb[4] = {0ull, 0ull, 0ull, 0ull};
                     if (fa) {
-                        sid = __ldg(staleF + f);
+                        sid = (ABM_PREFETCH >= 2 && fb == 0) ? sidPre : __ldg(staleF + f);
                         int cx, cy, ob;
                         if (P.gShift >= 0) {   // power-of-two grids: psi = x + G y + G^2 type (PredPreyAgent.h:59) by shifts
                             const int psi = sid & (P.S - 1), cell = psi & (GG - 1);
@@ -652,7 +746,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 sDl[slot] = dlt;
                 // BLK: the stored leaf carries delta_u in its sign; the proposed column's flips on acceptance (:334)
                 if constexpr (BLK) base = ((du < 0) != self) ? -base : base;
-                scratch[slot] = make_double2(acc, base);
+                if (c < scrChunks) sScr[slot] = make_double2(acc, base); else scratch[slot] = make_double2(acc, base);
             }
             if (kMC) {
                 if constexpr (BLK) {
@@ -726,7 +820,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             constexpr unsigned gMask = W == 32 ? 0xffffffffu : ((1u << W) - 1u);
             const int gShiftLane = (threadIdx.x & 31) & ~(W - 1);
             double2 scN = make_double2(0.0, 0.0);   // the staged {DE', signed leaf} of the coming round, one round ahead
-            if (gl < Ca) scN = scratch[gl];
+            if (gl < Ca) scN = 0 < scrChunks ? sScr[gl] : scratch[gl];
             #pragma unroll 1
             for (int lb = 0; lb < CW; lb += W) {
                 const int l = lb + gl;
@@ -734,7 +828,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 const unsigned u = valid ? (unsigned)sU[l] : 0x7fffffffu;
                 const double dl = valid ? sDl[l] : 0.0;
                 const double2 sc = scN;
-                if (l + W < Ca) scN = scratch[l + W];
+                if (l + W < Ca) scN = lb + W < scrChunks * W ? sScr[l + W] : scratch[l + W];
                 if (valid) ch.colRec[u] = sc;
                 double pin = dl;
 #pragma unroll
