@@ -209,7 +209,10 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     int maxCoupled = 1, maxTasks = 1, maxSF = 0, maxTA = 1, maxTB = 1, maxTC = 1;
     struct Pair { int u, k, m; };
     std::vector<Pair> pairs;
-    std::vector<int32_t> slotU, chunkHdr, staleF, nodes;
+    std::vector<int32_t> slotU, chunkHdr, staleF, nodes, endFx;
+    int nSyn = 0;
+    for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
+    if (nSyn > 8) return fail(ABM_ERR_INVALID, "more than 8 synopsis statistics");
     std::vector<uint16_t> contrib;
     std::vector<char> seen(std::max(nStates, 1), 0);
     for (int j = 0; j < nCols; ++j) {
@@ -327,6 +330,40 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         }
         rec.insert(rec.end(), staleF.begin(), staleF.end());
         if (rec.size() - base != staleWord + staleF.size()) return fail(ABM_ERR_INVALID, "internal: record layout");
+        // static end-state effect of the column (MODE_SAMPLE), per unit of delta_j: which states of ModelState(traj,T,T) its
+        // events of the last timestep feed (PredPreyAgent::consequences, PredPreyAgent.h:98-115) and what that adds to the
+        // synopsis squares (FiguresForPaper.h:245-263)
+        if (touchesEnd) {
+            endFx.clear();
+            int synD[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < nEv; ++k) {
+                const int i = colRow[colPtr[j] + k];
+                if (i < (T - 1) * S * kActs) continue;
+                const int a2 = i % kActs, psi = (i / kActs) % S, m = colVal[colPtr[j] + k];
+                const int type = psi / (G * G), cell = psi % (G * G), cy = cell / G, cx = cell % G, tb = type * G * G;
+                int tx[2] = {-1, -1}, ty[2] = {cy, cy};
+                if (a2 == 1) tx[0] = (cx + G - 1) % G;
+                else if (a2 == 2) tx[0] = (cx + 1) % G;
+                else if (a2 == 3) { tx[0] = cx; ty[0] = (cy + 1) % G; }
+                else if (a2 == 4) { tx[0] = cx; ty[0] = (cy + G - 1) % G; }
+                else if (a2 == 5) { tx[0] = cx; tx[1] = (cx + 1) % G; }
+                for (int q = 0; q < 2; ++q) {
+                    if (tx[q] < 0) continue;
+                    endFx.push_back(int32_t(uint32_t(tb + tx[q] + G * ty[q]) | (uint32_t(m & 0xff) << 24)));
+                    for (int z = 0; z < nSyn; ++z) {
+                        const int sz = G >> (z + 1), org = G - 2 * sz;
+                        if (tx[q] >= org && tx[q] < org + sz && ty[q] >= org && ty[q] < org + sz) synD[z] += m;
+                    }
+                }
+            }
+            rec.push_back(int32_t(endFx.size()));
+            for (int w = 0; w < 2; ++w) {
+                uint32_t pk = 0;
+                for (int z = 0; z < 4; ++z) pk |= uint32_t(synD[4 * w + z] & 0xff) << (8 * z);
+                rec.push_back(int32_t(pk));
+            }
+            rec.insert(rec.end(), endFx.begin(), endFx.end());
+        }
         if (rec.size() / 4 > 0xfffffff0ull) return fail(ABM_ERR_INVALID, "record table too large");
     }
     while (rec.size() % 4) rec.push_back(0);
@@ -387,8 +424,6 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     }
 #endif
     if (maxTA > 1000 || maxTB > 1000 || maxTC > 1000) return fail(ABM_ERR_INVALID, "too many sum-tree nodes touched by one column");
-    int nSyn = 0;
-    for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
     d.nSynopsis = nSyn;
     d.kappa = desc->kappa;
     std::vector<int32_t> colEvent(desc->nb_col, desc->nb_col + nCols);
@@ -451,7 +486,7 @@ int abm_chains_create(const abm_problem *p, int32_t nChains, uint64_t seed, uint
     al(&d.endStateSum, size_t(std::max(P.S, 1))); al(&d.synSum, n * std::max(P.nSynopsis, 1));
     al(&d.synSumSq, n * std::max(P.nSynopsis, 1)); al(&d.nSamples, n);
     al(&d.synNow, n * std::max(P.nSynopsis, 1)); al(&d.launchSamples, n);
-    al(&d.endOcc, n * std::max(P.S, 1)); al(&d.endStamp, n * std::max(P.S, 1)); al(&d.endAcc, n * std::max(P.S, 1));
+    al(&d.endRec, n * std::max(P.S, 1));
     if (e != cudaSuccess) {
         delete c;
         return fail(ABM_ERR_CUDA, std::string("chain allocation: ") + cudaGetErrorString(e));
@@ -699,7 +734,7 @@ int abm_chains_step_traced(abm_chains *c, int64_t nSteps, const double *uniforms
 static int zeroStatistics(abm_chains *c) {
     const DevProblem &P = c->p->d;
     const size_t n = size_t(c->n), ns = size_t(std::max(P.nSynopsis, 1));
-    CUDA_TRY(cudaMemsetAsync(c->d.endAcc, 0, n * std::max(P.S, 1) * sizeof(long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d.endRec, 0, n * std::max(P.S, 1) * sizeof(EndRec), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->d.synSum, 0, n * ns * sizeof(long long), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->d.synSumSq, 0, n * ns * sizeof(long long), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->d.nSamples, 0, n * sizeof(long long), c->stream));

@@ -63,6 +63,12 @@ struct DevProblem {
     const int32_t *colEvent;                   // tableau column of each basis column
 };
 
+// MODE_SAMPLE, per chain and agent state
+struct EndRec {
+    long long acc;           // sum over this chain's samples of the end-state occupancy (up to the last finished launch)
+    long long pend;          // running launch: sum over the occupancy changes of (change * index of the first sample seeing it)
+};
+
 struct DevChains {
     int nChains;
     int8_t *Xb;
@@ -79,9 +85,7 @@ struct DevChains {
     long long *endStateSum;  // [S]   ensemble sum
     long long *synSum, *synSumSq; // [nChains][nSynopsis]
     long long *nSamples;     // [nChains]
-    int32_t *endOcc;         // [nChains][S] current end-state occupancy (valid during a sampling launch)
-    int32_t *endStamp;       // [nChains][S] launch-local sample index at which endOcc last changed
-    long long *endAcc;       // [nChains][S] sum over this chain's samples of the end-state occupancy
+    EndRec *endRec;          // [nChains][S] end-state occupancy accumulators
     int32_t *synNow;         // [nChains][nSynopsis] synopsis of the current state (between sampling launches)
     long long *launchSamples; // [nChains] samples taken by the last sampling launch
 };

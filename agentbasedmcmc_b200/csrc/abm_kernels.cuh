@@ -32,7 +32,7 @@ constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 // ABM_PREFETCH: the first coupled-column chunks' lists (1) and the first stale factors (2) are requested together with
 // the column's rows, so these record reads share one memory round trip instead of following each other.
 #ifndef ABM_PREFETCH
-#define ABM_PREFETCH 2
+#define ABM_PREFETCH 3
 #endif
 // ABM_SMEM_SCRATCH: blocked tree: the {DE', leaf} pairs a step stages for its commit stay in shared memory for as many
 // leading coupled columns as 7 resident CTAs per SM leave room for (abm_problem_create sizes it); the rest goes through
@@ -219,42 +219,21 @@ __host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, i
     return (scrCap * 16 + sCap * 8 + rowsCap * 16 + 32 * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
 }
 
-// MODE_SAMPLE, rare path (an accepted proposal changed events of the last timestep): move the end-state occupancy
-// ModelState(traj,T,T) and return this lane's synopsis change.  Out of line to keep the step loop's code compact.
-__device__ __noinline__ int endStateUpdate(int G, int evBytes, int nSynopsis, int lastBase, int n, int nW, const int *sXoff,
-                                           const uint16_t *sXX, int32_t *endOcc, int32_t *endStamp, long long *endAcc,
-                                           int nSamp, int gl) {
-    const int GG = G * G;
-    int dsyn = 0;
-    for (int r = 0; r < nW; ++r) {
-        if (r >= n) continue;
-        const int xo = sXoff[r];
-        if (xo < lastBase || xo >= evBytes) continue;
-        const int a = xo & 7, psi = (xo - lastBase) >> 3;
-        const int xx = sXX[r];
-        const int dlt = (int)(int8_t)(xx >> 8) - (int)(int8_t)(xx & 0xff);
-        const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
-        int tg[2] = {-1, -1};   // consequences(act), PredPreyAgent.h:98-115
-        if (a == 1) tg[0] = tb + (cx + G - 1) % G + G * cy;
-        else if (a == 2) tg[0] = tb + (cx + 1) % G + G * cy;
-        else if (a == 3) tg[0] = tb + cx + G * ((cy + 1) % G);
-        else if (a == 4) tg[0] = tb + cx + G * ((cy + G - 1) % G);
-        else if (a == 5) { tg[0] = psi; tg[1] = tb + (cx + 1) % G + G * cy; }
-        for (int q = 0; q < 2; ++q) {
-            if (tg[q] < 0) continue;
-            if (gl == 0) {   // lazy accumulator: settle the samples taken at the old occupancy
-                endAcc[tg[q]] += (long long)endOcc[tg[q]] * (long long)(nSamp - endStamp[tg[q]]);
-                endStamp[tg[q]] = nSamp;
-                endOcc[tg[q]] += dlt;
-            }
-            if (gl < nSynopsis) {
-                const int sz = G >> (gl + 1), org = G - 2 * sz;
-                const int tc = tg[q] % GG, tx = tc % G, ty = tc / G;
-                if (tx >= org && tx < org + sz && ty >= org && ty < org + sz) dsyn += dlt;
-            }
-        }
+// MODE_SAMPLE: an accepted proposal (dj != 0) with events in the last timestep moves the end state ModelState(traj,T,T).
+// The column's effect is static up to the sign delta_j; fx = its list in the record: {nEnd, 8 x int8 synopsis change per
+// unit of delta_j, nEnd x (state | entry << 24)}.  The samples from index nSamp on see the new occupancy: their share
+// occ_end * N - sum(change * nSamp) is settled by sampleEndKernel, so this only issues reductions and waits for nothing.
+// Out of line: it runs in one step out of T and must not cost the step loop registers.  Returns the lane's synopsis change.
+__device__ __noinline__ int endStateEffects(const int32_t *__restrict__ fx, int dj, int nSynopsis, EndRec *endRec, int nSamp, int gl,
+                                            int W) {
+    if (dj == 0) return 0;
+    const int nEnd = __ldg(fx);
+    for (int k = gl; k < nEnd; k += W) {
+        const int w = __ldg(fx + 3 + k);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&endRec[w & 0xffffff].pend),
+                  (unsigned long long)((long long)(dj * (w >> 24)) * (long long)nSamp));
     }
-    return dsyn;
+    return gl < nSynopsis ? dj * (int)(int8_t)(__ldg(fx + 1 + (gl >> 2)) >> (8 * (gl & 3))) : 0;
 }
 
 __device__ __noinline__ void recordSeries(int32_t *series, int seriesThin, int seriesCap, int nSynopsis, int chain, long long tot,
@@ -343,7 +322,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     // incrementally, with per-state accumulators advanced lazily (occupancy x samples since the last change)
     int nSamp = 0;                      // feasible samples taken in this launch
     int syn = 0;                        // lane k < nSynopsis: agents inside the k-th nested square (FiguresForPaper.h:245-263)
-    const int lastBase = (P.T - 1) * P.S * kStateBytes;   // Xb offset of the events of the last timestep
     if (kSample) {   // end-state occupancy and synopsis were prepared by sampleBeginKernel
         if (chainValid && gl < P.nSynopsis) syn = S.synNow[(size_t)chain * P.nSynopsis + gl];
         if (gl < 16) sSyn[gl] = 0;
@@ -792,6 +770,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             if (R.outInf) R.outInf[o] = infN;
         }
 
+        if (kSample) {
+            // events of the last timestep changed by an accepted proposal move the end state (evaluated here, while the
+            // record pointers of the proposal are still live)
+            if (__any_sync(kFull, accept && colTouchesEnd))
+                syn += endStateEffects(staleF + nSF, (accept && colTouchesEnd) ? dj : 0, P.nSynopsis, S.endRec + (size_t)chainC * P.S, nSamp,
+                                       gl, W);
+        }
+
         // ---- applyProposal (:322-336)
         if (accept) {
             logImp = logImpN;
@@ -948,10 +934,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         }
         __syncwarp();
         if (kSample) {
-            // events of the last timestep changed by an accepted proposal move the end state
-            if (__any_sync(kFull, accept && colTouchesEnd))
-                syn += endStateUpdate(P.G, P.evBytes, P.nSynopsis, lastBase, accept ? n : 0, nW, sXoff, sXX, S.endOcc + (size_t)chainC * P.S,
-                                      S.endStamp + (size_t)chainC * P.S, S.endAcc + (size_t)chainC * P.S, nSamp, gl);
             // the do-while at SparseBasisSampler.h:247 hands out the state whenever it is feasible after a step
             if (act && infeas == 0) {
                 if (gl < P.nSynopsis) {   // MeanAndVariance::operator(), diagnostics/MeanAndVariance.h:35-45 (exact in int64)
@@ -1162,46 +1144,49 @@ __global__ void setStateKernel(DevProblem P, DevChains S) {
     if (lane == 0) S.logImp[chain] = total;
 }
 
-// Before a sampling launch: the current end-state occupancy ModelState(traj,T,T) (ModelState.h:27-36 via
-// State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115) and the synopsis
-// (FiguresForPaper.h:245-263) of every chain, from which stepKernel<MODE_SAMPLE> proceeds incrementally.  One warp per chain.
+// End-state occupancy ModelState(traj,T,T) (ModelState.h:27-36 via State::backwardOccupation, State.h:57-63, and
+// PredPreyAgent::consequences, PredPreyAgent.h:98-115) of one agent state from the events of the last timestep (Xl): MOVELEFT
+// from the right neighbour, MOVERIGHT from the left one, MOVEUP from below, MOVEDOWN from above, GIVEBIRTH from the state
+// itself (the parent stays) and from the left neighbour (the child)
+__device__ __forceinline__ int endOccupancy(const int8_t *__restrict__ Xl, int psi, int G) {
+    const int GG = G * G;
+    const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
+    const int left = tb + (cx + G - 1) % G + G * cy, right = tb + (cx + 1) % G + G * cy;
+    const int up = tb + cx + G * ((cy + 1) % G), down = tb + cx + G * ((cy + G - 1) % G);
+    return Xl[right * kStateBytes + 1] + Xl[left * kStateBytes + 2] + Xl[down * kStateBytes + 3] + Xl[up * kStateBytes + 4] +
+           Xl[psi * kStateBytes + 5] + Xl[left * kStateBytes + 5];
+}
+
+// Before a sampling launch: the synopsis (FiguresForPaper.h:245-263) of every chain's current end state, from which
+// stepKernel<MODE_SAMPLE> proceeds incrementally.  One warp per chain.
 __global__ void sampleBeginKernel(DevProblem P, DevChains S) {
     const int lane = threadIdx.x & 31;
     const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (chain >= S.nChains) return;
     const int G = P.G, GG = G * G;
     const int8_t *Xl = S.Xb + (size_t)chain * P.xStride + (size_t)(P.T - 1) * P.S * kStateBytes;
-    int32_t *endOcc = S.endOcc + (size_t)chain * P.S, *endStamp = S.endStamp + (size_t)chain * P.S;
-    for (int psi = lane; psi < P.S; psi += 32) {
-        const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
-        const int left = tb + (cx + G - 1) % G + G * cy, right = tb + (cx + 1) % G + G * cy;
-        const int up = tb + cx + G * ((cy + 1) % G), down = tb + cx + G * ((cy + G - 1) % G);
-        // incoming events: MOVELEFT from the right neighbour, MOVERIGHT from the left one, MOVEUP from below,
-        // MOVEDOWN from above, GIVEBIRTH from the state itself (parent stays) and from the left neighbour (child)
-        endOcc[psi] = Xl[right * kStateBytes + 1] + Xl[left * kStateBytes + 2] + Xl[down * kStateBytes + 3] +
-                      Xl[up * kStateBytes + 4] + Xl[psi * kStateBytes + 5] + Xl[left * kStateBytes + 5];
-        endStamp[psi] = 0;
-    }
-    __syncwarp();
     for (int k = 0; k < P.nSynopsis; ++k) {
         const int sz = G >> (k + 1), org = G - 2 * sz;   // sizes G/2, G/4, ...; origins 0, G/2, 3G/4, ...
         int part = 0;
         for (int c2 = lane; c2 < 2 * sz * sz; c2 += 32) {
             const int type = c2 / (sz * sz), cc = c2 - type * sz * sz;
-            part += endOcc[type * GG + (org + cc % sz) + G * (org + cc / sz)];
+            part += endOccupancy(Xl, type * GG + (org + cc % sz) + G * (org + cc / sz), G);
         }
         part = warpSumInt(part);
         if (lane == 0) S.synNow[(size_t)chain * P.nSynopsis + k] = part;
     }
 }
 
-// After a sampling launch: settle the lazy per-state accumulators and the sample counts.
+// After a sampling launch of N samples: a state's occupancy summed over them is occ_end * N - sum over its changes of
+// (change * index of the first sample that saw it); the second term was accumulated by the step kernel.
 __global__ void sampleEndKernel(DevProblem P, DevChains S) {
     const int chain = blockIdx.y;
     const long long nSamp = S.launchSamples[chain];
+    const int8_t *Xl = S.Xb + (size_t)chain * P.xStride + (size_t)(P.T - 1) * P.S * kStateBytes;
     for (int psi = blockIdx.x * blockDim.x + threadIdx.x; psi < P.S; psi += gridDim.x * blockDim.x) {
-        const size_t o = (size_t)chain * P.S + psi;
-        S.endAcc[o] += (long long)S.endOcc[o] * (nSamp - S.endStamp[o]);
+        EndRec &e = S.endRec[(size_t)chain * P.S + psi];
+        e.acc += (long long)endOccupancy(Xl, psi, P.G) * nSamp - e.pend;
+        e.pend = 0;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) S.nSamples[chain] += nSamp;
 }
@@ -1229,14 +1214,14 @@ __global__ void refreshBlockedTopKernel(DevProblem P, DevChains S) {
     }
 }
 
-// ensemble end-state sum: out[psi] += sum over a slice of chains of endAcc[chain][psi] (out zeroed by the caller)
+// ensemble end-state sum: out[psi] += sum over a slice of chains of endRec[chain][psi].acc (out zeroed by the caller)
 constexpr int kReduceSlice = 64;
 __global__ void reduceEndStateKernel(DevProblem P, DevChains S) {
     const int psi = blockIdx.x * blockDim.x + threadIdx.x;
     if (psi >= P.S) return;
     const int c0 = blockIdx.y * kReduceSlice, c1 = min(c0 + kReduceSlice, S.nChains);
     long long acc = 0;
-    for (int c = c0; c < c1; ++c) acc += S.endAcc[(size_t)c * P.S + psi];
+    for (int c = c0; c < c1; ++c) acc += S.endRec[(size_t)c * P.S + psi].acc;
     atomicAdd(reinterpret_cast<unsigned long long *>(S.endStateSum) + psi, (unsigned long long)acc);
 }
 

@@ -20,7 +20,7 @@ for mode in ("step", "sample", "step", "sample"):
         smp.sample(10 ** 12, max_steps=n_steps)
     smp.synchronize()
     dt = time.time() - t0
-    print(f"{mode}: {n_chains * n_steps / dt / 1e6:.1f} M chain-steps/s", flush=True)
+    print(f"{mode}: {n_chains * n_steps / dt / 1e6:.1f} M chain-steps/s (host clock), step kernel {smp.last_launch_ms():.2f} ms on the device", flush=True)
 t0 = time.time(); st = smp.statistics(); t1 = time.time(); c = smp.counters(); t2 = time.time()
 packed = E.pack_local(*st, c); t3 = time.time()
 print(f"statistics() {1e3*(t1-t0):.2f} ms, counters() {1e3*(t2-t1):.2f} ms, pack_local {1e3*(t3-t2):.2f} ms")
