@@ -5,6 +5,8 @@
 set -x
 TAG=${1:-r1}
 OUT=gpurun_out
+python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/${TAG}_smoke.log 2>&1; tail -1 $OUT/${TAG}_smoke.log
+python bench.py --impl reference --steps 3 --warmup 3 > $OUT/${TAG}_bench_reference_line.json 2> $OUT/${TAG}_bench_reference.err; tail -c 600 $OUT/${TAG}_bench_reference_line.json
 python bench.py > $OUT/${TAG}_bench_line.json 2> $OUT/${TAG}_bench.err; tail -c 2500 $OUT/${TAG}_bench_line.json
 python scripts/probe_sample.py pp32-16 8192 1000 > $OUT/${TAG}_sample_probe.txt 2>&1; tail -6 $OUT/${TAG}_sample_probe.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_bench_launches.csv \

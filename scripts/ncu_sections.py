@@ -21,7 +21,7 @@ marks = [("rng", find("for (long long s = 0")), ("descent", find("column draw"))
          ("columns: prefetch", find("coupled columns, one per lane")), ("importance", find("auto importance = [&]")),
          ("columns: chunks", find("double csLane = 0.0")), ("ratio/accept", find("calcRatioOfSums (:276")),
          ("apply X/delta", find("applyProposal (:322")), ("commit", find("const int Ca = accept")),
-         ("sample stats", find("events of the last timestep changed")), ("end", find("if (act) { ++iter"))]
+         ("sample stats", find("the do-while at SparseBasisSampler.h:247")), ("end", find("if (act) { ++iter"))]
 steps = float(sys.argv[2])
 hdr = rows[2]
 ci = {h: i for i, h in enumerate(hdr)}
