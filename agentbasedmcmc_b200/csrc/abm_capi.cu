@@ -143,7 +143,8 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     std::vector<long> xmin(nRows), xmax(nRows);
     for (int i = 0; i < nTab; ++i)
         if (rowOf[i] >= 0) rowF[rowOf[i]] = desc->tab_F[i], xmin[rowOf[i]] = xmax[rowOf[i]] = desc->tab_F[i];
-    int maxColNnz = 0;
+    int maxColNnz = 0, maxAbs = 1;
+    constexpr int kMaxAbsEntry = 4;
     for (int j = 0; j < nCols; ++j) {
         maxColNnz = std::max(maxColNnz, colPtr[j + 1] - colPtr[j]);
         for (int k = colPtr[j]; k < colPtr[j + 1]; ++k) {
@@ -152,9 +153,12 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
             if (k > colPtr[j] && colRow[k - 1] >= r) return fail(ABM_ERR_INVALID, "column entries must be ascending by row");
             colRow[k] = r;
             colVal[k] = desc->nb_val[k];
-            // PredPrey bases have unit entries only; the kernels tabulate the two possible
-            // one-step moves of a row per proposal, so anything else is rejected rather than mis-sampled
-            if (colVal[k] != 1 && colVal[k] != -1) return fail(ABM_ERR_INVALID, "only tableau entries of +-1 are supported");
+            // the paper's PredPrey bases have unit entries only; small problems (the reference's 3x3
+            // validation experiment) do not.  The kernels tabulate, per row of a proposal, every move -maxAbs..maxAbs a
+            // coupled column could add; the bound keeps that table small.
+            if (colVal[k] == 0 || colVal[k] < -kMaxAbsEntry || colVal[k] > kMaxAbsEntry)
+                return fail(ABM_ERR_INVALID, "tableau entries must be non-zero and at most 4 in magnitude");
+            maxAbs = std::max(maxAbs, std::abs(colVal[k]));
             rowPtr[r + 1]++;
             (colVal[k] < 0 ? xmin[r] : xmax[r]) += colVal[k];
         }
@@ -183,7 +187,11 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
 
     // factor tables
     int nVal = desc->ut_off[desc->n_tables];
-    std::vector<double> facVal(desc->ut_val, desc->ut_val + nVal);
+    // kFacPad zeros on both sides: a proposal tabulates every move up to +-maxAbs of each of its rows, including moves no
+    // coupled column can make, whose (unused) table look-ups may fall just outside the row's reachable range
+    constexpr int kFacPad = 8;
+    std::vector<double> facVal(size_t(nVal) + 2 * kFacPad, 0.0);
+    std::copy(desc->ut_val, desc->ut_val + nVal, facVal.begin() + kFacPad);
     std::vector<int4> rowParam(nRows);
     for (int i = 0, b = 0; i < nTab; ++i) {
         if (rowOf[i] < 0) continue;
@@ -193,7 +201,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         const long L = desc->tab_L[i], U = desc->tab_U[i];
         const long dlo = std::min(std::max(xmin[b], L), U), dhi = std::max(std::min(xmax[b], U), L);
         if (dlo < lo || dhi > lo + len - 1) return fail(ABM_ERR_INVALID, "factor table does not cover the reachable range of its row");
-        rowParam[b] = make_int4(xoff[b], desc->tab_L[i], desc->tab_U[i], desc->ut_off[id] - lo);
+        rowParam[b] = make_int4(xoff[b], desc->tab_L[i], desc->tab_U[i], kFacPad + desc->ut_off[id] - lo);
         ++b;
     }
 
@@ -413,13 +421,15 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.tCapB = (maxTB + 7) & ~7;
     d.tCap = d.tCapA + d.tCapB + ((maxTC + 7) & ~7);
     if (d.blockedTree) d.tCap = d.tCapA = d.tCapB = 0;   // the blocked tree's commit keeps no task list
+    d.maxAbs = maxAbs;
+    d.twoM = 2 * maxAbs;
     d.scrCap = 0;
 #if ABM_SMEM_SCRATCH
     if (d.blockedTree) {
         // what 7 resident CTAs per SM leave to one chain (228 KB per SM, 1 KB reserved per CTA), after the fixed arrays
         const int chainsPerCta = kWarpsPerCta * (32 / W);
         const int budget = (((228 * 1024) / 7 - 1024) / chainsPerCta) & ~15;
-        const int room = (budget - groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0)) / 16;
+        const int room = (budget - groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs)) / 16;
         d.scrCap = std::max(0, std::min(room, d.sCap + W - 1) / W * W);
     }
 #endif
@@ -591,7 +601,7 @@ static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
     constexpr int NG = 32 / W;
     const int chainsPerCta = kWarpsPerCta * NG;
     const int grid = (c->n + chainsPerCta - 1) / chainsPerCta;
-    const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap);
+    const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs);
     cudaError_t e = cudaFuncSetAttribute(stepKernel<MODE, W, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     stepKernel<MODE, W, BLK><<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);

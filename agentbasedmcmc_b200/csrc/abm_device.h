@@ -47,6 +47,8 @@ struct DevProblem {
     int blockedTree;        // 1: 32-ary blocked sum tree (colRec.y = leaf p_u), 0: the reference's binary sum tree
     int groupWidth;         // W
     int rowsCap, sCap, tCap;   // per-chain shared-memory capacities: rows, coupled columns, commit tasks
+    int maxAbs, twoM;          // largest |M_ij| of the basis (1 on the paper's PredPrey problems), and twice that: the row
+                               // moves tabulated per row of a proposal, -maxAbs..-1, 1..maxAbs
     int scrCap;                // blocked tree: leading coupled columns whose staged {DE', leaf} stay in shared memory (multiple of W)
     int tCapA, tCapB;          // task-list regions: levels >= 10, levels 5..9 (the rest of tCap: levels < 5)
     int nSynopsis;

@@ -37,6 +37,9 @@ constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 // ABM_SMEM_SCRATCH: blocked tree: the {DE', leaf} pairs a step stages for its commit stay in shared memory for as many
 // leading coupled columns as 7 resident CTAs per SM leave room for (abm_problem_create sizes it); the rest goes through
 // S.scratch as before.
+#ifndef ABM_UNIT_ONLY
+#define ABM_UNIT_ONLY 0
+#endif
 #ifndef ABM_SMEM_SCRATCH
 #define ABM_SMEM_SCRATCH 0
 #endif
@@ -215,8 +218,8 @@ __device__ __forceinline__ int selectDescending(const double (&v)[32 / W], doubl
 }
 
 // Bytes of shared memory one chain (group) needs; must match the carve-up in stepKernel.
-__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap) {
-    return (scrCap * 16 + sCap * 8 + rowsCap * 16 + 32 * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
+__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs) {
+    return (scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + 32 * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
 }
 
 // MODE_SAMPLE: an accepted proposal (dj != 0) with events in the last timestep moves the end state ModelState(traj,T,T).
@@ -268,14 +271,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     const int chainC = chainValid ? chain : 0;   // pointer arithmetic only; every access is predicated
 
     // ---- per-chain shared memory
-    const int gBytes = groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap);
+    const int gBytes = groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs);
     unsigned char *gs = smemRaw + (size_t)(warp * NG + g) * gBytes;
     double2 *sScr = reinterpret_cast<double2 *>(gs);                     // [scrCap] blocked tree: {DE', signed leaf} of the first
                                                                          //   coupled columns of a step (the rest: S.scratch)
     double *sDl = reinterpret_cast<double *>(sScr + P.scrCap);           // [sCap] delta of set() per coupled column
-    double *sG = sDl + P.sCap;                                           // [rowsCap][2] per row: DE' term for a coupled column
-                                                                         //   whose flip moves the row by -1 / +1
-    double *sNode = sG + 2 * P.rowsCap;                                  // [32] tree nodes of one descent round
+    double *sG = sDl + P.sCap;                                           // [rowsCap][2 maxAbs] per row: DE' term for a coupled
+                                                                         //   column whose flip moves the row by -maxAbs..-1, 1..maxAbs
+    double *sNode = sG + 2 * P.maxAbs * P.rowsCap;                                  // [32] tree nodes of one descent round
     double *sTop = sNode + 32;                                           // [32] the chain's highest tree nodes (root = sTop[0])
     long long *sSyn = reinterpret_cast<long long *>(sTop + 32);          // [2][8] MODE_SAMPLE: synopsis sum / sum of squares
     int *sU = reinterpret_cast<int *>(sSyn + 16);                        // [sCap] coupled columns, ascending
@@ -313,6 +316,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     const double kappa = P.kappa;
     const double *__restrict__ facVal = P.facVal;
     const int nCols = P.nCols;
+#if ABM_UNIT_ONLY   // measurement switch: unit tableau entries assumed at compile time
+    constexpr int kTwoM = 2, kMaxAbs = 1;
+#else
+    const int kTwoM = P.twoM, kMaxAbs = P.maxAbs;
+#endif
     constexpr bool kPhBlk = ABM_PHILOX_BLOCK != 0 && BLK;   // the blocked tree leaves sNode free to hold the drawn block
     constexpr int PB = W < 16 ? W : 16;
     int phIdx = PB;                     // next unread iteration of the drawn Philox block (PB: none left)
@@ -524,14 +532,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 const int xn = x + m * dj;                                                  // :299-300
                 sXoff[k] = xoff;
                 sXX[k] = (uint16_t)((x & 0xff) | ((xn & 0xff) << 8));
-                // dE = energy(x') - energy(x) (:302), and what this row adds to DE' of a coupled column whose flip would move
-                // the row by -1 / +1 (:309-310, unit entries): (energy(x'+s) - energy(x+s)) - dE
+                // dE = energy(x') - energy(x) (:302), and what this row adds to DE' of a coupled column u whose flip would move
+                // the row by s = M_iu delta_u (:309-310): (energy(x'+s) - energy(x+s)) - dE, for s = -maxAbs..-1, 1..maxAbs
+                // (PredPrey tableaux on the paper's problems have unit entries: two values per row)
                 double dE = 0.0;
 #pragma unroll 1
-                for (int d = 0; d < 3; ++d) {   // shift 0 first (dE itself), then -1 and +1
-                    const int sh = d == 0 ? 0 : 2 * d - 3;
+                for (int d = 0; d <= kTwoM; ++d) {   // shift 0 first (dE itself), then the shifts in ascending order
+                    const int sh = d == 0 ? 0 : (2 * d <= kTwoM ? d - kMaxAbs - 1 : d - kMaxAbs);
                     const double e = __dsub_rn(energyOf(xn + sh, r.y, r.z, r.w, facVal, kappa), energyOf(x + sh, r.y, r.z, r.w, facVal, kappa));
-                    if (d == 0) dE = e; else sG[2 * k + d - 1] = __dsub_rn(e, dE);
+                    if (d == 0) dE = e; else sG[kTwoM * k + d - 1] = __dsub_rn(e, dE);
                 }
                 dinf += infeasOf(xn, r.y, r.z) - infeasOf(x, r.y, r.z);                    // :303
             }
@@ -665,7 +674,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 const int ct = ct4[t];
                 if (ct != kNoContrib) {
                     const int k = ct & 0xff, mu = (int)(int8_t)(ct >> 8);
-                    acc = __dadd_rn(acc, sG[2 * k + (mu * du > 0 ? 1 : 0)]);                 // :308-310, unit entries
+                    const int sv = mu * du;                                                  // the row's move if u flipped
+                    acc = __dadd_rn(acc, sG[kTwoM * k + kMaxAbs + sv - (sv > 0 ? 1 : 0)]);     // :308-310
                 }
             }
             const int tW = warpMax(maxCnt);
@@ -675,7 +685,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     const int ct = __ldg(plane + t * W);
                     if (ct != kNoContrib) {
                         const int k = ct & 0xff, mu = (int)(int8_t)(ct >> 8);
-                        acc = __dadd_rn(acc, sG[2 * k + (mu * du > 0 ? 1 : 0)]);
+                        const int sv = mu * du;
+                        acc = __dadd_rn(acc, sG[kTwoM * k + kMaxAbs + sv - (sv > 0 ? 1 : 0)]);
                     }
                 }
             }

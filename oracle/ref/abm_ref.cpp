@@ -631,6 +631,71 @@ int cmdConstraints(const AbmpFile &f, const std::string &out, int rebuild) {
     return 0;
 }
 
+// The reference's own validation experiment for this path on PredPrey (Experiments::PredPreySingleObservation,
+// Experiments.cpp:49-65, through doSingleObservationExperiment, :129-168): 3x3 grid, 2 timesteps, Poisson start state with
+// rates 0.1 (predator) / 0.2 (prey), one observation "one prey at (1,1) at time 1", kappa = 3; the sampler starts from the
+// empty trajectory (SparseBasisSampler(posterior, kappa), SparseBasisSampler.h:199-206).  Writes the problem as an ABMP
+// file and, to `margOut`, the end-state means ModelState(sample, T, T) of (a) the reference sampler after nBurnin samples,
+// over nSamples, and (b) the reference RejectionSampler over nRejection samples -- the two things the experiment prints
+// and compares (RMS error, :163-167).
+#include "RejectionSampler.h"
+static int cmdSingleObservationExperiment(const std::string &out, const std::string &margOut, long nSamples, long nBurnin,
+                                          long nRejection, int seed) {
+    constexpr int G = 3, T = 2;
+    typedef PredPreyAgent<G> Agent;
+    const double pPredator = 0.1, pPrey = 2.0 * pPredator, kappa = 3.0;
+    Random::gen.seed(seed);
+    PredPreyProblem<G> problem;
+    problem.pPredator = pPredator;
+    problem.pPrey = pPrey;
+    problem.kappa = kappa;
+    problem.prior = makePrior<G>(T, 1, pPredator, pPrey);
+    problem.realTrajectory = Trajectory<Agent>(T);
+    problem.likelihood = Likelihood<Agent>(AgentStateObservation<Agent>(State<Agent>(1, Agent(1, 1, Agent::PREY)), 1, 1.0));
+    problem.posterior = problem.likelihood * problem.prior;
+    {
+        SilenceStdout quiet;
+        problem.tableau = TableauNormMinimiser<occ_t>(problem.posterior.constraints);   // the constructor runs findMinimalBasis()
+    }
+    AbmpFile f = exportProblem<G>(problem, seed, 0.0, 1.0, 1);
+    f.write(out);
+
+    std::vector<double> mcmc(Agent::domainSize(), 0.0), rej(Agent::domainSize(), 0.0);
+    long steps = 0;
+    {
+        SilenceStdout quiet;
+        SparseBasisSampler<occ_t> sampler(problem.tableau, problem.posterior.factors, problem.posterior.perturbableFunctionFactory(),
+                                          std::vector<occ_t>(), kappa);
+        for (long b = 0; b < nBurnin; ++b) sampler();
+        const long s0 = sampler.stats.nSamples();
+        for (long n = 0; n < nSamples; ++n) {
+            ModelState<Agent> endState(sampler(), T, T);
+            for (int k = 0; k < Agent::domainSize(); ++k) mcmc[k] += endState[k];
+        }
+        steps = sampler.stats.nSamples() - s0;
+    }
+    RejectionSampler<Trajectory<Agent>> rejectionSampler(problem.prior, problem.likelihood);
+    for (long n = 0; n < nRejection; ++n) {
+        ModelState<Agent> endState(rejectionSampler(), T, T);
+        for (int k = 0; k < Agent::domainSize(); ++k) rej[k] += endState[k];
+    }
+    double rms = 0.0;
+    for (int k = 0; k < Agent::domainSize(); ++k) {
+        mcmc[k] /= nSamples;
+        rej[k] /= nRejection;
+        rms += (mcmc[k] - rej[k]) * (mcmc[k] - rej[k]);
+    }
+    rms = sqrt(rms / Agent::domainSize());
+    AbmpFile o;
+    o.f64["mcmc_endstate_mean"] = mcmc;
+    o.f64["rejection_endstate_mean"] = rej;
+    o.f64["counts"] = {double(nSamples), double(nBurnin), double(nRejection), double(steps), rms};
+    o.write(margOut);
+    fprintf(stderr, "single-observation experiment: %ld samples (%ld Metropolis steps), %ld rejection samples, RMS error %.5f\n",
+            nSamples, steps, nRejection, rms);
+    return 0;
+}
+
 #define DISPATCH_G(G_, CALL)                                   \
     switch (G_) {                                              \
         case 3: { constexpr int G = 3; return CALL; }          \
@@ -674,6 +739,8 @@ static int run(int argc, char **argv) {
         const bool fastBasis = argc > 12 && std::string(argv[12]) == "fastbasis";
         DISPATCH_G(g, cmdGen<G>(T, seed, kappa, out, pPred, pPrey, pObs, pObsIf, startKind, fastBasis));
     }
+    if (cmd == "experiment3")   // experiment3 problem.abmp marginals.abmp nSamples nBurnin nRejection seed
+        return cmdSingleObservationExperiment(argv[2], argv[3], atol(argv[4]), atol(argv[5]), atol(argv[6]), atoi(argv[7]));
     AbmpFile f = AbmpFile::read(argv[2]);
     int g = f.I("pp_meta")[0];
     if (cmd == "init") { DISPATCH_G(g, cmdInit<G>(f, atoi(argv[3]), atoi(argv[4]), argv[5])); }

@@ -65,6 +65,18 @@ def main():
                                                     "n": np.array([20000, 64], np.int32),
                                                     # start states holding two agents that chose different acts (Poisson only)
                                                     "multi_act_t0": np.array([((x[:, 0] > 0).sum(axis=-1) >= 2).mean()])})
+    # The reference's own validation experiment on PredPrey (Experiments::PredPreySingleObservation, Experiments.cpp:49-65): 3x3 grid,
+    # 2 timesteps, Poisson start, one observation; its tableau has an entry of magnitude 2 and the grid is not a power of two.
+    # experiment3 = problem + end-state means of the reference sampler (500000 samples after 10000) and of the reference
+    # RejectionSampler (2000000 samples; 100000 in the experiment itself); then a golden step trace on the same problem.
+    if True:
+        raw, marg = tmp / "exp_pp3-2-single.abmp", tmp / "exp_pp3-2-single_means.abmp"
+        subprocess.run([str(REF), "experiment3", str(raw), str(marg), "500000", "10000", "2000000", "4321"], check=True)
+        xz(raw, HERE / "exp_pp3-2-single.abmp.xz")
+        xz(marg, HERE / "exp_pp3-2-single_means.abmp.xz")
+        traw = tmp / "trace_exp_pp3-2-single_301.abmp"
+        subprocess.run([str(REF), "trace", str(raw), "31", "301", "20000", "500", str(traw)], check=True)
+        xz(traw, HERE / "trace_exp_pp3-2-single_301.abmp.xz")
     # long reference chains for posterior marginals (64 chains x 60000 feasible samples after 60000 burn-in)
     raw = tmp / "marginals_pp8-4.abmp"
     subprocess.run([str(REF), "marginals", str(tmp / "pp8-4.abmp"), "64", "60000", "60000", str(raw)], check=True)

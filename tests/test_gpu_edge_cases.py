@@ -62,11 +62,12 @@ def test_errors_are_reported_not_swallowed():
         smp.findInitialFeasibleSolution(max_iterations=3)
     smp.findInitialFeasibleSolution()                   # and the search can be resumed afterwards
     assert np.all(smp.infeasibility() == 0)
-    # tableau entries other than +-1 (e.g. the reference's CatMouse agent) are rejected, not mis-sampled
+    # tableau entries beyond magnitude 4 are rejected, not mis-sampled (a proposal tabulates every move a coupled column
+    # could add to a row, -maxAbs..maxAbs: the reference's PredPrey problems need 1, its 3x3 validation experiment 2)
     bad = dict(p)
     bad["nb_val"] = p["nb_val"].copy()
-    bad["nb_val"][0] = 2
-    with pytest.raises(S.AbmError, match=r"\+-1"):
+    bad["nb_val"][0] = 5
+    with pytest.raises(S.AbmError, match=r"at most 4"):
         S.Problem(bad)
     # a factor table that does not cover its row's reachable range
     bad = dict(p)

@@ -29,7 +29,9 @@ TREES = ["blocked", "reference"]   # ABM_TREE_BLOCKED (default, fast) and ABM_TR
 @pytest.mark.parametrize("prob,trace,n_steps", [("pp8-4.abmp.xz", "trace_pp8-4_101.abmp.xz", 20000),
                                                 ("pp8-4.abmp.xz", "trace_pp8-4_102.abmp.xz", 20000),
                                                 ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz", 20000),
-                                                ("pp8-4-poisson.abmp.xz", "trace_pp8-4-poisson_103.abmp.xz", 20000)])
+                                                ("pp8-4-poisson.abmp.xz", "trace_pp8-4-poisson_103.abmp.xz", 20000),
+                                                # 3x3 grid, Poisson start, a tableau entry of magnitude 2 (Experiments.cpp:49-65)
+                                                ("exp_pp3-2-single.abmp.xz", "trace_exp_pp3-2-single_301.abmp.xz", 20000)])
 def test_reference_golden_trace(prob, trace, n_steps, tree):
     """Same mt19937 uniform stream as the reference run -> same columns, decisions, infeasibilities and X, in both
     sum-tree storages.  The blocked tree holds exact leaves, the reference's get(u) is a difference of drifting sums
@@ -204,6 +206,31 @@ def test_posterior_marginals_match_reference_long_run():
     acc = c[4:].sum() / c[:4].sum()
     assert abs(acc - 0.834) < 0.02
     assert np.all(np.isfinite(summ.rhat)) and np.all(summ.rhat > 0.99)   # 1500 correlated samples per chain: R-hat is well above 1
+
+
+@pytest.mark.parametrize("tree", TREES)
+def test_reference_validation_experiment(tree):
+    """Experiments::PredPreySingleObservation (Experiments.cpp:49-65 through doSingleObservationExperiment, :129-168) on the
+    GPU: 3x3 grid, 2 timesteps, Poisson start, one observation, kappa = 3, chains started from the empty trajectory as
+    SparseBasisSampler(posterior, kappa) does (:199-206).  The experiment compares the sampler's end-state means with the
+    RejectionSampler's (the reference's own run: RMS error 0.0036 with 500000 samples).  Here 2048 chains x 1000 samples
+    after 2000 steps of burn-in against the reference's 2000000 rejection samples: RMS error below 0.003, every state
+    within 0.008.  The problem has a tableau entry of magnitude 2 and a grid that is not a power of two."""
+    from agentbasedmcmc_b200 import ensemble as E
+    S = _gpu()
+    p, m = load_golden("exp_pp3-2-single.abmp.xz"), load_golden("exp_pp3-2-single_means.abmp.xz")
+    assert np.abs(p["nb_val"]).max() == 2
+    rej = m["rejection_endstate_mean"]
+    P = S.Problem(p, sum_tree=tree)
+    smp = S.SparseBasisSampler(P, n_chains=2048, seed=77)
+    smp.step(2000)
+    smp.sample(1000)
+    summ = E.sampler_summary(smp)
+    assert summ.n_samples == 2048 * 1000
+    err = summ.end_state_mean - rej
+    assert np.sqrt((err ** 2).mean()) < 0.003, f"RMS error {np.sqrt((err ** 2).mean()):.5f}"
+    assert np.abs(err).max() < 0.008
+    assert smp.stats.nInfeasibleSamples() < 0.6 * smp.stats.nSamples()
 
 
 @pytest.mark.parametrize("name", ["pp8-4", "pp8-4-poisson"])

@@ -10,7 +10,10 @@ from oracle.oracle import OracleChain, OracleProblem, mt_uniforms
 TRACES = [("pp8-4.abmp.xz", "trace_pp8-4_101.abmp.xz"), ("pp8-4.abmp.xz", "trace_pp8-4_102.abmp.xz"),
           ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz"),
           # Poisson start state (PoissonStartState.h:18-31: unbounded occupation rows, lgamma factors), SURVEY 8(f)4
-          ("pp8-4-poisson.abmp.xz", "trace_pp8-4-poisson_103.abmp.xz")]
+          ("pp8-4-poisson.abmp.xz", "trace_pp8-4-poisson_103.abmp.xz"),
+          # the problem of the reference's own validation experiment (Experiments::PredPreySingleObservation, Experiments.cpp:49-65):
+          # 3x3 grid (not a power of two), Poisson start, a tableau entry of magnitude 2
+          ("exp_pp3-2-single.abmp.xz", "trace_exp_pp3-2-single_301.abmp.xz")]
 
 
 def bits(a):
@@ -103,3 +106,25 @@ def test_end_state_occupancy_counts_agents():
     last = X[(T - 1) * S * A:T * S * A].reshape(S, A)
     # every non-DIE act yields one agent at T, GIVEBIRTH two (PredPreyAgent.h:98-115)
     assert c.end_state.sum() == last[:, 1:].sum() + last[:, 5].sum()
+
+
+def test_oracle_reproduces_reference_validation_experiment():
+    """Experiments::PredPreySingleObservation (Experiments.cpp:49-65, 129-168), the reference's own check of this path: the
+    sampler's end-state means against the RejectionSampler's.  Fixture: the reference's two estimates (500000 sampler
+    samples, RMS error 0.0036 between them; 2000000 rejection samples).  Here: 8 oracle chains from the empty trajectory
+    (SparseBasisSampler.h:199-206), 2000 samples burn-in, 100000 samples each; RMS error to the rejection means below
+    0.006 (measured 0.0021) and every state within 0.012."""
+    p, m = load_golden("exp_pp3-2-single.abmp.xz"), load_golden("exp_pp3-2-single_means.abmp.xz")
+    rej = m["rejection_endstate_mean"]
+    assert np.sqrt(((m["mcmc_endstate_mean"] - rej) ** 2).mean()) < 0.006      # the reference's own run
+    P = OracleProblem(p)
+    end, s1, s2, total = np.zeros(18, np.int64), np.zeros(8, np.int64), np.zeros(8, np.int64), 0
+    for c in range(8):
+        oc = OracleChain(P)
+        oc.seed_mt(100 + c)
+        oc.find_feasible()
+        oc.sample_stats(2000, 10 ** 9, np.zeros(18, np.int64), s1, s2)
+        total += oc.sample_stats(100000, 10 ** 9, end, s1, s2)
+    mean = end / total
+    assert np.sqrt(((mean - rej) ** 2).mean()) < 0.006
+    assert np.abs(mean - rej).max() < 0.012
