@@ -70,9 +70,56 @@ int run(int T, int nSamples) {
     return 0;
 }
 
+// The reference's validation experiment for this path (Experiments::PredPreySingleObservation, Experiments.cpp:49-65, body
+// of doSingleObservationExperiment, :129-168) with the GPU sampler constructed exactly as the experiment constructs the
+// reference one -- `sampler(posterior, kappa)`, empty initial trajectory -- next to the unmodified sampler on the same
+// Random::gen stream: burn-in, then nSamples samples summed into a ModelState; samples and aggregate must be identical.
+#include "PoissonStartState.h"
+#include "ModelState.h"
+int runExperiment(int nSamples) {
+    constexpr int GRIDSIZE = 3, nTimesteps = 2, nBurnin = 1000;
+    constexpr double pPredator = 0.1, pPrey = 2.0 * pPredator, kappa = 3.0;
+    typedef PredPreyAgent<GRIDSIZE> AGENT;
+    std::streambuf *old = std::cout.rdbuf(nullptr);
+    Prior<AGENT> prior(nTimesteps, PoissonStartState<AGENT>([](AGENT agent) { return agent.type() == AGENT::PREDATOR ? pPredator : pPrey; }));
+    Likelihood<AGENT> likelihood(AgentStateObservation<AGENT>(State<AGENT>(1, AGENT(1, 1, AGENT::PREY)), 1, 1.0));
+    auto posterior = likelihood * prior;
+    Random::gen.seed(2021);
+    SparseBasisSampler<ABM::occupation_type> ref(posterior, kappa);
+    std::mt19937 genRef = Random::gen;
+    Random::gen.seed(2021);
+    abmcmc::GpuSparseBasisSampler<ABM::occupation_type> gpu(posterior, kappa);
+    std::mt19937 genGpu = Random::gen;
+    std::cout.rdbuf(old);
+    if (!(genRef == genGpu) || ref.X != gpu.X) { printf("FAIL: construction differs\n"); return 1; }
+    ModelState<AGENT> aggRef, aggGpu;
+    for (int k = 0; k < nBurnin + nSamples; ++k) {
+        Random::gen = genRef;
+        const std::vector<ABM::occupation_type> &a = ref();
+        genRef = Random::gen;
+        Random::gen = genGpu;
+        const std::vector<ABM::occupation_type> &b = gpu();
+        genGpu = Random::gen;
+        if (a != b || !(genRef == genGpu)) { printf("FAIL: sample %d differs\n", k); return 1; }
+        if (!posterior.constraints.isValidSolution(b)) { printf("FAIL: sample %d is not a valid solution\n", k); return 1; }
+        if (k >= nBurnin) {
+            aggRef += ModelState<AGENT>(a, nTimesteps, nTimesteps);
+            aggGpu += ModelState<AGENT>(b, nTimesteps, nTimesteps);
+        }
+    }
+    for (int i = 0; i < AGENT::domainSize(); ++i)
+        if (aggRef[i] != aggGpu[i]) { printf("FAIL: aggregate state differs\n"); return 1; }
+    double total = 0.0;
+    for (int i = 0; i < AGENT::domainSize(); ++i) total += aggGpu[i];
+    printf("OK: PredPreySingleObservation: %d samples identical to the reference SparseBasisSampler (%d Metropolis steps), mean agents at T = %.4f\n",
+           nSamples, ref.stats.nSamples(), total / nSamples);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     int g = argc > 1 ? atoi(argv[1]) : 8, T = argc > 2 ? atoi(argv[2]) : 4, n = argc > 3 ? atoi(argv[3]) : 300;
     try {
+        if (g == 3) return runExperiment(n);
         if (g == 8) return run<8>(T, n);
         if (g == 16) return run<16>(T, n);
         printf("unsupported grid\n");

@@ -12,7 +12,9 @@ pytestmark = pytest.mark.gpu
 EXE = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "dropin_check"
 
 
-@pytest.mark.parametrize("grid,T,n", [(8, 4, 300), (16, 8, 60)])
+# grid 3: the reference's validation experiment Experiments::PredPreySingleObservation (Experiments.cpp:49-65) with the GPU
+# sampler constructed as `sampler(posterior, kappa)`; 8 and 16: the paper's problem generator
+@pytest.mark.parametrize("grid,T,n", [(8, 4, 300), (16, 8, 60), (3, 2, 5000)])
 def test_cpp_dropin_matches_reference_sample_for_sample(grid, T, n):
     if not EXE.exists():
         pytest.skip("oracle/_ref/dropin_check not built (needs /root/reference at build time)")
