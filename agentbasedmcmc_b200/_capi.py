@@ -18,7 +18,7 @@ SYMBOLS = [
     "abm_problem_get_info", "abm_problem_n_synopsis", "abm_chains_create", "abm_chains_destroy", "abm_chains_init",
     "abm_chains_init_from_prior", "abm_chains_find_feasible", "abm_chains_step", "abm_chains_step_traced", "abm_chains_sample",
     "abm_chains_synchronize", "abm_chains_get_state", "abm_chains_get_counters", "abm_chains_get_infeasibility",
-    "abm_chains_get_trajectories", "abm_chains_get_statistics", "abm_chains_reset_statistics",
+    "abm_chains_get_trajectories", "abm_chains_get_statistics", "abm_chains_enqueue_statistics", "abm_chains_wait_statistics", "abm_chains_reset_statistics",
     "abm_chains_record_series", "abm_chains_get_series",
     "abm_chains_last_launch_ms", "abm_basis_minimise", "abm_basis_destroy", "abm_basis_get_dims", "abm_basis_get", "abm_basis_get_rows",
 ]
@@ -82,6 +82,8 @@ def load():
     L.abm_chains_get_infeasibility.argtypes = [vp, i32p]
     L.abm_chains_get_trajectories.argtypes = [vp, i8p]
     L.abm_chains_get_statistics.argtypes = [vp, i64p, i64p, i64p, i64p, C.c_int]
+    L.abm_chains_enqueue_statistics.argtypes = [vp]
+    L.abm_chains_wait_statistics.argtypes = [vp, i64p, i64p, i64p, i64p, i64p]
     L.abm_chains_reset_statistics.argtypes = [vp]
     L.abm_chains_record_series.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.abm_chains_get_series.argtypes = [vp, i32p]

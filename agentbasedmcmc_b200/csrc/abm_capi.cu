@@ -88,6 +88,11 @@ struct abm_chains {
     bool initialised = false, feasible = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the last step / sample launch (abm_chains_last_launch_ms)
     bool timed = false;
+    // abm_chains_enqueue_statistics / abm_chains_wait_statistics: pinned staging + the event after its copies
+    int64_t *stage = nullptr;
+    size_t stageWords = 0;
+    cudaEvent_t evStats = nullptr;
+    bool statsPending = false;
 };
 
 // CUDA events on the chains' stream around a step kernel, so a caller can time the kernel itself
@@ -375,6 +380,7 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
         if (rec.size() / 4 > 0xfffffff0ull) return fail(ABM_ERR_INVALID, "record table too large");
     }
     while (rec.size() % 4) rec.push_back(0);
+    rec.insert(rec.end(), 64, 0);   // lanes read a record's last list one chunk at a time, past its end
     if (maxCoupled > 2040) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2040 others");
 
     // [7] lgamma(occ+1), [2][2][6] log(pi/pibar), then the factor log-probability of TrajectoryImportance::refresh
@@ -424,15 +430,21 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.maxAbs = maxAbs;
     d.twoM = 2 * maxAbs;
     d.scrCap = 0;
-#if ABM_SMEM_SCRATCH
+    d.nodeCap = (d.blockedTree && !ABM_PHILOX_BLOCK) ? 0 : 32;
+    d.t2Cap = 0;
     if (d.blockedTree) {
         // what 7 resident CTAs per SM leave to one chain (228 KB per SM, 1 KB reserved per CTA), after the fixed arrays
         const int chainsPerCta = kWarpsPerCta * (32 / W);
         const int budget = (((228 * 1024) / 7 - 1024) / chainsPerCta) & ~15;
-        const int room = (budget - groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs)) / 16;
-        d.scrCap = std::max(0, std::min(room, d.sCap + W - 1) / W * W);
-    }
+#if ABM_T2_SMEM
+        if (groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs, d.nodeCap, d.t2Len) <= budget) d.t2Cap = d.t2Len;
 #endif
+#if ABM_SMEM_SCRATCH
+        const int room = (budget - groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs, d.nodeCap, d.t2Cap)) / 16;
+        d.scrCap = std::max(0, std::min(room, d.sCap + W - 1) / W * W);
+#endif
+    }
+    if (const char *e = getenv("ABM_T2_SMEM_OFF")) if (atoi(e)) d.t2Cap = 0;   // measurement switch
     if (maxTA > 1000 || maxTB > 1000 || maxTC > 1000) return fail(ABM_ERR_INVALID, "too many sum-tree nodes touched by one column");
     d.nSynopsis = nSyn;
     d.kappa = desc->kappa;
@@ -511,6 +523,8 @@ int abm_chains_destroy(abm_chains *c) {
     cudaStreamSynchronize(c->stream);
     if (c->series) cudaFree(c->series);
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
+    if (c->evStats) cudaEventDestroy(c->evStats);
+    if (c->stage) cudaFreeHost(c->stage);
     delete c;
     return ABM_OK;
 }
@@ -601,7 +615,7 @@ static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
     constexpr int NG = 32 / W;
     const int chainsPerCta = kWarpsPerCta * NG;
     const int grid = (c->n + chainsPerCta - 1) / chainsPerCta;
-    const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs);
+    const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs, P.nodeCap, P.t2Cap);
     cudaError_t e = cudaFuncSetAttribute(stepKernel<MODE, W, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     stepKernel<MODE, W, BLK><<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);
@@ -773,7 +787,7 @@ int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
     if (maxSteps > 0 && (nSamples == 0 || nSamples >= maxSteps)) CUDA_TRY(launchStep<MODE_SAMPLE_FIXED>(c, r));
     else CUDA_TRY(launchStep<MODE_SAMPLE>(c, r));
     CUDA_TRY(markLaunch(c, false));
-    sampleEndKernel<<<dim3(std::max(1, std::min((P.S + 255) / 256, 8)), c->n), 256, 0, c->stream>>>(P, c->d);
+    sampleEndKernel<<<c->n, 256, 0, c->stream>>>(P, c->d);
     CUDA_TRY(cudaGetLastError());
     return ABM_OK;
 }
@@ -890,6 +904,63 @@ int abm_chains_get_statistics(abm_chains *c, int64_t *endStateSum, int64_t *synS
     if (synSumSq && ns) CUDA_TRY(cudaMemcpyAsync(synSumSq, c->d.synSumSq, n * ns * sizeof(int64_t), kind, c->stream));
     if (nSamples) CUDA_TRY(cudaMemcpyAsync(nSamples, c->d.nSamples, n * sizeof(int64_t), kind, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ABM_OK;
+}
+
+// Statistics read-back that does not stall the stream: enqueue = ensemble reduction + device-to-host copies into pinned
+// staging owned by the handle, ordered after everything launched so far; wait = block until those copies have landed (later
+// launches keep running) and hand the values to the caller's buffers.  Layout of the staging: end_state_sum[S],
+// syn_sum[n][d], syn_sumsq[n][d], n_samples[n], counters[n][8].
+int abm_chains_enqueue_statistics(abm_chains *c) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const DevProblem &P = c->p->d;
+    const size_t n = size_t(c->n), ns = size_t(P.nSynopsis), S = size_t(std::max(P.S, 0));
+    const size_t words = S + 2 * n * ns + n + 8 * n;
+    if (!c->stage || c->stageWords != words) {
+        if (c->stage) CUDA_TRY(cudaFreeHost(c->stage));
+        c->stage = nullptr;
+        CUDA_TRY(cudaMallocHost(&c->stage, words * sizeof(int64_t)));
+        c->stageWords = words;
+    }
+    if (!c->evStats) CUDA_TRY(cudaEventCreateWithFlags(&c->evStats, cudaEventDisableTiming));
+    int64_t *o = c->stage;
+    if (S > 0) {
+        CUDA_TRY(cudaMemsetAsync(c->d.endStateSum, 0, S * sizeof(long long), c->stream));
+        reduceEndStateKernel<<<dim3((P.S + 127) / 128, (c->n + kReduceSlice - 1) / kReduceSlice), 128, 0, c->stream>>>(P, c->d);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(o, c->d.endStateSum, S * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    o += S;
+    if (ns) {
+        CUDA_TRY(cudaMemcpyAsync(o, c->d.synSum, n * ns * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(o + n * ns, c->d.synSumSq, n * ns * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    o += 2 * n * ns;
+    CUDA_TRY(cudaMemcpyAsync(o, c->d.nSamples, n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(o + n, c->d.counters, n * 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaEventRecord(c->evStats, c->stream));
+    c->statsPending = true;
+    return ABM_OK;
+}
+
+int abm_chains_wait_statistics(abm_chains *c, int64_t *endStateSum, int64_t *synSum, int64_t *synSumSq, int64_t *nSamples,
+                               abm_mcmc_counters *counters) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    if (!c->statsPending) return fail(ABM_ERR_STATE, "abm_chains_enqueue_statistics has not been called");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaEventSynchronize(c->evStats));
+    c->statsPending = false;
+    const DevProblem &P = c->p->d;
+    const size_t n = size_t(c->n), ns = size_t(P.nSynopsis), S = size_t(std::max(P.S, 0));
+    const int64_t *o = c->stage;
+    if (endStateSum) memcpy(endStateSum, o, S * sizeof(int64_t));
+    o += S;
+    if (synSum) memcpy(synSum, o, n * ns * sizeof(int64_t));
+    if (synSumSq) memcpy(synSumSq, o + n * ns, n * ns * sizeof(int64_t));
+    o += 2 * n * ns;
+    if (nSamples) memcpy(nSamples, o, n * sizeof(int64_t));
+    if (counters) memcpy(counters, o + n, n * 8 * sizeof(int64_t));
     return ABM_OK;
 }
 

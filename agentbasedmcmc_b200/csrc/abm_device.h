@@ -49,6 +49,8 @@ struct DevProblem {
     int rowsCap, sCap, tCap;   // per-chain shared-memory capacities: rows, coupled columns, commit tasks
     int maxAbs, twoM;          // largest |M_ij| of the basis (1 on the paper's PredPrey problems), and twice that: the row
                                // moves tabulated per row of a proposal, -maxAbs..-1, 1..maxAbs
+    int nodeCap, t2Cap;        // shared-memory doubles per chain: descent staging (reference tree: 32) / blocked tree's sums of 1024
+                               // leaves when 7 resident CTAs per SM leave room for them (t2Len, else 0)
     int scrCap;                // blocked tree: leading coupled columns whose staged {DE', leaf} stay in shared memory (multiple of W)
     int tCapA, tCapB;          // task-list regions: levels >= 10, levels 5..9 (the rest of tCap: levels < 5)
     int nSynopsis;

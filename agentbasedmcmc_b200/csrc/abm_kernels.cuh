@@ -37,6 +37,17 @@ constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 // ABM_SMEM_SCRATCH: blocked tree: the {DE', leaf} pairs a step stages for its commit stay in shared memory for as many
 // leading coupled columns as 7 resident CTAs per SM leave room for (abm_problem_create sizes it); the rest goes through
 // S.scratch as before.
+// ABM_T2_SMEM: blocked tree: the sums of 1024 leaves stay in shared memory during a launch when they fit next to the other
+// per-chain arrays at 7 CTAs per SM (32x32x16: 161 doubles per chain): one L2 round trip less per column draw, and their
+// updates are shared-memory adds instead of L2 reductions.
+#ifndef ABM_T2_SMEM
+#define ABM_T2_SMEM 0
+#endif
+// ABM_END_DEFERRED: sample launches: the end-state effect list of an accepted proposal is requested when the proposal is
+// accepted and applied after the commit (its round trip overlaps the commit) instead of through an out-of-line call.
+#ifndef ABM_END_DEFERRED
+#define ABM_END_DEFERRED 1
+#endif
 #ifndef ABM_UNIT_ONLY
 #define ABM_UNIT_ONLY 0
 #endif
@@ -218,8 +229,10 @@ __device__ __forceinline__ int selectDescending(const double (&v)[32 / W], doubl
 }
 
 // Bytes of shared memory one chain (group) needs; must match the carve-up in stepKernel.
-__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs) {
-    return (scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + 32 * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
+// nodeCap: 32 doubles of descent / summation staging (reference tree; 0 for the blocked tree); t2Cap: the blocked tree's sums of
+// 1024 leaves when they are kept in shared memory for the launch (0 otherwise)
+__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs, int nodeCap, int t2Cap) {
+    return (scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
 }
 
 // MODE_SAMPLE: an accepted proposal (dj != 0) with events in the last timestep moves the end state ModelState(traj,T,T).
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     const int chainC = chainValid ? chain : 0;   // pointer arithmetic only; every access is predicated
 
     // ---- per-chain shared memory
-    const int gBytes = groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs);
+    const int gBytes = groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs, P.nodeCap, P.t2Cap);
     unsigned char *gs = smemRaw + (size_t)(warp * NG + g) * gBytes;
     double2 *sScr = reinterpret_cast<double2 *>(gs);                     // [scrCap] blocked tree: {DE', signed leaf} of the first
                                                                          //   coupled columns of a step (the rest: S.scratch)
@@ -279,7 +292,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     double *sG = sDl + P.sCap;                                           // [rowsCap][2 maxAbs] per row: DE' term for a coupled
                                                                          //   column whose flip moves the row by -maxAbs..-1, 1..maxAbs
     double *sNode = sG + 2 * P.maxAbs * P.rowsCap;                                  // [32] tree nodes of one descent round
-    double *sTop = sNode + 32;                                           // [32] the chain's highest tree nodes (root = sTop[0])
+    double *sT2 = sNode + P.nodeCap;                                     // [t2Cap] blocked tree: sums of 1024 leaves, when they fit
+    double *sTop = sT2 + P.t2Cap;                                        // [32] the chain's highest tree nodes (root = sTop[0])
     long long *sSyn = reinterpret_cast<long long *>(sTop + 32);          // [2][8] MODE_SAMPLE: synopsis sum / sum of squares
     int *sU = reinterpret_cast<int *>(sSyn + 16);                        // [sCap] coupled columns, ascending
     int *sXoff = sU + P.sCap;                                            // [rowsCap] Xb offsets of the rows
@@ -303,6 +317,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (chainValid && k < nTop) v = BLK ? tier3[k] : ch.tier2[(k << P.topShift) >> 10];
         sTop[k] = v;
     }
+    const bool t2s = BLK && P.t2Cap > 0;   // the second-highest level of the blocked tree lives in shared memory, too
+    if (t2s)
+        for (int k = gl; k < P.t2Len; k += W) sT2[k] = chainValid ? ch.tier2[k] : 0.0;
     __syncwarp();
     double2 *scratch = S.scratch + (size_t)chainC * P.sCap;
     const int scrChunks = BLK ? P.scrCap / W : 0;   // chunks of coupled columns whose staged values stay in shared memory
@@ -329,6 +346,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     // State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115), kept
     // incrementally, with per-state accumulators advanced lazily (occupancy x samples since the last change)
     int nSamp = 0;                      // feasible samples taken in this launch
+    int fxN = 0, fxK = 0, fxS = 0;      // pending end-state effect of an accepted proposal (ABM_END_DEFERRED)
     int syn = 0;                        // lane k < nSynopsis: agents inside the k-th nested square (FiguresForPaper.h:245-263)
     if (kSample) {   // end-state occupancy and synopsis were prepared by sampleBeginKernel
         if (chainValid && gl < P.nSynopsis) syn = S.synNow[(size_t)chain * P.nSynopsis + gl];
@@ -411,7 +429,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 for (int k = 0; k < NG; ++k) {
                     const int e = first + gl * NG + k;
                     v[k] = 0.0;
-                    if (act && e < count) v[k] = lvl == 2 ? __ldcg(ch.tier2 + e) : (lvl == 1 ? __ldcg(ch.tier1 + e) : fabs(ch.colRec[e].y));   // leaf sign = delta_e; the two tiers are updated by L2 reductions
+                    if (act && e < count)   // leaf sign = delta_e; tiers in global memory are updated by L2 reductions
+                        v[k] = lvl == 2 ? (t2s ? sT2[e] : __ldcg(ch.tier2 + e)) : (lvl == 1 ? __ldcg(ch.tier1 + e) : fabs(ch.colRec[e].y));
                 }
                 sel = first + selectDescending<W>(v, target, gl);
             }
@@ -784,9 +803,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (kSample) {
             // events of the last timestep changed by an accepted proposal move the end state (evaluated here, while the
             // record pointers of the proposal are still live)
+#if ABM_END_DEFERRED
+            // the effect list is requested now and applied after the commit, so its round trip overlaps the commit
+            if (accept && colTouchesEnd) {
+                const int32_t *__restrict__ fx = staleF + nSF;
+                fxN = __ldg(fx) * dj;                    // nEnd, signed by delta_j (nEnd >= 1 for such a column)
+                fxK = __ldg(fx + 3 + gl);                // speculative beyond nEnd: the record table is padded
+                fxS = __ldg(fx + 1 + (gl >> 2));
+                if (abs(fxN) > W) fxN = 0, syn += endStateEffects(fx, dj, P.nSynopsis, S.endRec + (size_t)chainC * P.S, nSamp, gl, W);
+            }
+#else
             if (__any_sync(kFull, accept && colTouchesEnd))
                 syn += endStateEffects(staleF + nSF, (accept && colTouchesEnd) ? dj : 0, P.nSynopsis, S.endRec + (size_t)chainC * P.S, nSamp,
                                        gl, W);
+#endif
         }
 
         // ---- applyProposal (:322-336)
@@ -846,7 +876,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     if (valid && tail) {
                         const double seg = __dsub_rn(pin, basev);
                         if (lv == 5) atomicAdd(&ch.tier1[u >> 5], seg);
-                        else if (lv == 10) atomicAdd(&ch.tier2[u >> 10], seg);
+                        else if (lv == 10) {
+                            if (t2s) sT2[u >> 10] = __dadd_rn(sT2[u >> 10], seg); else atomicAdd(&ch.tier2[u >> 10], seg);
+                        }
                         else sTop[u >> 15] = __dadd_rn(sTop[u >> 15], seg);
                     }
                 }
@@ -944,6 +976,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
         }
         __syncwarp();
+#if ABM_END_DEFERRED
+        if (kSample && fxN != 0) {
+            const int sgn = fxN < 0 ? -1 : 1;
+            if (gl < abs(fxN))
+                atomicAdd(reinterpret_cast<unsigned long long *>(&S.endRec[(size_t)chainC * P.S + (fxK & 0xffffff)].pend),
+                          (unsigned long long)((long long)(sgn * (fxK >> 24)) * (long long)nSamp));
+            if (gl < P.nSynopsis) syn += sgn * (int)(int8_t)(fxS >> (8 * (gl & 3)));
+            fxN = 0;
+        }
+#endif
         if (kSample) {
             // the do-while at SparseBasisSampler.h:247 hands out the state whenever it is feasible after a step
             if (act && infeas == 0) {
@@ -963,6 +1005,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (chainValid) {
             if (BLK) tier3[k] = sTop[k]; else ch.tier2[(k << P.topShift) >> 10] = sTop[k];
         }
+    if (t2s && chainValid)
+        for (int k = gl; k < P.t2Len; k += W) ch.tier2[k] = sT2[k];
     if (kSample && chainValid) {   // the lazy accumulators are settled by sampleEndKernel
         if (gl < P.nSynopsis) {
             S.synSum[(size_t)chain * P.nSynopsis + gl] += sSyn[gl];
@@ -1159,13 +1203,19 @@ __global__ void setStateKernel(DevProblem P, DevChains S) {
 // PredPreyAgent::consequences, PredPreyAgent.h:98-115) of one agent state from the events of the last timestep (Xl): MOVELEFT
 // from the right neighbour, MOVERIGHT from the left one, MOVEUP from below, MOVEDOWN from above, GIVEBIRTH from the state
 // itself (the parent stays) and from the left neighbour (the child)
-__device__ __forceinline__ int endOccupancy(const int8_t *__restrict__ Xl, int psi, int G) {
+__device__ __forceinline__ int endOccupancy(const int8_t *__restrict__ Xl, int psi, int G, int gShift = -1) {
     const int GG = G * G;
-    const int type = psi / GG, cell = psi - type * GG, cy = cell / G, cx = cell - cy * G, tb = type * GG;
-    const int left = tb + (cx + G - 1) % G + G * cy, right = tb + (cx + 1) % G + G * cy;
-    const int up = tb + cx + G * ((cy + 1) % G), down = tb + cx + G * ((cy + G - 1) % G);
-    return Xl[right * kStateBytes + 1] + Xl[left * kStateBytes + 2] + Xl[down * kStateBytes + 3] + Xl[up * kStateBytes + 4] +
-           Xl[psi * kStateBytes + 5] + Xl[left * kStateBytes + 5];
+    int type, cx, cy;
+    if (gShift >= 0) { type = psi >> (2 * gShift); cy = (psi & (GG - 1)) >> gShift; cx = psi & (G - 1); }
+    else { type = psi / GG; const int cell = psi - type * GG; cy = cell / G; cx = cell - cy * G; }
+    const int tb = type * GG;
+    const int left = tb + (cx == 0 ? G - 1 : cx - 1) + G * cy, right = tb + (cx == G - 1 ? 0 : cx + 1) + G * cy;
+    const int up = tb + cx + G * (cy == G - 1 ? 0 : cy + 1), down = tb + cx + G * (cy == 0 ? G - 1 : cy - 1);
+    // one aligned 64-bit word per agent state: act a is byte a
+    const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(Xl);
+    const unsigned long long wl = X8[left];
+    auto act = [](unsigned long long w, int a) { return (int)(int8_t)(w >> (8 * a)); };
+    return act(X8[right], 1) + act(wl, 2) + act(X8[down], 3) + act(X8[up], 4) + act(X8[psi], 5) + act(wl, 5);
 }
 
 // Before a sampling launch: the synopsis (FiguresForPaper.h:245-263) of every chain's current end state, from which
@@ -1190,16 +1240,18 @@ __global__ void sampleBeginKernel(DevProblem P, DevChains S) {
 
 // After a sampling launch of N samples: a state's occupancy summed over them is occ_end * N - sum over its changes of
 // (change * index of the first sample that saw it); the second term was accumulated by the step kernel.
-__global__ void sampleEndKernel(DevProblem P, DevChains S) {
-    const int chain = blockIdx.y;
+__global__ void sampleEndKernel(DevProblem P, DevChains S) {   // one CTA per chain
+    const int chain = blockIdx.x;
     const long long nSamp = S.launchSamples[chain];
     const int8_t *Xl = S.Xb + (size_t)chain * P.xStride + (size_t)(P.T - 1) * P.S * kStateBytes;
-    for (int psi = blockIdx.x * blockDim.x + threadIdx.x; psi < P.S; psi += gridDim.x * blockDim.x) {
-        EndRec &e = S.endRec[(size_t)chain * P.S + psi];
-        e.acc += (long long)endOccupancy(Xl, psi, P.G) * nSamp - e.pend;
-        e.pend = 0;
+    longlong2 *rec = reinterpret_cast<longlong2 *>(S.endRec + (size_t)chain * P.S);   // {acc, pend}
+    for (int psi = threadIdx.x; psi < P.S; psi += blockDim.x) {
+        longlong2 e = rec[psi];
+        e.x += (long long)endOccupancy(Xl, psi, P.G, P.gShift) * nSamp - e.y;
+        e.y = 0;
+        rec[psi] = e;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) S.nSamples[chain] += nSamp;
+    if (threadIdx.x == 0) S.nSamples[chain] += nSamp;
 }
 
 // Blocked sum tree, before every launch: the two upper levels are recomputed from the level below (sums of 32 entries,

@@ -191,6 +191,23 @@ class SparseBasisSampler:
                                                      _ptr(ns, C.c_int64), 0))
         return end, ss, sq, ns
 
+    def enqueue_statistics(self):
+        """Orders the statistics read-back after everything launched so far and returns (abm_chains_enqueue_statistics);
+        launches issued afterwards keep running while `wait_statistics` collects it."""
+        check(_capi.load().abm_chains_enqueue_statistics(self.h))
+
+    def wait_statistics(self):
+        """(end_state_sum, syn_sum, syn_sumsq, n_samples, counters[n_chains][8]) of the last `enqueue_statistics`."""
+        P = self.problem
+        end = np.zeros(2 * P.grid_size ** 2, np.int64)
+        ss = np.zeros((self.n_chains, P.n_synopsis), np.int64)
+        sq = np.zeros((self.n_chains, P.n_synopsis), np.int64)
+        ns = np.zeros(self.n_chains, np.int64)
+        cnt = np.zeros((self.n_chains, 8), np.int64)
+        check(_capi.load().abm_chains_wait_statistics(self.h, _ptr(end, C.c_int64), _ptr(ss, C.c_int64), _ptr(sq, C.c_int64),
+                                                      _ptr(ns, C.c_int64), _ptr(cnt, C.c_int64)))
+        return end, ss, sq, ns, cnt
+
     def statistics_into(self, end_ptr: int, syn_sum_ptr: int, syn_sumsq_ptr: int, n_samples_ptr: int):
         """Same, into DEVICE buffers (raw pointers, e.g. torch tensors' data_ptr()) for an NCCL all-reduce."""
         vp = lambda p: C.cast(C.c_void_p(p), C.POINTER(C.c_int64)) if p else None

@@ -221,12 +221,16 @@ def bench_ours(args):
     t0 = time.perf_counter()
     d2h = 0
     summary = None
+    # launch k+1 is queued behind the read-back of launch k, so the device never waits for the host: stream order is
+    # sample 0, read-back 0, sample 1, read-back 1, ...; the host collects read-back k while sample k+1 runs
     smp.sample(10 ** 12, max_steps=mh)          # mh Metropolis steps per chain, statistics of every feasible state
+    smp.enqueue_statistics()                    # ensemble reduction + device -> pinned host copies, asynchronous
     for k in range(args.steps):
-        end, ss, sq, ns = smp.statistics()      # device -> host buffers (waits for launch k)
-        c = smp.counters()
-        if k + 1 < args.steps:                  # launch k+1 runs while the host reduces the statistics of launch k
+        if k + 1 < args.steps:
             smp.sample(10 ** 12, max_steps=mh)
+        end, ss, sq, ns, c = smp.wait_statistics()   # statistics and counters after launch k, in host buffers
+        if k + 1 < args.steps:
+            smp.enqueue_statistics()
         d2h = end.nbytes + ss.nbytes + sq.nbytes + ns.nbytes + c.nbytes
         packed = E.pack_local(end, ss, sq, ns, c)
         if world > 1:
@@ -301,15 +305,15 @@ def bench_ours(args):
                          "algorithmic_bytes_per_chain_step": bytes_per_step, "kernel": "abm::stepKernel<MODE_MCMC>",
                          "kernel_ms_per_launch": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
-                    "what": "abm_chains_sample (steps + on-device end-state/synopsis statistics) + abm_chains_get_statistics + "
-                            "abm_chains_get_counters into host buffers + ensemble all-reduce, host clock, every step; the next launch is "
-                            "issued before the host reduces the statistics just read; inputs of a step are "
-                            "kernel arguments only (the problem and the chain states are uploaded once, at construction)"},
+                    "what": "abm_chains_sample (steps + on-device end-state/synopsis statistics) + abm_chains_enqueue_statistics / "
+                            "abm_chains_wait_statistics (ensemble reduction, statistics and counters into host buffers) + ensemble "
+                            "all-reduce, host clock, every step; launch k+1 is queued behind the read-back of launch k; inputs of a "
+                            "step are kernel arguments only (the problem and the chain states are uploaded once, at construction)"},
             "ensemble": {"chains": summary.n_chains, "feasible_samples": summary.n_samples,
                          "mean_agents_at_T": float(summary.end_state_mean.sum()),
                          "rhat_synopsis": [round(float(x), 4) for x in summary.rhat]},
             "ess": ess,
-            # per bench step: refreshBlockedTopKernel (0.16 ms) + stepKernel<MODE_MCMC> (profiles/*_bench_launches.csv)
+            # per bench step of the timed region: refreshBlockedTopKernel (0.16 ms) + stepKernel<MODE_MCMC> (profiles/*_bench_launches.csv)
             "gpu_launches": 2 * args.steps,
             "clocks": clocks.summary(),
         }

@@ -166,6 +166,13 @@ ABM_API int abm_chains_get_trajectories(abm_chains *c, int8_t *events);
  * chains' device, so a caller can hand them to an NCCL all-reduce without a host round trip). */
 ABM_API int abm_chains_get_statistics(abm_chains *c, int64_t *end_state_sum, int64_t *syn_sum, int64_t *syn_sumsq,
                                       int64_t *n_samples, int device_ptrs);
+/* The same read-back without stalling the stream (FiguresForPaper.h:93-104 drains its statistics while the sampler thread
+ * keeps running): enqueue orders the ensemble reduction and the copies (into pinned staging owned by the handle) after
+ * everything launched so far and returns; launches issued afterwards run on.  wait blocks until those copies have landed and
+ * fills the caller's HOST buffers (any may be NULL); counters as abm_chains_get_counters.  One enqueue may be pending. */
+ABM_API int abm_chains_enqueue_statistics(abm_chains *c);
+ABM_API int abm_chains_wait_statistics(abm_chains *c, int64_t *end_state_sum, int64_t *syn_sum, int64_t *syn_sumsq,
+                                       int64_t *n_samples, abm_mcmc_counters *per_chain_counters);
 ABM_API int abm_chains_reset_statistics(abm_chains *c);
 /* Optional thinned time series of the synopsis statistics (what `save(firstSynopsisSamples)` keeps, FiguresForPaper.h:96),
  * for the first n_chains chains: every `thin`-th feasible sample, at most `capacity` per chain.  The series feeds the

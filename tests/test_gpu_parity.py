@@ -174,6 +174,15 @@ def test_sample_statistics_match_oracle():
         if c < 4:
             assert np.array_equal(series[c], ser[:, :nsyn])
     assert np.array_equal(end, o_end)
+    # the non-blocking read-back returns the same numbers (and the counters) while a later launch is already queued
+    cnt = smp.counters()
+    smp.enqueue_statistics()
+    smp.step(50)
+    end2, ss2, sq2, ns2, cnt2 = smp.wait_statistics()
+    assert np.array_equal(end2, end) and np.array_equal(ss2, ss) and np.array_equal(sq2, sq) and np.array_equal(ns2, ns)
+    assert np.array_equal(cnt2, cnt)
+    with pytest.raises(S.AbmError):
+        smp.wait_statistics()          # nothing pending any more
     smp.reset_statistics()
     end, ss, sq, ns = smp.statistics()
     assert end.sum() == 0 and ss.sum() == 0 and ns.sum() == 0
