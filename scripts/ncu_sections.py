@@ -17,7 +17,7 @@ def find(pat):
     raise KeyError(pat)
 
 
-marks = [("rng", find("for (long long s = 0")), ("descent", find("column draw")), ("record+rows", find("Proposal::Proposal (:288")),
+marks = [("rng", find("for (long long s = 0")), ("descent", find("---- column draw")), ("record+rows", find("Proposal::Proposal (:288")),
          ("columns: prefetch", find("coupled columns, one per lane")), ("importance", find("auto importance = [&]")),
          ("columns: chunks", find("double csLane = 0.0")), ("ratio/accept", find("calcRatioOfSums (:276")),
          ("apply X/delta", find("applyProposal (:322")), ("commit", find("const int Ca = accept")),
