@@ -149,6 +149,12 @@ public:
     void step(int64_t nSteps) { detail::check(abm_chains_step(chains_, nSteps), "abm_chains_step"); }
     void sample(int64_t nSamples, int64_t maxSteps = 0) { detail::check(abm_chains_sample(chains_, nSamples, maxSteps), "abm_chains_sample"); }
     void synchronize() { detail::check(abm_chains_synchronize(chains_), "abm_chains_synchronize"); }
+    // statistics of the batched chains without stalling them (what the statistics thread of FiguresForPaper.h:86-104 does beside
+    // the sampler thread): enqueue after a sample() call, keep launching, collect with waitStatistics (any pointer may be null)
+    void enqueueStatistics() { detail::check(abm_chains_enqueue_statistics(chains_), "abm_chains_enqueue_statistics"); }
+    void waitStatistics(int64_t *endStateSum, int64_t *synSum, int64_t *synSumSq, int64_t *nSamples, abm_mcmc_counters *counters) {
+        detail::check(abm_chains_wait_statistics(chains_, endStateSum, synSum, synSumSq, nSamples, counters), "abm_chains_wait_statistics");
+    }
     abm_chains *chains() { return chains_; }
     abm_problem *problem() { return problem_; }
 

@@ -46,6 +46,13 @@ int run(int T, int nSamples) {
     gpu.batched(64, 99);
     gpu.step(2000);
     gpu.sample(50);
+    gpu.enqueueStatistics();           // read-back queued behind the sample launch ...
+    gpu.sample(1);                     // ... while the chains move on (and stop at a feasible state again)
+    std::vector<int64_t> nSamp(64);
+    std::vector<abm_mcmc_counters> cnt(64);
+    gpu.waitStatistics(nullptr, nullptr, nullptr, nSamp.data(), cnt.data());
+    for (int c = 0; c < 64; ++c)
+        if (nSamp[c] != 50) { printf("FAIL: chain %d reports %lld samples\n", c, (long long)nSamp[c]); return 1; }
     gpu.synchronize();
     std::vector<int8_t> ev(size_t(64) * T * PredPreyAgent<G>::domainSize() * 6);
     abmcmc::detail::check(abm_chains_get_trajectories(gpu.chains(), ev.data()), "get_trajectories");
