@@ -1,4 +1,5 @@
+# Development aid: one GPU session = the GPU test suite, the smoke check and a pass over every kernel mode.
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:stepKernelILi3E -s 1 -c 1 \
-    -f -o gpurun_out/prof_r1d_sample python scripts/probe_sample_only.py pp16-8 8192 100 > gpurun_out/r1d_ncu_sample.log 2>&1
-tail -2 gpurun_out/r1d_ncu_sample.log
+( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ) > gpurun_out/final_tests.log 2>&1; tail -2 gpurun_out/final_tests.log
+python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -1
+timeout 200 python scripts/mode_sweep_probe.py 2>&1 | tail -7
