@@ -45,6 +45,12 @@ def main():
         subprocess.run([str(REF), "gen", str(g), str(t), "1234", "10.0", str(raw), "0.05", "0.05", "0.05", "1.0", "poisson"], check=True,
                        stdout=subprocess.DEVNULL)
         xz(raw, HERE / f"pp{g}-{t}-poisson.abmp.xz")
+    # posterior.constraints of the problems, as the reference assembles them: the input of TableauNormMinimiser, against whose
+    # tableau (in the problem fixtures) the own basis builder is checked (tests/test_basis_builder.py)
+    for name in ["pp8-4", "pp16-8", "pp16-8-poisson"] + (["pp32-16"] if with32 else []):
+        craw = tmp / f"constraints_{name}.abmp"
+        subprocess.run([str(REF), "constraints", str(tmp / f"{name}.abmp"), str(craw), "0"], check=True)
+        xz(craw, HERE / f"constraints_{name}.abmp.xz")
     # (problem, initSeed, chainSeed, nSteps, checkpointEvery)
     traces = [("pp8-4", 11, 101, 20000, 500), ("pp8-4", 12, 102, 20000, 500), ("pp16-8", 12, 202, 20000, 500),
               ("pp8-4-poisson", 11, 103, 20000, 500)]
@@ -74,6 +80,9 @@ def main():
         subprocess.run([str(REF), "experiment3", str(raw), str(marg), "500000", "10000", "2000000", "4321"], check=True)
         xz(raw, HERE / "exp_pp3-2-single.abmp.xz")
         xz(marg, HERE / "exp_pp3-2-single_means.abmp.xz")
+        craw = tmp / "constraints_exp_pp3-2-single.abmp"
+        subprocess.run([str(REF), "constraints", str(raw), str(craw), "0"], check=True)
+        xz(craw, HERE / "constraints_exp_pp3-2-single.abmp.xz")
         traw = tmp / "trace_exp_pp3-2-single_301.abmp"
         subprocess.run([str(REF), "trace", str(raw), "31", "301", "20000", "500", str(traw)], check=True)
         xz(traw, HERE / "trace_exp_pp3-2-single_301.abmp.xz")

@@ -14,7 +14,8 @@ from conftest import load_golden
 KEYS = ("dims", "tab_L", "tab_U", "tab_F", "col_basic", "nb_col", "nb_ptr", "nb_row", "nb_val")
 
 
-@pytest.mark.parametrize("name", ["pp8-4", "pp16-8", "pp16-8-poisson", "pp32-16"])
+# exp_pp3-2-single: the reference's validation experiment (Experiments.cpp:49-65); its tableau has an entry of magnitude 2
+@pytest.mark.parametrize("name", ["pp8-4", "pp16-8", "pp16-8-poisson", "pp32-16", "exp_pp3-2-single"])
 def test_basis_equals_reference_tableau(name):
     from agentbasedmcmc_b200 import basis
     c, p = load_golden(f"constraints_{name}.abmp.xz"), load_golden(f"{name}.abmp.xz")
@@ -24,7 +25,8 @@ def test_basis_equals_reference_tableau(name):
     for k in KEYS:
         assert np.array_equal(b[k], p[k]), k
     # the reference needed gen_seconds for the whole problem (dominated by TableauNormMinimiser: 211-320 s at 32x32x16)
-    assert dt < max(5.0, 0.1 * float(p["gen_seconds"][0]))
+    if "gen_seconds" in p:
+        assert dt < max(5.0, 0.1 * float(p["gen_seconds"][0]))
     # structure of the result: every equality row reduced (its basic variable is a column), one auxiliary per inequality
     basic_rows = b["basis"][(b["tab_L"] == b["tab_U"])]
     assert np.all(basic_rows >= 0) and np.all(basic_rows < b["dims"][1]) and np.unique(basic_rows).size == basic_rows.size
