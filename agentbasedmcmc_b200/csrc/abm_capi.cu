@@ -618,6 +618,11 @@ static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
     const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs, P.nodeCap, P.t2Cap);
     cudaError_t e = cudaFuncSetAttribute(stepKernel<MODE, W, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
+    static const int carveout = getenv("ABM_SMEM_CARVEOUT") ? atoi(getenv("ABM_SMEM_CARVEOUT")) : -1;   // measurement switch: percent of
+    if (carveout >= 0) {                                                                              // the L1/shared array given to shared memory
+        e = cudaFuncSetAttribute(stepKernel<MODE, W, BLK>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        if (e != cudaSuccess) return e;
+    }
     stepKernel<MODE, W, BLK><<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);
     return cudaGetLastError();
 }
