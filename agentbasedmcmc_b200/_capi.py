@@ -14,7 +14,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / os.environ.get("ABM_LIB", "libabmcmc_b200.so")
 
 SYMBOLS = [
-    "abm_last_error", "abm_version", "abm_device_count", "abm_problem_create", "abm_problem_destroy",
+    "abm_last_error", "abm_version", "abm_device_count", "abm_problem_create", "abm_problem_validate", "abm_problem_destroy",
     "abm_problem_get_info", "abm_problem_n_synopsis", "abm_chains_create", "abm_chains_destroy", "abm_chains_init",
     "abm_chains_init_from_prior", "abm_chains_find_feasible", "abm_chains_step", "abm_chains_step_traced", "abm_chains_sample",
     "abm_chains_synchronize", "abm_chains_get_state", "abm_chains_get_counters", "abm_chains_get_infeasibility",
@@ -65,6 +65,7 @@ def load():
     i8p, i32p, i64p, u8p, f64p = (C.POINTER(t) for t in (C.c_int8, C.c_int32, C.c_int64, C.c_uint8, C.c_double))
     L.abm_last_error.restype = C.c_char_p
     L.abm_problem_create.argtypes = [C.POINTER(ProblemDesc), C.c_int, vpp]
+    L.abm_problem_validate.argtypes = [C.POINTER(ProblemDesc), C.POINTER(ProblemInfo)]
     L.abm_problem_destroy.argtypes = [vp]
     L.abm_problem_get_info.argtypes = [vp, C.POINTER(ProblemInfo)]
     L.abm_problem_n_synopsis.argtypes = [vp]

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -119,12 +120,15 @@ int abm_device_count(void) {
 }
 
 // ------------------------------------------------------------------------------------------------
-int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **out) {
-    if (!desc || !out) return fail(ABM_ERR_INVALID, "null argument");
-    *out = nullptr;
-    if (abm_device_count() <= device || device < 0) return fail(ABM_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");
-    CUDA_TRY(cudaSetDevice(device));
-    if (const char *e = getenv("ABM_L2_FETCH")) CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(e))));   // experiment: 32 / 64 / 128
+// hostOnly != null: the host half only (validation, record layout, sizes) -- abm_problem_validate; nothing touches a device
+static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_problem **out, abm_problem_info *hostOnly) {
+    if (!desc || (!out && !hostOnly)) return fail(ABM_ERR_INVALID, "null argument");
+    if (out) *out = nullptr;
+    if (!hostOnly) {
+        if (abm_device_count() <= device || device < 0) return fail(ABM_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");
+        CUDA_TRY(cudaSetDevice(device));
+        if (const char *e = getenv("ABM_L2_FETCH")) CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(e))));   // experiment: 32 / 64 / 128
+    }
     const int nTab = desc->n_tab_rows, nCols = desc->n_nonbasic;
     if (nTab <= 0 || nCols <= 0) return fail(ABM_ERR_INVALID, "empty problem");
 
@@ -399,7 +403,8 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
             }
     }
 
-    abm_problem *p = new abm_problem();
+    std::unique_ptr<abm_problem> owner(new abm_problem());
+    abm_problem *p = owner.get();
     p->device = device;
     p->xoff = xoff;
     DevProblem &d = p->d;
@@ -449,23 +454,37 @@ int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **o
     d.nSynopsis = nSyn;
     d.kappa = desc->kappa;
     std::vector<int32_t> colEvent(desc->nb_col, desc->nb_col + nCols);
+    abm_problem_info &inf = p->info;
+    inf.n_rows = nRows; inf.n_cols = nCols; inf.nnz = nnz; inf.n_events = nEvents;
+    inf.max_col_nnz = maxColNnz; inf.max_coupled = maxCoupled; inf.tree_depth = depth; inf.n_states = nStates;
+    inf.chain_state_bytes = int64_t(xStride) + int64_t(nCols) * 17 + int64_t(d.t1Len + d.t2Len) * 8 + int64_t(d.sCap) * 16;
+    if (hostOnly) {   // what the uploads below would occupy
+        auto bytes = [](const auto &v) { return int64_t(v.size() * sizeof(v[0])); };
+        inf.shared_bytes = bytes(recIdx) + bytes(rec) + bytes(facVal) + bytes(impTab) + bytes(colPtr) + bytes(colRow) + bytes(colVal) +
+                           bytes(rowPtr) + bytes(rowCol) + bytes(rowVal) + bytes(rowF) + bytes(rowParam) + bytes(colEvent);
+        *hostOnly = inf;
+        return ABM_OK;
+    }
     cudaError_t e = cudaSuccess;
     auto up = [&](auto **dst, const auto &v) { if (e == cudaSuccess) e = p->arena.upload(dst, v); };
     up(&d.recIdx, recIdx); up(&d.rec, rec); up(&d.facVal, facVal); up(&d.impTab, impTab);
     up(&d.colPtr, colPtr); up(&d.colRow, colRow); up(&d.colVal, colVal);
     up(&d.rowPtr, rowPtr); up(&d.rowCol, rowCol); up(&d.rowVal, rowVal);
     up(&d.rowF, rowF); up(&d.rowParam, rowParam); up(&d.colEvent, colEvent);
-    if (e != cudaSuccess) {
-        delete p;
-        return fail(ABM_ERR_CUDA, std::string("problem upload: ") + cudaGetErrorString(e));
-    }
-    abm_problem_info &inf = p->info;
-    inf.n_rows = nRows; inf.n_cols = nCols; inf.nnz = nnz; inf.n_events = nEvents;
-    inf.max_col_nnz = maxColNnz; inf.max_coupled = maxCoupled; inf.tree_depth = depth; inf.n_states = nStates;
-    inf.chain_state_bytes = int64_t(xStride) + int64_t(nCols) * 17 + int64_t(d.t1Len + d.t2Len) * 8 + int64_t(d.sCap) * 16;
+    if (e != cudaSuccess) return fail(ABM_ERR_CUDA, std::string("problem upload: ") + cudaGetErrorString(e));
     inf.shared_bytes = int64_t(p->arena.bytes);
-    *out = p;
+    *out = owner.release();
     return ABM_OK;
+}
+
+int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **out) {
+    if (!out) return fail(ABM_ERR_INVALID, "null argument");
+    return problemCreateImpl(desc, device, out, nullptr);
+}
+
+int abm_problem_validate(const abm_problem_desc *desc, abm_problem_info *info) {
+    if (!info) return fail(ABM_ERR_INVALID, "null argument");
+    return problemCreateImpl(desc, 0, nullptr, info);
 }
 
 int abm_problem_destroy(abm_problem *p) {

@@ -19,6 +19,38 @@ def _ptr(a, ct):
     return None if a is None else a.ctypes.data_as(C.POINTER(ct))
 
 
+def _problem_desc(abmp: dict, with_importance: bool = True, sum_tree: str = "blocked"):
+    """abm_problem_desc of an ABMP dict (and the arrays it points into, which must outlive the call that uses it)."""
+    k = {}
+    for name in ("tab_L", "tab_U", "tab_F", "nb_col", "nb_ptr", "nb_row", "nb_val", "fac_id", "ut_lo", "ut_off"):
+        k[name] = np.ascontiguousarray(abmp[name], dtype=np.int32)
+    for name in ("ut_val", "imp_lgamma", "imp_logratio"):
+        k[name] = np.ascontiguousarray(abmp.get(name, np.zeros(24)), dtype=np.float64)
+    d = ProblemDesc()
+    d.n_tab_rows, d.n_nonbasic = int(abmp["dims"][0]), int(abmp["dims"][3])
+    for name in ("tab_L", "tab_U", "tab_F", "nb_col", "nb_ptr", "nb_row", "nb_val", "fac_id", "ut_lo", "ut_off"):
+        setattr(d, name, _ptr(k[name], C.c_int32))
+    d.n_tables = k["ut_lo"].size
+    d.ut_val = _ptr(k["ut_val"], C.c_double)
+    d.kappa = float(abmp["kappa"][0])
+    use_imp = with_importance and "pp_meta" in abmp
+    d.grid_size = int(abmp["pp_meta"][0]) if use_imp else 0
+    d.n_timesteps = int(abmp["pp_meta"][1]) if use_imp else 0
+    d.imp_lgamma = _ptr(k["imp_lgamma"], C.c_double)
+    d.imp_logratio = _ptr(k["imp_logratio"], C.c_double)
+    d.sum_tree = {"blocked": 0, "reference": 1}[sum_tree]
+    return d, k
+
+
+def validate_problem(abmp: dict, with_importance: bool = True, sum_tree: str = "blocked") -> ProblemInfo:
+    """The host half of `Problem(...)` alone (abm_problem_validate): every check and the sizes, no device needed."""
+    d, keep = _problem_desc(abmp, with_importance, sum_tree)
+    info = ProblemInfo()
+    check(_capi.load().abm_problem_validate(C.byref(d), C.byref(info)))
+    del keep
+    return info
+
+
 class Problem:
     """Shared read-only structure of a sampler (tableau, bounds, factor tables, importance tables) on one GPU.
 
@@ -32,24 +64,7 @@ class Problem:
         L = _capi.load()
         self.abmp = abmp
         self.device = device
-        k = {}
-        for name in ("tab_L", "tab_U", "tab_F", "nb_col", "nb_ptr", "nb_row", "nb_val", "fac_id", "ut_lo", "ut_off"):
-            k[name] = np.ascontiguousarray(abmp[name], dtype=np.int32)
-        for name in ("ut_val", "imp_lgamma", "imp_logratio"):
-            k[name] = np.ascontiguousarray(abmp.get(name, np.zeros(24)), dtype=np.float64)
-        d = ProblemDesc()
-        d.n_tab_rows, d.n_nonbasic = int(abmp["dims"][0]), int(abmp["dims"][3])
-        for name in ("tab_L", "tab_U", "tab_F", "nb_col", "nb_ptr", "nb_row", "nb_val", "fac_id", "ut_lo", "ut_off"):
-            setattr(d, name, _ptr(k[name], C.c_int32))
-        d.n_tables = k["ut_lo"].size
-        d.ut_val = _ptr(k["ut_val"], C.c_double)
-        d.kappa = float(abmp["kappa"][0])
-        use_imp = with_importance and "pp_meta" in abmp
-        d.grid_size = int(abmp["pp_meta"][0]) if use_imp else 0
-        d.n_timesteps = int(abmp["pp_meta"][1]) if use_imp else 0
-        d.imp_lgamma = _ptr(k["imp_lgamma"], C.c_double)
-        d.imp_logratio = _ptr(k["imp_logratio"], C.c_double)
-        d.sum_tree = {"blocked": 0, "reference": 1}[sum_tree]
+        d, self._keep = _problem_desc(abmp, with_importance, sum_tree)
         self.sum_tree = sum_tree
         h = C.c_void_p()
         check(L.abm_problem_create(C.byref(d), device, C.byref(h)))

@@ -95,6 +95,10 @@ ABM_API int abm_device_count(void); /* 0 when no CUDA device is usable */
 /* ---- problem: replaces the tableau-copy half of SparseBasisSampler::SparseBasisSampler (:121-158) */
 ABM_API int abm_problem_create(const abm_problem_desc *desc, int device, abm_problem **out);
 ABM_API int abm_problem_destroy(abm_problem *p);
+/* The host half of abm_problem_create alone -- every check (entry magnitudes, int8 row ranges, factor-table coverage, record
+ * limits) and the sizes it would allocate -- without touching a device: a host program can reject a problem, or size its
+ * chain count for the memory of a GPU (info->chain_state_bytes), before it owns one. */
+ABM_API int abm_problem_validate(const abm_problem_desc *desc, abm_problem_info *info);
 ABM_API int abm_problem_get_info(const abm_problem *p, abm_problem_info *info);
 
 /* ---- chains: n_chains independent samplers; chain c draws from the Philox4x32-10 stream keyed by
