@@ -64,3 +64,27 @@ def test_basis_rejects_bad_input():
         basis.minimise([0, 1], [-3], [1], [0], [0])
     with pytest.raises(AbmError):   # an equality whose only coefficient is not a unit: no admissible pivot
         basis.minimise([0, 1], [0], [2], [4], [4])
+
+
+@pytest.mark.parametrize("grid,T,seed,start", [(3, 2, 1, "bernoulli"), (3, 3, 2, "poisson"), (4, 3, 3, "bernoulli"), (4, 4, 4, "poisson"),
+                                               (8, 2, 5, "bernoulli"), (8, 3, 6, "poisson"), (8, 4, 7, "bernoulli"), (16, 2, 8, "poisson")])
+def test_basis_equals_reference_on_fresh_problems(grid, T, seed, start, tmp_path):
+    """Differential run against the unmodified reference on problems that are not fixtures: the reference's generator
+    (`abm_ref gen`: PredPreyProblem's constructor, other seeds, grids, horizons and both start states) builds the problem and
+    its tableau; the own builder must reproduce that tableau from the exported constraints, entry for entry."""
+    import subprocess
+    from pathlib import Path
+    from agentbasedmcmc_b200 import basis
+    from agentbasedmcmc_b200.abmp import read_abmp
+    ref = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "abm_ref"
+    if not ref.exists():
+        pytest.skip("oracle/_ref/abm_ref not built (needs /root/reference at build time)")
+    prob, cons = tmp_path / "p.abmp", tmp_path / "c.abmp"
+    dens = "0.1" if grid <= 4 else "0.05"
+    subprocess.run([str(ref), "gen", str(grid), str(T), str(seed), "10.0", str(prob), dens, dens, "0.1", "1.0", start], check=True,
+                   capture_output=True, timeout=600)
+    subprocess.run([str(ref), "constraints", str(prob), str(cons), "0"], check=True, capture_output=True, timeout=600)
+    p, c = read_abmp(prob), read_abmp(cons)
+    b = basis.minimise(c["con_ptr"], c["con_idx"], c["con_val"], c["con_lower"], c["con_upper"])
+    for k in KEYS:
+        assert np.array_equal(b[k], p[k]), k

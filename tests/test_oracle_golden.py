@@ -33,7 +33,31 @@ def hash_X(X):
 
 @pytest.mark.parametrize("prob,trace", TRACES)
 def test_oracle_matches_reference_trace(prob, trace):
-    p, t = load_golden(prob), load_golden(trace)
+    check_trace(load_golden(prob), load_golden(trace))
+
+
+@pytest.mark.parametrize("grid,T,seed,start", [(3, 2, 21, "poisson"), (4, 3, 22, "bernoulli"), (8, 3, 23, "poisson"), (8, 5, 24, "bernoulli"),
+                                               (16, 3, 25, "bernoulli")])
+def test_oracle_matches_reference_on_fresh_problems(grid, T, seed, start, tmp_path):
+    """Differential run on problems that are not fixtures: `abm_ref gen` (the reference's PredPreyProblem constructor) and
+    `abm_ref trace` (the unmodified sampler, step by step) with other seeds, grids, horizons and both start states; the
+    oracle must reproduce the trace bit for bit, doubles included."""
+    import subprocess
+    from pathlib import Path
+    from agentbasedmcmc_b200.abmp import read_abmp
+    ref = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "abm_ref"
+    if not ref.exists():
+        pytest.skip("oracle/_ref/abm_ref not built (needs /root/reference at build time)")
+    prob, trace = tmp_path / "p.abmp", tmp_path / "t.abmp"
+    dens = "0.1" if grid <= 4 else "0.05"
+    subprocess.run([str(ref), "gen", str(grid), str(T), str(seed), "10.0", str(prob), dens, dens, "0.1", "1.0", start], check=True,
+                   capture_output=True, timeout=600)
+    subprocess.run([str(ref), "trace", str(prob), str(seed + 100), str(seed + 200), "4000", "500", str(trace)], check=True,
+                   capture_output=True, timeout=600)
+    check_trace(read_abmp(prob), read_abmp(trace))
+
+
+def check_trace(p, t):
     P = OracleProblem(p)
     c = OracleChain(P, t["init_state"])
     c.seed_mt(int(t["seeds"][1]))
