@@ -32,3 +32,12 @@ def test_ours_arm_fails_loudly_without_a_device():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
     assert out.returncode != 0
     assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_reference_arm_runs_on_rank_zero_only():
+    """Under torchrun (N > 1) rank 0 alone runs and prints the reference line; the other ranks exit 0 without work."""
+    import os
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "pp8-4"], env=env,
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
