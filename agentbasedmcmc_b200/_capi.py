@@ -20,8 +20,13 @@ SYMBOLS = [
     "abm_chains_synchronize", "abm_chains_get_state", "abm_chains_get_counters", "abm_chains_get_infeasibility",
     "abm_chains_get_trajectories", "abm_chains_get_statistics", "abm_chains_enqueue_statistics", "abm_chains_wait_statistics", "abm_chains_reset_statistics",
     "abm_chains_record_series", "abm_chains_get_series",
+    "abm_chains_sample_injected", "abm_comm_unique_id", "abm_comm_create", "abm_comm_from_nccl", "abm_comm_destroy",
+    "abm_chains_get_moments", "abm_chains_allreduce_moments", "abm_chains_enqueue_moments", "abm_chains_wait_moments",
     "abm_chains_last_launch_ms", "abm_basis_minimise", "abm_basis_destroy", "abm_basis_get_dims", "abm_basis_get", "abm_basis_get_rows",
 ]
+
+
+MOMENTS_EXACT_HEAD, MOMENTS_REAL, COMM_ID_BYTES = 26, 24, 128   # ABM_MOMENTS_EXACT_HEAD, ABM_MOMENTS_REAL, ABM_COMM_ID_BYTES
 
 
 class AbmError(RuntimeError):
@@ -89,6 +94,15 @@ def load():
     L.abm_chains_record_series.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.abm_chains_get_series.argtypes = [vp, i32p]
     L.abm_chains_last_launch_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.abm_chains_sample_injected.argtypes = [vp, C.c_int64, f64p]
+    L.abm_comm_unique_id.argtypes = [u8p]
+    L.abm_comm_create.argtypes = [C.c_int32, C.c_int32, u8p, C.c_int, vpp]
+    L.abm_comm_from_nccl.argtypes = [vp, vpp]
+    L.abm_comm_destroy.argtypes = [vp]
+    L.abm_chains_get_moments.argtypes = [vp, i64p, f64p]
+    L.abm_chains_allreduce_moments.argtypes = [vp, vp, i64p, f64p]
+    L.abm_chains_enqueue_moments.argtypes = [vp, vp]
+    L.abm_chains_wait_moments.argtypes = [vp, i64p, f64p]
     L.abm_basis_minimise.argtypes = [C.c_int32, i32p, i32p, i32p, i32p, i32p, vpp]
     L.abm_basis_destroy.argtypes = [vp]
     L.abm_basis_get_dims.argtypes = [vp, i32p, i32p, i32p, i32p, i64p, i64p]

@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -94,6 +96,12 @@ struct abm_chains {
     size_t stageWords = 0;
     cudaEvent_t evStats = nullptr;
     bool statsPending = false;
+    // abm_chains_enqueue_moments / abm_chains_wait_moments
+    long long *momExact = nullptr;   // device [kMomExactHead + S]; d.endStateSum points at its tail
+    double *momReal = nullptr;       // device [kMomReal]
+    int64_t *momStage = nullptr;     // pinned: exact, then real
+    cudaEvent_t evMom = nullptr;
+    bool momPending = false;
 };
 
 // CUDA events on the chains' stream around a step kernel, so a caller can time the kernel itself
@@ -119,6 +127,18 @@ int abm_device_count(void) {
     return n;
 }
 
+// HBM bytes abm_chains_create allocates per chain (same expressions)
+static int64_t chainStateBytes(const DevProblem &P) {
+    const int64_t ns = std::max(P.nSynopsis, 1), S = std::max(P.S, 1);
+    return int64_t(P.xStride)                                   // Xb
+           + int64_t(P.nCols) * (sizeof(double2) + 1)            // colRec, delta
+           + int64_t(P.t1Len + P.t2Len + 32) * sizeof(double)    // tier1, tier2, tier3
+           + int64_t(P.sCap) * sizeof(double2)                   // scratch
+           + 8 + 4 + 8 + 8 * 8                                   // logImp, infeas, iter, counters
+           + ns * (8 + 8 + 4) + 8 + 8                            // synSum, synSumSq, synNow, nSamples, launchSamples
+           + S * int64_t(sizeof(EndRec));                        // endRec
+}
+
 // ------------------------------------------------------------------------------------------------
 // hostOnly != null: the host half only (validation, record layout, sizes) -- abm_problem_validate; nothing touches a device
 static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_problem **out, abm_problem_info *hostOnly) {
@@ -131,6 +151,17 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     }
     const int nTab = desc->n_tab_rows, nCols = desc->n_nonbasic;
     if (nTab <= 0 || nCols <= 0) return fail(ABM_ERR_INVALID, "empty problem");
+    if (!desc->tab_L || !desc->tab_U || !desc->tab_F || !desc->nb_col || !desc->nb_ptr || !desc->fac_id || !desc->ut_lo ||
+        !desc->ut_off || !desc->ut_val)
+        return fail(ABM_ERR_INVALID, "null array in the problem description");
+    if (desc->nb_ptr[0] != 0) return fail(ABM_ERR_INVALID, "nb_ptr must start at 0");
+    for (int j = 0; j < nCols; ++j)
+        if (desc->nb_ptr[j + 1] < desc->nb_ptr[j]) return fail(ABM_ERR_INVALID, "nb_ptr must be non-decreasing");
+    if (desc->nb_ptr[nCols] > 0 && (!desc->nb_row || !desc->nb_val)) return fail(ABM_ERR_INVALID, "null array in the problem description");
+    if (desc->n_tables <= 0) return fail(ABM_ERR_INVALID, "no factor tables");
+    if (desc->ut_off[0] != 0) return fail(ABM_ERR_INVALID, "ut_off must start at 0");
+    for (int k = 0; k < desc->n_tables; ++k)
+        if (desc->ut_off[k + 1] <= desc->ut_off[k]) return fail(ABM_ERR_INVALID, "ut_off must be increasing (no empty factor table)");
 
     // sampler rows = tableau rows that are not equalities, in order (SparseBasisSampler.h:128-140)
     std::vector<int32_t> rowOf(nTab, -1);
@@ -457,7 +488,7 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     abm_problem_info &inf = p->info;
     inf.n_rows = nRows; inf.n_cols = nCols; inf.nnz = nnz; inf.n_events = nEvents;
     inf.max_col_nnz = maxColNnz; inf.max_coupled = maxCoupled; inf.tree_depth = depth; inf.n_states = nStates;
-    inf.chain_state_bytes = int64_t(xStride) + int64_t(nCols) * 17 + int64_t(d.t1Len + d.t2Len) * 8 + int64_t(d.sCap) * 16;
+    inf.chain_state_bytes = chainStateBytes(d);
     if (hostOnly) {   // what the uploads below would occupy
         auto bytes = [](const auto &v) { return int64_t(v.size() * sizeof(v[0])); };
         inf.shared_bytes = bytes(recIdx) + bytes(rec) + bytes(facVal) + bytes(impTab) + bytes(colPtr) + bytes(colRow) + bytes(colVal) +
@@ -524,7 +555,9 @@ int abm_chains_create(const abm_problem *p, int32_t nChains, uint64_t seed, uint
     al(&d.tier1, n * P.t1Len); al(&d.tier2, n * P.t2Len); al(&d.tier3, n * 32);
     al(&d.logImp, n); al(&d.infeas, n); al(&d.iter, n); al(&d.counters, n * 8);
     al(&d.scratch, n * P.sCap);
-    al(&d.endStateSum, size_t(std::max(P.S, 1))); al(&d.synSum, n * std::max(P.nSynopsis, 1));
+    al(&c->momExact, size_t(kMomExactHead) + size_t(std::max(P.S, 1))); al(&c->momReal, size_t(kMomReal));
+    if (e == cudaSuccess) d.endStateSum = c->momExact + kMomExactHead;
+    al(&d.synSum, n * std::max(P.nSynopsis, 1));
     al(&d.synSumSq, n * std::max(P.nSynopsis, 1)); al(&d.nSamples, n);
     al(&d.synNow, n * std::max(P.nSynopsis, 1)); al(&d.launchSamples, n);
     al(&d.endRec, n * std::max(P.S, 1));
@@ -544,6 +577,8 @@ int abm_chains_destroy(abm_chains *c) {
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     if (c->evStats) cudaEventDestroy(c->evStats);
     if (c->stage) cudaFreeHost(c->stage);
+    if (c->evMom) cudaEventDestroy(c->evMom);
+    if (c->momStage) cudaFreeHost(c->momStage);
     delete c;
     return ABM_OK;
 }
@@ -585,14 +620,13 @@ int abm_chains_init(abm_chains *c, const int8_t *initEvents, int32_t nInit) {
     if (!c || nInit < 0 || (nInit > 0 && !initEvents)) return fail(ABM_ERR_INVALID, "bad argument");
     CUDA_TRY(cudaSetDevice(c->p->device));
     const size_t n = size_t(c->n);
+    DeviceArena tmp;   // freed on every return path
     int8_t *dInit = nullptr;
     if (nInit > 0) {
-        CUDA_TRY(cudaMalloc(&dInit, n * nInit));
+        CUDA_TRY(tmp.alloc(&dInit, n * nInit));
         CUDA_TRY(cudaMemcpyAsync(dInit, initEvents, n * nInit, cudaMemcpyHostToDevice, c->stream));
     }
-    const int rc = initFromDevice(c, dInit, nInit);
-    if (dInit) cudaFree(dInit);
-    return rc;
+    return initFromDevice(c, dInit, nInit);   // synchronises the stream before returning
 }
 
 int abm_chains_init_from_prior(abm_chains *c, const double *actPmf, double pPredator, double pPrey, uint64_t seed,
@@ -603,10 +637,11 @@ int abm_chains_init_from_prior(abm_chains *c, const double *actPmf, double pPred
     if (P.G <= 0) return fail(ABM_ERR_INVALID, "prior sampling needs the PredPrey geometry");
     CUDA_TRY(cudaSetDevice(c->p->device));
     const size_t n = size_t(c->n), bytes = n * size_t(P.nEvents);
+    DeviceArena tmp;   // freed on every return path
     int8_t *dEvents = nullptr;
     double *dPmf = nullptr;
-    CUDA_TRY(cudaMalloc(&dEvents, bytes));
-    CUDA_TRY(cudaMalloc(&dPmf, 24 * sizeof(double)));
+    CUDA_TRY(tmp.alloc(&dEvents, bytes));
+    CUDA_TRY(tmp.alloc(&dPmf, size_t(24)));
     CUDA_TRY(cudaMemcpyAsync(dPmf, actPmf, 24 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const size_t smem = size_t(2) * P.S * sizeof(int);
     cudaError_t e = cudaFuncSetAttribute(priorSampleKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -621,8 +656,7 @@ int abm_chains_init_from_prior(abm_chains *c, const double *actPmf, double pPred
         if (e != cudaSuccess) rc = fail(ABM_ERR_CUDA, cudaGetErrorString(e));
     }
     if (rc == ABM_OK) rc = initFromDevice(c, dEvents, P.nEvents);
-    cudaFree(dEvents);
-    cudaFree(dPmf);
+    else cudaStreamSynchronize(c->stream);   // nothing may still use the temporaries when the arena frees them
     return rc;
 }
 
@@ -664,6 +698,8 @@ static cudaError_t launchStep(const abm_chains *c, const RunParams &r) {
 
 extern "C" {
 
+constexpr int64_t kMaxStepsPerLaunch = 1ll << 30;   // per-launch step and sample counters are 32-bit registers
+
 static RunParams baseParams(const abm_chains *c) {
     RunParams r{};
     r.seed = c->seed;
@@ -679,12 +715,14 @@ int abm_chains_find_feasible(abm_chains *c, int64_t maxIterations, const double 
     const DevProblem &P = c->p->d;
     const size_t n = size_t(c->n);
     if (maxIterations <= 0) maxIterations = INT64_MAX;
+    DeviceArena tmp;   // freed on every return path (each launch below is followed by a stream synchronisation)
     double *dU = nullptr;
-    long long *dIters = nullptr;
-    CUDA_TRY(cudaMalloc(&dIters, n * sizeof(long long)));
+    long long *dIters = nullptr;   // per-call iteration counts: the kernel ADDS to them across the launches of this call only
+    CUDA_TRY(tmp.alloc(&dIters, n));
     CUDA_TRY(cudaMemsetAsync(dIters, 0, n * sizeof(long long), c->stream));
     if (uniforms) {
-        CUDA_TRY(cudaMalloc(&dU, n * nUniforms * sizeof(double)));
+        if (nUniforms <= 0) return fail(ABM_ERR_INVALID, "uniforms without a count");
+        CUDA_TRY(tmp.alloc(&dU, n * size_t(nUniforms)));
         CUDA_TRY(cudaMemcpyAsync(dU, uniforms, n * nUniforms * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         maxIterations = std::min<int64_t>(maxIterations, nUniforms);
     }
@@ -711,8 +749,6 @@ int abm_chains_find_feasible(abm_chains *c, int64_t maxIterations, const double 
         CUDA_TRY(cudaMemcpy(it.data(), dIters, n * sizeof(long long), cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < n; ++k) iterationsOut[k] = it[k];
     }
-    CUDA_TRY(cudaFree(dIters));
-    if (dU) CUDA_TRY(cudaFree(dU));
     if (!allFeasible) return fail(ABM_ERR_NOT_FEASIBLE, "feasibility search hit its iteration limit");
     setStateKernel<<<(c->n + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, c->stream>>>(P, c->d);
     CUDA_TRY(cudaGetLastError());
@@ -725,10 +761,14 @@ int abm_chains_step(abm_chains *c, int64_t nSteps) {
     if (!c || nSteps < 0) return fail(ABM_ERR_INVALID, "bad argument");
     if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
     CUDA_TRY(cudaSetDevice(c->p->device));
-    RunParams r = baseParams(c);
-    r.nSteps = nSteps;
     CUDA_TRY(markLaunch(c, true));
-    CUDA_TRY(launchStep<MODE_MCMC>(c, r));
+    // the kernel counts a launch's steps in 32-bit registers (the per-chain totals are 64-bit): longer requests are split
+    for (int64_t done = 0; done < nSteps || (nSteps == 0 && done == 0);) {
+        RunParams r = baseParams(c);
+        r.nSteps = std::min<int64_t>(nSteps - done, kMaxStepsPerLaunch);
+        CUDA_TRY(launchStep<MODE_MCMC>(c, r));
+        done += std::max<int64_t>(r.nSteps, 1);
+    }
     CUDA_TRY(markLaunch(c, false));
     return ABM_OK;
 }
@@ -745,6 +785,7 @@ int abm_chains_last_launch_ms(abm_chains *c, float *ms) {
 int abm_chains_step_traced(abm_chains *c, int64_t nSteps, const double *uniforms, const int32_t *proposals,
                            int32_t *outJ, uint8_t *outAcc, int32_t *outInf) {
     if (!c || nSteps < 0) return fail(ABM_ERR_INVALID, "bad argument");
+    if (nSteps > kMaxStepsPerLaunch) return fail(ABM_ERR_INVALID, "at most 2^30 traced steps per call");
     if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
     CUDA_TRY(cudaSetDevice(c->p->device));
     const size_t n = size_t(c->n), ns = size_t(nSteps);
@@ -796,8 +837,12 @@ int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
     if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
     if (c->p->d.G <= 0) return fail(ABM_ERR_INVALID, "sample statistics need the PredPrey geometry");
     CUDA_TRY(cudaSetDevice(c->p->device));
+    // per-launch step and sample counts live in 32-bit registers: one call is one launch of at most 2^30 steps / samples
+    if (nSamples > kMaxStepsPerLaunch && (maxSteps <= 0 || maxSteps > kMaxStepsPerLaunch))
+        return fail(ABM_ERR_INVALID, "at most 2^30 samples or steps per abm_chains_sample call");
+    if (maxSteps > kMaxStepsPerLaunch) return fail(ABM_ERR_INVALID, "at most 2^30 steps per abm_chains_sample call");
     RunParams r = baseParams(c);
-    r.nSteps = maxSteps > 0 ? maxSteps : INT64_MAX;
+    r.nSteps = maxSteps > 0 ? maxSteps : kMaxStepsPerLaunch;
     r.nSamples = nSamples;
     r.series = c->series;
     r.nSeriesChains = c->nSeriesChains;
@@ -993,6 +1038,185 @@ int abm_chains_reset_statistics(abm_chains *c) {
     CUDA_TRY(cudaSetDevice(c->p->device));
     int rc = zeroStatistics(c);
     if (rc != ABM_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ABM_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded on first use: the library must load (and single-GPU use must work) on a host without NCCL, and no NCCL type
+// appears in the C ABI.  Only the handful of entry points the ensemble reduction needs.
+struct Id128 { char bytes[ABM_COMM_ID_BYTES]; };   // ncclUniqueId (nccl.h: struct { char internal[128]; })
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Id128 /* ncclUniqueId, by value */, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string error;
+};
+constexpr int kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+NcclApi *ncclApi() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("ABM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm) continue;
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) { api.error = "NCCL library not found (libnccl.so.2; set ABM_NCCL_LIB)"; return; }
+        auto sym = [&](const char *n) { void *f = dlsym(api.lib, n); if (!f) api.error = std::string("missing NCCL symbol ") + n; return f; };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    });
+    return &api;
+}
+#define NCCL_TRY(api, expr)                                                                                  \
+    do {                                                                                                     \
+        int r_ = (expr);                                                                                     \
+        if (r_ != 0) return fail(ABM_ERR_CUDA, std::string(#expr) + ": " + (api)->GetErrorString(r_));       \
+    } while (0)
+}  // namespace
+
+struct abm_comm {
+    void *nccl = nullptr;   // ncclComm_t
+    bool owned = false;
+    int device = -1;
+};
+
+extern "C" {
+
+int abm_comm_unique_id(uint8_t id[ABM_COMM_ID_BYTES]) {
+    if (!id) return fail(ABM_ERR_INVALID, "null argument");
+    NcclApi *a = ncclApi();
+    if (!a->error.empty()) return fail(ABM_ERR_CUDA, a->error);
+    NCCL_TRY(a, a->GetUniqueId(id));
+    return ABM_OK;
+}
+
+int abm_comm_create(int32_t nRanks, int32_t rank, const uint8_t id[ABM_COMM_ID_BYTES], int device, abm_comm **out) {
+    if (!out || !id || nRanks <= 0 || rank < 0 || rank >= nRanks) return fail(ABM_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    NcclApi *a = ncclApi();
+    if (!a->error.empty()) return fail(ABM_ERR_CUDA, a->error);
+    if (abm_device_count() <= device || device < 0) return fail(ABM_ERR_CUDA, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    Id128 uid;
+    memcpy(uid.bytes, id, ABM_COMM_ID_BYTES);
+    void *comm = nullptr;
+    NCCL_TRY(a, a->CommInitRank(&comm, nRanks, uid, rank));
+    abm_comm *c = new abm_comm();
+    c->nccl = comm;
+    c->owned = true;
+    c->device = device;
+    *out = c;
+    return ABM_OK;
+}
+
+int abm_comm_from_nccl(void *ncclComm, abm_comm **out) {
+    if (!out || !ncclComm) return fail(ABM_ERR_INVALID, "null argument");
+    NcclApi *a = ncclApi();
+    if (!a->error.empty()) return fail(ABM_ERR_CUDA, a->error);
+    abm_comm *c = new abm_comm();
+    c->nccl = ncclComm;
+    *out = c;
+    return ABM_OK;
+}
+
+int abm_comm_destroy(abm_comm *comm) {
+    if (!comm) return ABM_OK;
+    if (comm->owned && comm->nccl) {
+        if (comm->device >= 0) cudaSetDevice(comm->device);
+        ncclApi()->CommDestroy(comm->nccl);
+    }
+    delete comm;
+    return ABM_OK;
+}
+
+// device reduction of this GPU's chains (+ NCCL sum over the ranks of comm), then the copies into pinned staging
+int abm_chains_enqueue_moments(abm_chains *c, abm_comm *comm) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const DevProblem &P = c->p->d;
+    const size_t S = size_t(std::max(P.S, 0)), nExact = kMomExactHead + S;
+    if (!c->momStage) CUDA_TRY(cudaMallocHost(&c->momStage, nExact * sizeof(int64_t) + kMomReal * sizeof(double)));
+    if (!c->evMom) CUDA_TRY(cudaEventCreateWithFlags(&c->evMom, cudaEventDisableTiming));
+    if (S > 0) {
+        CUDA_TRY(cudaMemsetAsync(c->d.endStateSum, 0, S * sizeof(long long), c->stream));
+        reduceEndStateKernel<<<dim3((P.S + 127) / 128, (c->n + kReduceSlice - 1) / kReduceSlice), 128, 0, c->stream>>>(P, c->d);
+        CUDA_TRY(cudaGetLastError());
+    }
+    momentsKernel<<<1, 256, 0, c->stream>>>(P, c->d, c->momExact, c->momReal);
+    CUDA_TRY(cudaGetLastError());
+    if (comm && comm->nccl) {
+        NcclApi *a = ncclApi();
+        NCCL_TRY(a, a->GroupStart());
+        NCCL_TRY(a, a->AllReduce(c->momExact, c->momExact, nExact, kNcclInt64, kNcclSum, comm->nccl, c->stream));
+        NCCL_TRY(a, a->AllReduce(c->momReal, c->momReal, kMomReal, kNcclFloat64, kNcclSum, comm->nccl, c->stream));
+        NCCL_TRY(a, a->GroupEnd());
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->momStage, c->momExact, nExact * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->momStage + nExact, c->momReal, kMomReal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaEventRecord(c->evMom, c->stream));
+    c->momPending = true;
+    return ABM_OK;
+}
+
+int abm_chains_wait_moments(abm_chains *c, int64_t *exact, double *real) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    if (!c->momPending) return fail(ABM_ERR_STATE, "abm_chains_enqueue_moments has not been called");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaEventSynchronize(c->evMom));
+    c->momPending = false;
+    const size_t nExact = kMomExactHead + size_t(std::max(c->p->d.S, 0));
+    if (exact) memcpy(exact, c->momStage, nExact * sizeof(int64_t));
+    if (real) memcpy(real, c->momStage + nExact, kMomReal * sizeof(double));
+    return ABM_OK;
+}
+
+int abm_chains_allreduce_moments(abm_chains *c, abm_comm *comm, int64_t *exact, double *real) {
+    int rc = abm_chains_enqueue_moments(c, comm);
+    if (rc != ABM_OK) return rc;
+    return abm_chains_wait_moments(c, exact, real);
+}
+
+int abm_chains_get_moments(abm_chains *c, int64_t *exact, double *real) { return abm_chains_allreduce_moments(c, nullptr, exact, real); }
+
+// abm_chains_sample with the uniforms injected: exactly nSteps steps, statistics after every step that ends feasible
+int abm_chains_sample_injected(abm_chains *c, int64_t nSteps, const double *uniforms) {
+    if (!c || nSteps <= 0 || !uniforms) return fail(ABM_ERR_INVALID, "bad argument");
+    if (nSteps > INT32_MAX) return fail(ABM_ERR_INVALID, "at most 2^31-1 steps per launch");
+    if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
+    if (c->p->d.G <= 0) return fail(ABM_ERR_INVALID, "sample statistics need the PredPrey geometry");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const size_t n = size_t(c->n), ns = size_t(nSteps);
+    DeviceArena tmp;
+    double *dU = nullptr;
+    CUDA_TRY(tmp.alloc(&dU, n * ns * 2));
+    CUDA_TRY(cudaMemcpyAsync(dU, uniforms, n * ns * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RunParams r = baseParams(c);
+    r.nSteps = nSteps;
+    r.injU = dU;
+    r.uStride = 2 * nSteps;
+    const DevProblem &P = c->p->d;
+    sampleBeginKernel<<<(c->n + 3) / 4, 128, 0, c->stream>>>(P, c->d);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launchStep<MODE_SAMPLE_FIXED>(c, r));
+    sampleEndKernel<<<c->n, 256, 0, c->stream>>>(P, c->d);
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ABM_OK;
 }

@@ -1288,4 +1288,74 @@ __global__ void reduceEndStateKernel(DevProblem P, DevChains S) {
     atomicAdd(reinterpret_cast<unsigned long long *>(S.endStateSum) + psi, (unsigned long long)acc);
 }
 
+// Per-GPU additive moments of the ensemble, reduced on the device (the reference sums its
+// threads' results in a serial loop over std::futures, FiguresForPaper.h:62-65).  Everything a multi-GPU SUM all-reduce needs
+// to rebuild the marginals and W, B, var+, R-hat (diagnostics/MultiChainStats.h:141-181):
+//   exact[0] chains with at least two samples, [1] feasible samples, [2..10) MCMCStatistics counters,
+//        [10..18) sum over chains of the synopsis sums, [18..26) of the sums of squares, [26..26+S) end-state occupancy sums
+//   real [0..8) sum over chains of the chain mean (MeanAndVariance::mean, MeanAndVariance.h:52-54), [8..16) of its square,
+//        [16..24) of the chain variance (sampleVariance, :57-59)
+// One CTA; every partial sum is combined in a fixed order (shuffle tree, then warps in order), so the doubles are reproducible.
+constexpr int kMomExactHead = 26, kMomReal = 24;
+__global__ void __launch_bounds__(256) momentsKernel(DevProblem P, DevChains S, long long *__restrict__ exact, double *__restrict__ real) {
+    __shared__ long long shI[8][kMomExactHead];
+    __shared__ double shD[8][kMomReal];
+    long long vi[kMomExactHead];
+    double vd[kMomReal];
+#pragma unroll
+    for (int k = 0; k < kMomExactHead; ++k) vi[k] = 0;
+#pragma unroll
+    for (int k = 0; k < kMomReal; ++k) vd[k] = 0.0;
+    const int d = P.nSynopsis;
+    for (int c = threadIdx.x; c < S.nChains; c += blockDim.x) {
+        const long long n = S.nSamples[c];
+        vi[1] += n;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) vi[2 + q] += S.counters[(size_t)c * 8 + q];
+        if (n > 1) vi[0] += 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < d) {
+                const long long s = S.synSum[(size_t)c * d + k], q = S.synSumSq[(size_t)c * d + k];
+                vi[10 + k] += s;
+                vi[18 + k] += q;
+                if (n > 1) {
+                    const double sd = (double)s, qd = (double)q, inv = 1.0 / (double)n;
+                    const double mean = sd * inv;
+                    const double var = (qd - sd * sd * inv) * (1.0 / (double)(n - 1));
+                    vd[k] += mean;
+                    vd[8 + k] += mean * mean;
+                    vd[16 + k] += var;
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < kMomExactHead; ++k) vi[k] += __shfl_xor_sync(kFull, vi[k], o);
+#pragma unroll
+        for (int k = 0; k < kMomReal; ++k) vd[k] += __shfl_xor_sync(kFull, vd[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kMomExactHead; ++k) shI[warp][k] = vi[k];
+#pragma unroll
+        for (int k = 0; k < kMomReal; ++k) shD[warp][k] = vd[k];
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    if (threadIdx.x < kMomExactHead) {
+        long long a = 0;
+        for (int w = 0; w < nw; ++w) a += shI[w][threadIdx.x];
+        exact[threadIdx.x] = a;
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + kMomReal) {
+        double a = 0.0;
+        for (int w = 0; w < nw; ++w) a += shD[w][threadIdx.x - 32];
+        real[threadIdx.x - 32] = a;
+    }
+}
+
 }  // namespace abm

@@ -223,6 +223,31 @@ class SparseBasisSampler:
                                                       _ptr(ns, C.c_int64), _ptr(cnt, C.c_int64)))
         return end, ss, sq, ns, cnt
 
+    def sample_injected(self, n_steps: int, uniforms):
+        """`sample` for exactly n_steps steps with the uniforms injected ([n_chains][2*n_steps]); statistics parity runs."""
+        u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(self.n_chains, 2 * n_steps)
+        check(_capi.load().abm_chains_sample_injected(self.h, n_steps, _ptr(u, C.c_double)))
+
+    # ---- ensemble moments reduced on the device (abm_chains_get_moments & co., include/abmcmc_b200.h)
+    def _moment_buffers(self):
+        S = 2 * self.problem.grid_size ** 2
+        return np.zeros(_capi.MOMENTS_EXACT_HEAD + S, np.int64), np.zeros(_capi.MOMENTS_REAL, np.float64)
+
+    def moments(self, comm=None):
+        """(exact int64[26 + S], real float64[24]) of this GPU's chains, summed over the ranks of `comm` (ensemble.Comm)."""
+        ex, re = self._moment_buffers()
+        check(_capi.load().abm_chains_allreduce_moments(self.h, comm.h if comm is not None else None, _ptr(ex, C.c_int64),
+                                                        _ptr(re, C.c_double)))
+        return ex, re
+
+    def enqueue_moments(self, comm=None):
+        check(_capi.load().abm_chains_enqueue_moments(self.h, comm.h if comm is not None else None))
+
+    def wait_moments(self):
+        ex, re = self._moment_buffers()
+        check(_capi.load().abm_chains_wait_moments(self.h, _ptr(ex, C.c_int64), _ptr(re, C.c_double)))
+        return ex, re
+
     def statistics_into(self, end_ptr: int, syn_sum_ptr: int, syn_sumsq_ptr: int, n_samples_ptr: int):
         """Same, into DEVICE buffers (raw pointers, e.g. torch tensors' data_ptr()) for an NCCL all-reduce."""
         vp = lambda p: C.cast(C.c_void_p(p), C.POINTER(C.c_int64)) if p else None

@@ -77,7 +77,7 @@ typedef struct {
     int32_t max_col_nnz, max_coupled; /* longest column; most columns sharing a row with one column */
     int32_t tree_depth;               /* bit length of n_cols-1 (MutableCategoricalArray.cpp:41-48) */
     int32_t n_states;                 /* T * 2 * G * G (0 without importance)                    */
-    int64_t chain_state_bytes;        /* HBM bytes of one chain                                   */
+    int64_t chain_state_bytes;        /* HBM bytes of one chain (everything abm_chains_create allocates per chain) */
     int64_t shared_bytes;             /* HBM bytes of the shared structure                        */
 } abm_problem_info;
 
@@ -146,6 +146,8 @@ ABM_API int abm_chains_step_traced(abm_chains *c, int64_t n_steps, const double 
  * (a feasible state is a sample each time the loop condition :247 sees infeasibility == 0), accumulating
  * the ensemble statistics below after each one.  max_steps bounds the work per chain (0 = unbounded); n_samples == 0 with
  * max_steps > 0 means "sample for exactly max_steps steps". */
+/* One call is one launch: at most 2^30 steps (max_steps == 0 stands for that bound) and, when the quota is the binding
+ * limit, at most 2^30 samples; abm_chains_step splits longer requests into several launches itself. */
 ABM_API int abm_chains_sample(abm_chains *c, int64_t n_samples, int64_t max_steps);
 
 ABM_API int abm_chains_synchronize(abm_chains *c);
@@ -185,6 +187,42 @@ ABM_API int abm_chains_reset_statistics(abm_chains *c);
 ABM_API int abm_chains_record_series(abm_chains *c, int32_t n_chains, int32_t thin, int32_t capacity);
 ABM_API int abm_chains_get_series(abm_chains *c, int32_t *out);
 ABM_API int abm_problem_n_synopsis(const abm_problem *p); /* floor(log2(G)) - 1 (FiguresForPaper.h:246) */
+
+/* The random inputs of a sampling launch injected, for parity testing of the statistics: exactly n_steps steps per chain with
+ * uniforms host [n_chains][2*n_steps] (u1 = column draw, u2 = accept draw), statistics accumulated as by abm_chains_sample
+ * after every step that ends feasible.  Synchronous. */
+ABM_API int abm_chains_sample_injected(abm_chains *c, int64_t n_steps, const double *uniforms);
+
+/* ---- ensemble moments and their multi-GPU reduction.  The reference adds up its threads'
+ * results in a serial loop over std::futures (FiguresForPaper.h:62-65) and computes W, B, var+, R-hat from per-sequence
+ * means and variances (diagnostics/MultiChainStats.h:141-181).  Here each GPU reduces its chains on the device to one short
+ * ADDITIVE vector, and the vectors of all GPUs are summed by one NCCL all-reduce:
+ *   exact[ABM_MOMENTS_EXACT_HEAD + n_agent_states] int64:
+ *     [0] chains with >= 2 samples  [1] feasible samples  [2..10) MCMCStatistics counters (n_proposals[2][2], n_accepted[2][2])
+ *     [10..18) sum over chains of the synopsis sums  [18..26) of the synopsis sums of squares (first n_synopsis entries used)
+ *     [26 ...) end-state occupancy sums (ModelState(traj,T,T) summed over chains and samples)
+ *   real[ABM_MOMENTS_REAL] double: [0..8) sum over chains of the chain mean, [8..16) of its square, [16..24) of the chain
+ *     variance (MeanAndVariance::mean / sampleVariance, diagnostics/MeanAndVariance.h:52-59)
+ * abm_chains_get_moments: this GPU's vectors into host buffers.  abm_chains_allreduce_moments: the same summed over all ranks
+ * of `comm` (NULL = this GPU only).  enqueue / wait: the same without stalling the stream (one may be pending), like
+ * abm_chains_enqueue_statistics; the read-back is ~17 KB instead of the per-chain tables. */
+#define ABM_MOMENTS_EXACT_HEAD 26
+#define ABM_MOMENTS_REAL 24
+typedef struct abm_comm abm_comm;
+/* NCCL plumbing without an NCCL type in the signature: rank 0 makes an id (ncclGetUniqueId, 128 bytes), the host program
+ * distributes it by whatever it has (MPI, a file, torch.distributed), every rank then joins (ncclCommInitRank on the device
+ * of its chains).  abm_comm_from_nccl borrows an existing ncclComm_t instead (not destroyed by abm_comm_destroy).
+ * libnccl.so.2 is loaded on first use (environment ABM_NCCL_LIB overrides the name); without it these calls fail with
+ * ABM_ERR_CUDA and single-GPU use is unaffected. */
+#define ABM_COMM_ID_BYTES 128
+ABM_API int abm_comm_unique_id(uint8_t id[ABM_COMM_ID_BYTES]);
+ABM_API int abm_comm_create(int32_t n_ranks, int32_t rank, const uint8_t id[ABM_COMM_ID_BYTES], int device, abm_comm **out);
+ABM_API int abm_comm_from_nccl(void *nccl_comm, abm_comm **out);
+ABM_API int abm_comm_destroy(abm_comm *comm);
+ABM_API int abm_chains_get_moments(abm_chains *c, int64_t *exact, double *real);
+ABM_API int abm_chains_allreduce_moments(abm_chains *c, abm_comm *comm, int64_t *exact, double *real);
+ABM_API int abm_chains_enqueue_moments(abm_chains *c, abm_comm *comm);
+ABM_API int abm_chains_wait_moments(abm_chains *c, int64_t *exact, double *real);
 
 /* Device time of the last abm_chains_step / _step_traced / _sample launch (CUDA events on the chains' stream around the
  * step kernel; waits for it to finish).  For measurements: the traced variant's host copies are outside. */

@@ -121,6 +121,10 @@ public:
         // one Metropolis step per device call, each fed the two doubles the reference would draw from Random::gen
         // (column draw, then accept test); stops at the first feasible state like the do-while at :221-247.
         // This is the exact, sample-for-sample mode; throughput comes from the batched interface below.
+        // abm_chains_step_traced reads [n_chains][2] uniforms and writes [n_chains] flags: the buffers below are one chain's
+        if (nChains_ != 1)
+            throw std::logic_error("GpuSparseBasisSampler::operator(): the exact mode drives one chain; after batched() / "
+                                   "batchedFromPrior() use step() / sample() / statistics");
         double u[2];
         int32_t inf = 0;
         uint8_t acc = 0;
@@ -155,6 +159,8 @@ public:
     void waitStatistics(int64_t *endStateSum, int64_t *synSum, int64_t *synSumSq, int64_t *nSamples, abm_mcmc_counters *counters) {
         detail::check(abm_chains_wait_statistics(chains_, endStateSum, synSum, synSumSq, nSamples, counters), "abm_chains_wait_statistics");
     }
+    // uniforms drawn ahead per device call of the exact-mode feasibility search (tests shrink it to cross many blocks)
+    static int64_t &feasibilityBlock() { static int64_t b = 1 << 14; return b; }
     abm_chains *chains() { return chains_; }
     abm_problem *problem() { return problem_; }
 
@@ -177,7 +183,9 @@ private:
         } else {
             // findInitialFeasibleSolution (:254-263) on Random::gen: one uniform per iteration.  Blocks are drawn from a
             // copy; afterwards the real generator is advanced by exactly the iterations the search used.
-            const int64_t block = 1 << 14;
+            // abm_chains_find_feasible reports the iterations of THAT call (its device counter is zeroed per call), so after a
+            // block that ends feasible the generator is the block's start advanced by the block's own iterations
+            const int64_t block = feasibilityBlock();
             std::vector<double> u(block);
             int rc;
             do {

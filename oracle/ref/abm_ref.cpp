@@ -19,6 +19,17 @@
 #include "Likelihood.h"
 #include "PredPreyProblem.h"
 #include "SparseBasisSampler.h"
+// FiguresForPaper.h (synopsis(), :245-263) and diagnostics/MultiChainStats.h pull in the vendored gnuplot-iostream, which needs
+// Boost.Iostreams; its include guard is pre-defined and a no-op Gnuplot class stands in
+#define GNUPLOT_IOSTREAM_H
+#include <cfloat>
+#include <tuple>
+struct Gnuplot {
+    template <class T> Gnuplot &operator<<(const T &) { return *this; }
+    template <class T> void send1d(const T &) {}
+    template <class T> void send2d(const T &) {}
+};
+#include "FiguresForPaper.h"
 
 #include "abmcmc_b200/abmp_io.hpp"
 #include "abmcmc_b200/reference_flatten.hpp"
@@ -281,15 +292,30 @@ int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int ev
         t.i32["inf" + sfx] = {int32_t(s.currentInfeasibility)};
     };
     snapshot("0");
-    std::vector<int32_t> trJ, trInf, ckHash, ckInf;
+    std::vector<int32_t> trJ, trInf, ckHash, ckInf, ckEnd, ckSyn;
     std::vector<uint8_t> trAcc;
     std::vector<double> ckLogImp, ckSum;
     trJ.reserve(nSteps);
+    // what the reference's statistics pipeline sees (FiguresForPaper.h:93-104): every state the do-while of
+    // nextSampleWithInfeasibleImportance (SparseBasisSampler.h:247) hands out, i.e. the state after every step that ends
+    // feasible, mapped by TrajectoryToModelState(T,T) (ModelState.h:27-36) and synopsis() (FiguresForPaper.h:245-263) --
+    // the reference's own code -- and summed as Sum<ModelState> / MeanAndVariance do
+    typedef PredPreyAgent<G> Agent;
+    const int T = problem.nTimesteps();
+    std::vector<double> smpEnd(Agent::domainSize(), 0.0);
+    MeanAndVariance smpSyn;
+    long nFeasible = 0;
     for (long k = 0; k < nSteps; ++k) {
         auto r = s.step();
         trJ.push_back(r.j);
         trAcc.push_back(r.accepted ? 1 : 0);
         trInf.push_back(int32_t(r.infeasibility));
+        if (s.currentInfeasibility == 0) {
+            ModelState<Agent> endState(s.X, T, T);
+            for (int q = 0; q < Agent::domainSize(); ++q) smpEnd[q] += endState[q];
+            smpSyn(FiguresForPaper<G, 1>::synopsis(endState));
+            ++nFeasible;
+        }
         if ((k + 1) % every == 0 || k + 1 == nSteps) {
             uint64_t h = hashX(s.X);
             ckHash.push_back(int32_t(uint32_t(h)));
@@ -297,8 +323,17 @@ int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int ev
             ckLogImp.push_back(s.currentLogImportance);
             ckSum.push_back(s.basisDistribution.sum());
             ckInf.push_back(int32_t(s.currentInfeasibility));
+            ModelState<Agent> endState(s.X, T, T);
+            for (int q = 0; q < Agent::domainSize(); ++q) ckEnd.push_back(int32_t(endState[q]));
+            for (double v : FiguresForPaper<G, 1>::synopsis(endState)) ckSyn.push_back(int32_t(v));
         }
     }
+    t.i32["ck_endstate"] = ckEnd;        // [checkpoints][S]  ModelState(X,T,T)
+    t.i32["ck_synopsis"] = ckSyn;        // [checkpoints][nSynopsis]
+    t.f64["smp_endstate_sum"] = smpEnd;  // [S] over the feasible states
+    t.f64["smp_syn_sum"] = std::vector<double>(std::begin(smpSyn.sum), std::end(smpSyn.sum));
+    t.f64["smp_syn_sumsq"] = std::vector<double>(std::begin(smpSyn.sumOfSquares), std::end(smpSyn.sumOfSquares));
+    t.i32["smp_n"] = {int32_t(nFeasible)};
     t.i32["tr_j"] = trJ;
     t.u8["tr_acc"] = trAcc;
     t.i32["tr_inf"] = trInf;
@@ -445,29 +480,42 @@ int cmdBench(const AbmpFile &f, int nThreads, long samplesPerStep, int warmup, i
         for (auto &x : fut) x.wait();
     }
     double setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
-    std::vector<double> secs;
+    // Every thread times its own loop: a round's Metropolis-step rate is the SUM of the per-thread rates (steps per feasible
+    // sample vary widely between chains, so joining the threads and dividing by the slowest would under-report the CPU).
+    std::vector<double> secs, rates;
     std::vector<long> stepCounts;
     for (int r = 0; r < warmup + steps; ++r) {
-        long before = 0;
-        for (auto &s : samplers) before += s->stats.nSamples();
+        std::vector<double> tSec(nThreads, 0.0);
+        std::vector<long> tSteps(nThreads, 0);
         auto t0 = std::chrono::steady_clock::now();
         std::vector<std::future<void>> fut;
         for (int t = 0; t < nThreads; ++t)
             fut.push_back(std::async(std::launch::async, [&, t]() {
                 Random::gen = gens[t];
+                const long before = samplers[t]->stats.nSamples();
+                auto a = std::chrono::steady_clock::now();
                 for (long k = 0; k < samplesPerStep; ++k) (*samplers[t])();
+                tSec[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+                tSteps[t] = samplers[t]->stats.nSamples() - before;
                 gens[t] = Random::gen;
             }));
         for (auto &x : fut) x.wait();
         double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        long after = 0;
-        for (auto &s : samplers) after += s->stats.nSamples();
-        if (r >= warmup) { secs.push_back(dt); stepCounts.push_back(after - before); }
+        if (r >= warmup) {
+            double rate = 0.0;
+            long st = 0;
+            for (int t = 0; t < nThreads; ++t) { rate += tSteps[t] / tSec[t]; st += tSteps[t]; }
+            secs.push_back(dt);
+            rates.push_back(rate);
+            stepCounts.push_back(st);
+        }
     }
     printf("{\"impl\": \"reference\", \"grid\": %d, \"threads\": %d, \"samples_per_step\": %ld, \"setup_seconds\": %.3f, \"step_seconds\": [", G, nThreads, samplesPerStep, setup);
     for (size_t k = 0; k < secs.size(); ++k) printf("%s%.6f", k ? ", " : "", secs[k]);
     printf("], \"chain_steps\": [");
     for (size_t k = 0; k < stepCounts.size(); ++k) printf("%s%ld", k ? ", " : "", stepCounts[k]);
+    printf("], \"steps_per_s\": [");
+    for (size_t k = 0; k < rates.size(); ++k) printf("%s%.3f", k ? ", " : "", rates[k]);
     printf("]}\n");
     return 0;
 }
@@ -597,6 +645,139 @@ int cmdSeries(const AbmpFile &f, int nThreads, long nSamples, long burnin, const
     return 0;
 }
 
+// Long reference chains for the paper-scale posterior fixture (protocol: FiguresForPaper.h:40-104): per thread one chain from
+// its own prior sample (:56), `burnin` calls of sampler() (Drop, :93), then nSamples calls, each mapped by the reference's
+// own TrajectoryToModelState(T,T) (ModelState.h:27-36) and synopsis() (FiguresForPaper.h:245-263).  Kept per chain: the
+// MeanAndVariance sums, the end-state sum, means over consecutive batches of `batch` samples (burn-in batches separately:
+// the relaxation from the first feasible state), and every `thin`-th synopsis sample.  Sampling part timed per thread.
+template <int G>
+int cmdPosterior(const AbmpFile &f, int nThreads, long nSamples, long burnin, long batch, long thin, const std::string &out, int seedBase) {
+    typedef PredPreyAgent<G> Agent;
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    const int T = problem.nTimesteps();
+    const int S = Agent::domainSize();
+    int nSyn = 0;
+    for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;
+    Random::gen.seed(97531 + seedBase);
+    std::vector<std::vector<occ_t>> inits;
+    for (int t = 0; t < nThreads; ++t) inits.push_back(priorSample<G>(problem));
+    struct Res {
+        std::vector<double> synSum, synSumSq, end, batchMeans, burnMeans;
+        std::vector<int32_t> series;
+        double seconds = 0, burnSeconds = 0;
+        long steps = 0, burnSteps = 0, initIters = 0;
+        std::vector<long> counters;
+    };
+    std::vector<std::future<Res>> fut;
+    {
+        SilenceStdout quiet;
+        for (int t = 0; t < nThreads; ++t)
+            fut.push_back(std::async(std::launch::async, [&problem, &inits, t, T, S, nSyn, nSamples, burnin, batch, thin, seedBase]() {
+                Random::gen.seed(9000 + seedBase + t);
+                SparseBasisSampler<occ_t> sampler(problem.tableau, problem.posterior.factors,
+                                                  problem.posterior.perturbableFunctionFactory(), inits[t], problem.kappa);
+                Res r;
+                r.synSum.assign(nSyn, 0.0); r.synSumSq.assign(nSyn, 0.0); r.end.assign(S, 0.0);
+                std::vector<double> bacc(nSyn, 0.0);
+                auto tb = std::chrono::steady_clock::now();
+                for (long b = 0; b < burnin; ++b) {
+                    const std::vector<occ_t> &x = sampler();
+                    if (batch > 0) {   // relaxation curve only: the burn-in samples enter no statistic
+                        if (b % 16 == 0) {   // the end state of every 16th burn-in sample is enough for a batch mean
+                            ModelState<Agent> endState(x, T, T);
+                            std::valarray<double> syn = FiguresForPaper<G, 1>::synopsis(endState);
+                            for (int d = 0; d < nSyn; ++d) bacc[d] += syn[d];
+                        }
+                        if ((b + 1) % batch == 0) {
+                            for (int d = 0; d < nSyn; ++d) { r.burnMeans.push_back(bacc[d] / (batch / 16)); bacc[d] = 0.0; }
+                        }
+                    }
+                }
+                r.burnSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count();
+                r.burnSteps = sampler.stats.nSamples();
+                std::fill(bacc.begin(), bacc.end(), 0.0);
+                const long s0 = sampler.stats.nSamples();
+                MeanAndVariance mv;
+                auto t0 = std::chrono::steady_clock::now();
+                for (long n = 0; n < nSamples; ++n) {
+                    const std::vector<occ_t> &x = sampler();
+                    ModelState<Agent> endState(x, T, T);
+                    std::valarray<double> syn = FiguresForPaper<G, 1>::synopsis(endState);
+                    mv(syn);
+                    for (int q = 0; q < S; ++q) r.end[q] += endState[q];
+                    for (int d = 0; d < nSyn; ++d) bacc[d] += syn[d];
+                    if (batch > 0 && (n + 1) % batch == 0)
+                        for (int d = 0; d < nSyn; ++d) { r.batchMeans.push_back(bacc[d] / batch); bacc[d] = 0.0; }
+                    if (thin > 0 && n % thin == 0)
+                        for (int d = 0; d < nSyn; ++d) r.series.push_back(int32_t(syn[d]));
+                }
+                r.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                r.steps = sampler.stats.nSamples() - s0;
+                for (int d = 0; d < nSyn; ++d) { r.synSum[d] = mv.sum[d]; r.synSumSq[d] = mv.sumOfSquares[d]; }
+                for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) r.counters.push_back(sampler.stats.nProposals[a][b]);
+                for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) r.counters.push_back(sampler.stats.nAccepted[a][b]);
+                return r;
+            }));
+        for (auto &x : fut) x.wait();
+    }
+    AbmpFile o;
+    std::vector<double> synSum, synSumSq, end, batchMeans, burnMeans, timing, counters;
+    std::vector<int32_t> series;
+    for (auto &x : fut) {
+        Res r = x.get();
+        synSum.insert(synSum.end(), r.synSum.begin(), r.synSum.end());
+        synSumSq.insert(synSumSq.end(), r.synSumSq.begin(), r.synSumSq.end());
+        end.insert(end.end(), r.end.begin(), r.end.end());
+        batchMeans.insert(batchMeans.end(), r.batchMeans.begin(), r.batchMeans.end());
+        burnMeans.insert(burnMeans.end(), r.burnMeans.begin(), r.burnMeans.end());
+        series.insert(series.end(), r.series.begin(), r.series.end());
+        timing.push_back(r.seconds); timing.push_back(double(r.steps)); timing.push_back(r.burnSeconds); timing.push_back(double(r.burnSteps));
+        for (long c : r.counters) counters.push_back(double(c));
+    }
+    o.f64["syn_sum"] = synSum;            // [nThreads][nSyn]
+    o.f64["syn_sumsq"] = synSumSq;
+    o.f64["endstate_sum"] = end;          // [nThreads][S]
+    o.f64["batch_means"] = batchMeans;    // [nThreads][nSamples / batch][nSyn]
+    o.f64["burnin_batch_means"] = burnMeans;   // [nThreads][burnin / batch][nSyn]
+    o.i32["series_thin"] = series;        // [nThreads][ceil(nSamples / thin)][nSyn]
+    o.f64["timing"] = timing;             // [nThreads]{sampling seconds, sampling Metropolis steps, burn-in seconds, burn-in steps}
+    o.f64["counters"] = counters;         // [nThreads][8] nProposals[2][2], nAccepted[2][2] (whole chain)
+    o.f64["meta"] = {double(nThreads), double(nSamples), double(burnin), double(batch), double(thin), double(nSyn), double(S), double(seedBase)};
+    o.write(out);
+    return 0;
+}
+
+// The reference's own diagnostics (diagnostics/ChainStats.h, MultiChainStats.h) on a stored synopsis series
+// (i32 "series" [nSeq][n][d], as written by `series`): every sequence becomes one ChainStats exactly as
+// FiguresForPaper::startStatsThread builds them (nLags = 200, maxLagProportion = 0.5, :89-90), then
+// MultiChainStats::{W, B, varPlus, potentialScaleReduction, effectiveSamples}.  Prints one JSON line; pins diagnostics.py.
+static int cmdRefStats(const AbmpFile &f, int split) {
+    const auto &sh = f.I("shape");
+    const int nSeq = sh[0], n = sh[1], d = sh[2];
+    const auto &ser = f.I("series");
+    MultiChainStats ms(0.0, "refstats");
+    const int parts = split ? 2 : 1, len = n / parts;
+    for (int c = 0; c < nSeq; ++c)
+        for (int h = 0; h < parts; ++h) {
+            std::valarray<std::valarray<double>> samples(std::valarray<double>(0.0, d), len);
+            for (int i = 0; i < len; ++i)
+                for (int k = 0; k < d; ++k) samples[i][k] = ser[(size_t(c) * n + size_t(h) * len + i) * d + k];
+            std::vector<ChainStats> one;
+            one.emplace_back(std::move(samples), 200, 0.5, std::valarray<double>(0.0, 1), MCMCStatistics());
+            ms += std::move(one);
+        }
+    auto pr = [](const char *name, const std::valarray<double> &v, bool last = false) {
+        printf("\"%s\": [", name);
+        for (size_t k = 0; k < v.size(); ++k) printf("%s%.17g", k ? ", " : "", v[k]);
+        printf("]%s", last ? "" : ", ");
+    };
+    printf("{\"n_sequences\": %d, \"n_samples_per_sequence\": %d, \"vario_stride\": %d, ", ms.nChains(), ms.nSamplesPerChain(), ms.front().varioStride);
+    pr("W", ms.W()); pr("B", ms.B()); pr("var_plus", ms.varPlus()); pr("rhat", ms.potentialScaleReduction());
+    pr("mean", ms.mean()); pr("n_eff", ms.effectiveSamples(), true);
+    printf("}\n");
+    return 0;
+}
+
 // The input of TableauNormMinimiser: posterior.constraints (a ConvexPolyhedron, one Constraint per factor:
 // lowerBound <= coefficients . X <= upperBound), exported as CSR in the reference's own entry order, plus the tableau the
 // unmodified TableauNormMinimiser makes of it (timed).  Feeds the parity test of the own basis builder (abm_basis_*).
@@ -719,6 +900,8 @@ static int run(int argc, char **argv) {
                 "  abm_ref bench in.abmp nThreads samplesPerStep warmup steps\n"
                 "  abm_ref marginals in.abmp nThreads nSamples burnin out.abmp\n"
                 "  abm_ref series in.abmp nThreads nSamples burnin out.abmp\n"
+                "  abm_ref posterior in.abmp nThreads nSamples burnin batch thin out.abmp [seedBase]\n"
+                "  abm_ref refstats series.abmp [splitHalves]\n"
                 "  abm_ref constraints in.abmp out.abmp [rebuild: 1 = also time the reference TableauNormMinimiser on them]\n");
         return 2;
     }
@@ -742,6 +925,7 @@ static int run(int argc, char **argv) {
     if (cmd == "experiment3")   // experiment3 problem.abmp marginals.abmp nSamples nBurnin nRejection seed
         return cmdSingleObservationExperiment(argv[2], argv[3], atol(argv[4]), atol(argv[5]), atol(argv[6]), atoi(argv[7]));
     AbmpFile f = AbmpFile::read(argv[2]);
+    if (cmd == "refstats") return cmdRefStats(f, argc > 3 ? atoi(argv[3]) : 0);   // refstats series.abmp [split each sequence in halves]
     int g = f.I("pp_meta")[0];
     if (cmd == "init") { DISPATCH_G(g, cmdInit<G>(f, atoi(argv[3]), atoi(argv[4]), argv[5])); }
     if (cmd == "trace") { DISPATCH_G(g, cmdTrace<G>(f, atoi(argv[3]), atoi(argv[4]), atol(argv[5]), atoi(argv[6]), argv[7])); }
@@ -750,6 +934,9 @@ static int run(int argc, char **argv) {
     if (cmd == "bench") { DISPATCH_G(g, cmdBench<G>(f, atoi(argv[3]), atol(argv[4]), atoi(argv[5]), atoi(argv[6]))); }
     if (cmd == "marginals") { DISPATCH_G(g, cmdMarginals<G>(f, atoi(argv[3]), atol(argv[4]), atol(argv[5]), argv[6])); }
     if (cmd == "constraints") { DISPATCH_G(g, cmdConstraints<G>(f, argv[3], argc > 4 ? atoi(argv[4]) : 0)); }
+    if (cmd == "posterior") {   // posterior in.abmp nThreads nSamples burnin batch thin out.abmp [seedBase]
+        DISPATCH_G(g, cmdPosterior<G>(f, atoi(argv[3]), atol(argv[4]), atol(argv[5]), atol(argv[6]), atol(argv[7]), argv[8], argc > 9 ? atoi(argv[9]) : 0));
+    }
     if (cmd == "series") { DISPATCH_G(g, cmdSeries<G>(f, atoi(argv[3]), atol(argv[4]), atol(argv[5]), argv[6])); }
     fprintf(stderr, "unknown command %s\n", cmd.c_str());
     return 2;

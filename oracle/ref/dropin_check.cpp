@@ -10,6 +10,7 @@
 #include "SparseBasisSampler.h"
 
 #include "abmcmc_b200/gpu_sampler.hpp"
+#include <cmath>
 
 template <int G>
 int run(int T, int nSamples) {
@@ -54,6 +55,33 @@ int run(int T, int nSamples) {
     for (int c = 0; c < 64; ++c)
         if (nSamp[c] != 50) { printf("FAIL: chain %d reports %lld samples\n", c, (long long)nSamp[c]); return 1; }
     gpu.synchronize();
+    // operator() drives ONE chain: on a batched object it must refuse instead of overrunning its one-chain buffers
+    try {
+        gpu();
+        printf("FAIL: operator() on a batched sampler did not throw\n");
+        return 1;
+    } catch (const std::logic_error &) {}
+    // the ensemble moments reduced on the device (abm_chains_get_moments) against the per-chain tables
+    {
+        const int S = PredPreyAgent<G>::domainSize(), d = abm_problem_n_synopsis(gpu.problem());
+        std::vector<int64_t> end(S), ss(size_t(64) * d), sq(size_t(64) * d), ns(64), exact(ABM_MOMENTS_EXACT_HEAD + S);
+        std::vector<double> real(ABM_MOMENTS_REAL);
+        std::vector<abm_mcmc_counters> cn(64);
+        abmcmc::detail::check(abm_chains_get_statistics(gpu.chains(), end.data(), ss.data(), sq.data(), ns.data(), 0), "get_statistics");
+        abmcmc::detail::check(abm_chains_get_counters(gpu.chains(), cn.data()), "get_counters");
+        abmcmc::detail::check(abm_chains_get_moments(gpu.chains(), exact.data(), real.data()), "get_moments");
+        int64_t nTot = 0, prop00 = 0;
+        for (int c = 0; c < 64; ++c) { nTot += ns[c]; prop00 += cn[c].n_proposals[0][0]; }
+        bool ok = exact[0] == 64 && exact[1] == nTot && exact[2] == prop00;
+        for (int k = 0; k < d; ++k) {
+            int64_t a = 0, b = 0;
+            double m = 0.0;
+            for (int c = 0; c < 64; ++c) { a += ss[size_t(c) * d + k]; b += sq[size_t(c) * d + k]; m += double(ss[size_t(c) * d + k]) * (1.0 / double(ns[c])); }
+            ok = ok && exact[10 + k] == a && exact[18 + k] == b && std::fabs(real[k] - m) <= 1e-12 * std::fabs(m);
+        }
+        for (int q = 0; q < S; ++q) ok = ok && exact[ABM_MOMENTS_EXACT_HEAD + q] == end[q];
+        if (!ok) { printf("FAIL: device-reduced moments differ from the per-chain tables\n"); return 1; }
+    }
     std::vector<int8_t> ev(size_t(64) * T * PredPreyAgent<G>::domainSize() * 6);
     abmcmc::detail::check(abm_chains_get_trajectories(gpu.chains(), ev.data()), "get_trajectories");
     size_t ne = ev.size() / 64;
@@ -123,8 +151,68 @@ int runExperiment(int nSamples) {
     return 0;
 }
 
+// Multi-GPU ensemble reduction from a C++ host: `dropin_check moments <rank> <nRanks> <idFile>
+// <outFile>`, one process per GPU.  Rank 0 makes the NCCL id and publishes it through idFile; every rank runs its own batched
+// chains (seed by rank) on device <rank>, reduces them with abm_chains_get_moments (local) and abm_chains_allreduce_moments
+// (all ranks), and writes both vectors to outFile.<rank>; the caller checks all == sum of the locals on every rank.
+#include <fstream>
+#include <unistd.h>
+int runMoments(int rank, int nRanks, const std::string &idFile, const std::string &outFile) {
+    constexpr int G = 8, T = 4;
+    Random::gen.seed(1234);
+    std::streambuf *old = std::cout.rdbuf(nullptr);
+    PredPreyProblem<G> problem(T, 0.05, 0.05, 0.05, 1.0, 10.0);
+    std::vector<ABM::occupation_type> init = problem.prior.nextSample(false);
+    Random::gen.seed(77);
+    abmcmc::GpuSparseBasisSampler<ABM::occupation_type> gpu(problem.tableau, problem.posterior.factors,
+                                                            problem.posterior.perturbableFunctionFactory(), init, problem.kappa, rank);
+    std::cout.rdbuf(old);
+    uint8_t id[ABM_COMM_ID_BYTES];
+    if (rank == 0) {
+        abmcmc::detail::check(abm_comm_unique_id(id), "abm_comm_unique_id");
+        std::ofstream(idFile + ".tmp", std::ios::binary).write(reinterpret_cast<const char *>(id), sizeof id);
+        rename((idFile + ".tmp").c_str(), idFile.c_str());
+    } else {
+        for (int tries = 0; tries < 600; ++tries) {
+            std::ifstream f(idFile, std::ios::binary);
+            if (f.read(reinterpret_cast<char *>(id), sizeof id)) break;
+            usleep(100000);
+            if (tries == 599) { printf("FAIL: no NCCL id from rank 0\n"); return 1; }
+        }
+    }
+    abm_comm *comm = nullptr;
+    abmcmc::detail::check(abm_comm_create(nRanks, rank, id, rank, &comm), "abm_comm_create");
+    gpu.batched(48 + 16 * rank, 1000 + rank);
+    gpu.step(1000);
+    gpu.sample(40 + rank);
+    const int S = PredPreyAgent<G>::domainSize();
+    std::vector<int64_t> local(ABM_MOMENTS_EXACT_HEAD + S), all(ABM_MOMENTS_EXACT_HEAD + S);
+    std::vector<double> localR(ABM_MOMENTS_REAL), allR(ABM_MOMENTS_REAL);
+    abmcmc::detail::check(abm_chains_get_moments(gpu.chains(), local.data(), localR.data()), "get_moments");
+    abmcmc::detail::check(abm_chains_allreduce_moments(gpu.chains(), comm, all.data(), allR.data()), "allreduce_moments");
+    abm_comm_destroy(comm);
+    std::ofstream o(outFile + "." + std::to_string(rank));
+    o.precision(17);
+    for (int64_t v : local) o << v << " ";
+    o << "\n";
+    for (double v : localR) o << v << " ";
+    o << "\n";
+    for (int64_t v : all) o << v << " ";
+    o << "\n";
+    for (double v : allR) o << v << " ";
+    o << "\n";
+    printf("OK: rank %d of %d: %lld chains, %lld samples locally; %lld chains, %lld samples over all ranks\n", rank, nRanks,
+           (long long)local[0], (long long)local[1], (long long)all[0], (long long)all[1]);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 5 && std::string(argv[1]) == "moments") {
+        try { return runMoments(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]); }
+        catch (const std::exception &e) { printf("FAIL: %s\n", e.what()); return 1; }
+    }
     int g = argc > 1 ? atoi(argv[1]) : 8, T = argc > 2 ? atoi(argv[2]) : 4, n = argc > 3 ? atoi(argv[3]) : 300;
+    if (argc > 4) abmcmc::GpuSparseBasisSampler<ABM::occupation_type>::feasibilityBlock() = atol(argv[4]);
     try {
         if (g == 3) return runExperiment(n);
         if (g == 8) return run<8>(T, n);

@@ -26,7 +26,25 @@ def xz(src: Path, dst: Path):
     print(f"{dst.name}: {dst.stat().st_size} bytes")
 
 
+TRACES = [("pp8-4", 11, 101, 20000, 500), ("pp8-4", 12, 102, 20000, 500), ("pp16-8", 12, 202, 20000, 500),
+          ("pp8-4-poisson", 11, 103, 20000, 500), ("exp_pp3-2-single", 31, 301, 20000, 500)]
+
+
+def traces_only():
+    """--traces-only: re-run `abm_ref trace` on the COMMITTED problem fixtures (same seeds, so the step arrays are reproduced
+    bit for bit; used when the trace format gains arrays, e.g. the reference's own end state / synopsis per checkpoint)."""
+    tmp = Path(tempfile.mkdtemp())
+    for name, s0, s1, n, every in TRACES:
+        raw = tmp / f"{name}.abmp"
+        raw.write_bytes(lzma.decompress((HERE / f"{name}.abmp.xz").read_bytes()))
+        out = tmp / f"trace_{name}_{s1}.abmp"
+        subprocess.run([str(REF), "trace", str(raw), str(s0), str(s1), str(n), str(every), str(out)], check=True)
+        xz(out, HERE / f"trace_{name}_{s1}.abmp.xz")
+
+
 def main():
+    if "--traces-only" in sys.argv:
+        return traces_only()
     with32 = "--with-32" in sys.argv
     tmp = Path(tempfile.mkdtemp())
     problems = [(8, 4), (16, 8)] + ([(32, 16)] if with32 else [])
@@ -52,9 +70,7 @@ def main():
         subprocess.run([str(REF), "constraints", str(tmp / f"{name}.abmp"), str(craw), "0"], check=True)
         xz(craw, HERE / f"constraints_{name}.abmp.xz")
     # (problem, initSeed, chainSeed, nSteps, checkpointEvery)
-    traces = [("pp8-4", 11, 101, 20000, 500), ("pp8-4", 12, 102, 20000, 500), ("pp16-8", 12, 202, 20000, 500),
-              ("pp8-4-poisson", 11, 103, 20000, 500)]
-    for name, s0, s1, n, every in traces:
+    for name, s0, s1, n, every in TRACES[:4]:
         raw = tmp / f"trace_{name}_{s1}.abmp"
         subprocess.run([str(REF), "trace", str(tmp / f"{name}.abmp"), str(s0), str(s1), str(n), str(every), str(raw)], check=True)
         xz(raw, HERE / f"trace_{name}_{s1}.abmp.xz")

@@ -69,6 +69,42 @@ def test_reference_golden_trace(prob, trace, n_steps, tree):
 
 
 @pytest.mark.parametrize("tree", TREES)
+@pytest.mark.parametrize("prob,trace", [("pp8-4.abmp.xz", "trace_pp8-4_101.abmp.xz"), ("pp16-8.abmp.xz", "trace_pp16-8_202.abmp.xz"),
+                                        ("pp8-4-poisson.abmp.xz", "trace_pp8-4-poisson_103.abmp.xz")])
+def test_sample_statistics_match_reference(prob, trace, tree):
+    """Row a16 pinned to the reference: a sampling launch fed the reference run's mt19937 stream must accumulate exactly the
+    sums the reference's own statistics pipeline formed over the feasible states of that run -- ModelState(traj,T,T)
+    (ModelState.h:27-36), synopsis() (FiguresForPaper.h:245-263), MeanAndVariance (diagnostics/MeanAndVariance.h:35-45) --
+    which `abm_ref trace` recorded with the reference's code (smp_* arrays of the trace fixtures)."""
+    from oracle.oracle import mt_uniforms
+    S = _gpu()
+    p, t = load_golden(prob), load_golden(trace)
+    n_init, n = int(t["init_iters"][0]), t["tr_j"].size
+    u = mt_uniforms(int(t["seeds"][1]), n_init + 2 * n)
+    P = S.Problem(p, sum_tree=tree)
+    smp = S.SparseBasisSampler(P, t["init_state"], find_feasible=False)
+    smp.findInitialFeasibleSolution(uniforms=u[:n_init + 8].copy())
+    # two launches: the incremental end state must carry over a launch boundary
+    smp.sample_injected(n // 2, u[n_init:n_init + n])
+    smp.sample_injected(n - n // 2, u[n_init + n:n_init + 2 * n])
+    end, ss, sq, ns = smp.statistics()
+    assert int(ns[0]) == int(t["smp_n"][0])
+    assert np.array_equal(end, t["smp_endstate_sum"].astype(np.int64))
+    assert np.array_equal(ss[0], t["smp_syn_sum"].astype(np.int64))
+    assert np.array_equal(sq[0], t["smp_syn_sumsq"].astype(np.int64))
+    assert np.array_equal(smp.state(0)[0], t["XN"])
+    # the device-reduced moments carry the same numbers (abm_chains_get_moments)
+    ex, re = smp.moments()
+    d = ss.shape[1]
+    assert ex[0] == 1 and ex[1] == ns[0] and np.array_equal(ex[2:10], smp.counters()[0])
+    assert np.array_equal(ex[10:10 + d], ss[0]) and np.array_equal(ex[18:18 + d], sq[0]) and np.array_equal(ex[26:], end)
+    mean = ss[0] * (1.0 / ns[0])
+    var = (sq[0] - ss[0].astype(np.float64) * ss[0] * (1.0 / ns[0])) * (1.0 / (ns[0] - 1))
+    assert np.allclose(re[0:d], mean, rtol=1e-14) and np.allclose(re[8:8 + d], mean * mean, rtol=1e-14)
+    assert np.allclose(re[16:16 + d], var, rtol=1e-12)
+
+
+@pytest.mark.parametrize("tree", TREES)
 @pytest.mark.parametrize("prob,n_chains,n_steps", [("pp8-4.abmp.xz", 16, 4000), ("pp16-8.abmp.xz", 6, 3000),
                                                    ("pp16-8-poisson.abmp.xz", 4, 3000)])
 def test_philox_free_running_matches_oracle(prob, n_chains, n_steps, tree):

@@ -89,6 +89,51 @@ def check_trace(p, t):
     assert np.array_equal(bits(c.DE), bits(t["DEN"]))
     assert np.array_equal(bits(c.leaf), bits(t["leafN"]))
     assert np.array_equal(c.counters, t["counters"])
+    check_statistics(p, t)
+
+
+def reference_synopsis(end, G):
+    """FiguresForPaper::synopsis (FiguresForPaper.h:245-263) restated for the checks below: agents of both species inside
+    nested squares of side G/2, G/4, ... > 1 along the diagonal.  end: ModelState, id = x + G y + G^2 type (PredPreyAgent.h:59)."""
+    grid = np.asarray(end).reshape(2, G, G).sum(axis=0)   # [y][x]
+    out, origin, part = [], 0, G // 2
+    while part > 1:
+        out.append(int(grid[origin:origin + part, origin:origin + part].sum()))
+        origin += part
+        part //= 2
+    return out
+
+
+def check_statistics(p, t):
+    """Row a16: the per-sample statistics pinned to what the REFERENCE computed.  The trace carries, from the reference's own
+    ModelState(X,T,T) (ModelState.h:27-36) and synopsis() (FiguresForPaper.h:245-263): the end state and synopsis at every
+    checkpoint, and the sums its statistics pipeline forms over every feasible state of the run (FiguresForPaper.h:93-104).
+    The oracle must reproduce all of them exactly."""
+    if "ck_endstate" not in t or "pp_meta" not in p:
+        return
+    G = int(p["pp_meta"][0])
+    S, every, n = 2 * G * G, int(t["ck_every"][0]), t["tr_j"].size
+    n_syn = len(reference_synopsis(np.zeros(S, np.int64), G))
+    ck_end = t["ck_endstate"].reshape(-1, S)
+    ck_syn = t["ck_synopsis"].reshape(ck_end.shape[0], n_syn)
+    P = OracleProblem(p)
+    c = OracleChain(P, t["init_state"])
+    c.seed_mt(int(t["seeds"][1]))
+    c.find_feasible()
+    for k in range(n // every):
+        c.step(every)
+        assert np.array_equal(c.end_state, ck_end[k])
+        assert reference_synopsis(ck_end[k], G) == ck_syn[k].tolist()   # the restated synopsis against the reference's
+    # the running sums, through the oracle's own statistics loop (orc_chain_sample_stats)
+    c = OracleChain(P, t["init_state"])
+    c.seed_mt(int(t["seeds"][1]))
+    c.find_feasible()
+    end, s1, s2 = np.zeros(S, np.int64), np.zeros(8, np.int64), np.zeros(8, np.int64)
+    taken = c.sample_stats(10 ** 12, n, end, s1, s2)
+    assert taken == int(t["smp_n"][0])
+    assert np.array_equal(end, t["smp_endstate_sum"].astype(np.int64))
+    assert np.array_equal(s1[:n_syn], t["smp_syn_sum"].astype(np.int64))
+    assert np.array_equal(s2[:n_syn], t["smp_syn_sumsq"].astype(np.int64))
 
 
 def test_injected_uniform_stream_equals_mt_stream():
