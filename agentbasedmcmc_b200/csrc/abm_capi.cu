@@ -203,7 +203,6 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
             (colVal[k] < 0 ? xmin[r] : xmax[r]) += colVal[k];
         }
     }
-    if (maxColNnz > 32) return fail(ABM_ERR_INVALID, "columns with more than 32 entries are not supported");
     for (int i = 0; i < nRows; ++i) {
         rowPtr[i + 1] += rowPtr[i];
         if (xmin[i] < -128 || xmax[i] > 127) return fail(ABM_ERR_INVALID, "row value range exceeds int8");
@@ -245,27 +244,80 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
         ++b;
     }
 
-    // lanes per chain: the records are laid out for it (chunks of W coupled columns)
+    // lanes per chain (the records do not depend on it)
     int W = 16;
     if (const char *e = getenv("ABM_GROUP_WIDTH")) W = atoi(e);
     if (W != 8 && W != 16 && W != 32) return fail(ABM_ERR_INVALID, "ABM_GROUP_WIDTH must be 8, 16 or 32");
 
+    // energy tables: energy(i, x) (SparseBasisSampler.h:341-345) of every row class {L, U, factor table}, tabulated over the
+    // values a step can ask for (the row's reachable range widened by the largest entry, for the moves of coupled columns),
+    // with exactly the arithmetic the kernels used to do per evaluation: factor(clamp(x)) - kappa * distance, each operation
+    // rounded once.  A row then carries one 16-bit table base and energy(i, x) is a single load.
+    constexpr int kRowsMax = 24;   // rows per column a record can describe (5 bits of a pair code, 24..31 reserved)
+    if (maxColNnz > kRowsMax) return fail(ABM_ERR_INVALID, "columns with more than 24 entries are not supported");
+    std::vector<double> eTab(256, 0.0);
+    std::vector<int32_t> rowEBase(nRows);
+    {
+        struct Cls { long L, U; int id; long lo, hi; std::vector<int> rows; };
+        std::vector<Cls> classes;
+        std::vector<int> clsOf(nRows);
+        for (int i = 0, b = 0; i < nTab; ++i) {
+            if (rowOf[i] < 0) continue;
+            const long L = desc->tab_L[i], U = desc->tab_U[i];
+            const int id = desc->fac_id[b];
+            int c = -1;
+            for (size_t q = 0; q < classes.size(); ++q)
+                if (classes[q].L == L && classes[q].U == U && classes[q].id == id) { c = int(q); break; }
+            if (c < 0) { classes.push_back({L, U, id, xmin[b], xmax[b], {}}); c = int(classes.size()) - 1; }
+            classes[c].lo = std::min(classes[c].lo, xmin[b]);
+            classes[c].hi = std::max(classes[c].hi, xmax[b]);
+            clsOf[b] = c;
+            ++b;
+        }
+        std::vector<int> base(classes.size());
+        const long margin = maxAbs + 1;
+        for (size_t q = 0; q < classes.size(); ++q) {
+            const Cls &c = classes[q];
+            const long clo = c.lo - margin, chi = c.hi + margin;
+            const long b0 = long(eTab.size()) - clo;   // energy(x) = eTab[b0 + x]
+            if (b0 < 0 || b0 + chi >= 65536 + 128) return fail(ABM_ERR_INVALID, "energy tables too large");
+            base[q] = int(b0);
+            const int lo = desc->ut_lo[c.id], len = desc->ut_off[c.id + 1] - desc->ut_off[c.id];
+            for (long x = clo; x <= chi; ++x) {
+                const long cl = std::max(c.L, std::min(x, c.U));
+                const long dist = x < c.L ? c.L - x : (x > c.U ? x - c.U : 0);
+                const long idx = std::min<long>(std::max<long>(cl - lo, 0), len - 1);   // outside the table: unreachable values only
+                volatile double f = desc->ut_val[desc->ut_off[c.id] + idx];
+                volatile double pen = desc->kappa * double(dist);
+                volatile double e = f - pen;
+                eTab.push_back(double(e));
+            }
+        }
+        for (int b = 0; b < nRows; ++b) {
+            rowEBase[b] = base[clsOf[b]];
+            if (rowEBase[b] < 0 || rowEBase[b] > 65535) return fail(ABM_ERR_INVALID, "energy table base out of range");
+        }
+        eTab.insert(eTab.end(), 256, 0.0);
+    }
+
     // column records (layout: abm_device.h)
-    std::vector<int4> recIdx(nCols);
-    std::vector<int32_t> rec;
-    rec.reserve((size_t)nnz * 24);
+    std::vector<uint2> recIdx(nCols);
+    std::vector<uint32_t> rec;
+    rec.reserve((size_t)nnz * 12);
     int maxCoupled = 1, maxTasks = 1, maxSF = 0, maxTA = 1, maxTB = 1, maxTC = 1;
     struct Pair { int u, k, m; };
     std::vector<Pair> pairs;
-    std::vector<int32_t> slotU, chunkHdr, staleF, nodes, endFx;
+    std::vector<int32_t> staleF, nodes, endFx;
+    std::vector<uint32_t> slots, xtra;
     int nSyn = 0;
     for (int ps = G / 2; ps > 1; ps /= 2) ++nSyn;   // FiguresForPaper.h:246-249
     if (nSyn > 8) return fail(ABM_ERR_INVALID, "more than 8 synopsis statistics");
-    std::vector<uint16_t> contrib;
     std::vector<char> seen(std::max(nStates, 1), 0);
+    auto pairCode = [](int k, int m) { return uint32_t(k | ((m > 0 ? m - 1 : 4 + (-m - 1)) << 5)); };   // 5 bits row, 3 bits entry
+    size_t maxRecWords = 0;
     for (int j = 0; j < nCols; ++j) {
         while (rec.size() % 4) rec.push_back(0);
-        const uint32_t recStart = uint32_t(rec.size() / 4);
+        const size_t recStart = rec.size();
         const int n = colPtr[j + 1] - colPtr[j];
         pairs.clear();
         pairs.push_back({j, -1, 0});   // the proposed column itself (changedDE[j] = -currentDE[j], :294)
@@ -275,48 +327,41 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
                 if (rowCol[r] != j) pairs.push_back({rowCol[r], k, rowVal[r]});
         }
         std::stable_sort(pairs.begin(), pairs.end(), [](const Pair &a, const Pair &b) { return a.u < b.u || (a.u == b.u && a.k < b.k); });
-        // distinct columns ascending, each with its shared rows in row order
-        slotU.clear();
-        std::vector<std::pair<size_t, size_t>> runs;
+        // distinct columns ascending, each with its shared rows in row order: one 32-bit slot per column
+        // {u - uBase (16 bits) | first shared row | second shared row}; a column sharing more than two rows points into `xtra`
+        slots.clear();
+        xtra.clear();
+        nodes.clear();
+        const int uBase = pairs.front().u;
+        // a column whose coupled columns span more than 16 bits of ids (64x64 grids) gets WIDE slots: the id in a word of its own
+        const bool wide = pairs.back().u - uBase > 0xffff;
         for (size_t a2 = 0; a2 < pairs.size();) {
             size_t b2 = a2;
             while (b2 < pairs.size() && pairs[b2].u == pairs[a2].u) ++b2;
-            slotU.push_back(pairs[a2].u);
-            runs.push_back({a2, b2});
+            const int u = pairs[a2].u, cnt = pairs[a2].k < 0 ? 0 : int(b2 - a2);
+            if (wide) slots.push_back(uint32_t(u));
+            uint32_t w = wide ? 0u : uint32_t(u - uBase);
+            if (cnt <= 2) {
+                w |= (cnt >= 1 ? pairCode(pairs[a2].k, pairs[a2].m) : 0xffu) << 16;
+                w |= (cnt >= 2 ? pairCode(pairs[a2 + 1].k, pairs[a2 + 1].m) : 0xffu) << 24;
+            } else {
+                if (xtra.size() > 255) return fail(ABM_ERR_INVALID, "too many columns sharing more than two rows with one column");
+                w |= 0xfeu << 16 | uint32_t(xtra.size()) << 24;
+                // list: count, then the pair codes, four per word
+                std::vector<uint32_t> bytes{uint32_t(cnt)};
+                for (int t = 0; t < cnt; ++t) bytes.push_back(pairCode(pairs[a2 + t].k, pairs[a2 + t].m));
+                while (bytes.size() % 4) bytes.push_back(0xff);
+                for (size_t q = 0; q < bytes.size(); q += 4) xtra.push_back(bytes[q] | bytes[q + 1] << 8 | bytes[q + 2] << 16 | bytes[q + 3] << 24);
+            }
+            slots.push_back(w);
+            int a3 = u;
+            nodes.push_back(a3);
+            while (a3) { a3 &= a3 - 1; nodes.push_back(a3); }
             a2 = b2;
         }
-        const int C = int(slotU.size());
-        const int nChunks = (C + W - 1) / W;
+        const int C = int(slots.size()) / (wide ? 2 : 1);
         maxCoupled = std::max(maxCoupled, C);
-        slotU.resize(size_t(nChunks) * W, -1);
-        chunkHdr.assign(nChunks, 0);
-        contrib.clear();
-        for (int c = 0; c < nChunks; ++c) {
-            int maxCnt = 0;
-            for (int q = 0; q < W; ++q) {
-                const int l = c * W + q;
-                if (l < C && pairs[runs[l].first].k >= 0) maxCnt = std::max(maxCnt, int(runs[l].second - runs[l].first));
-            }
-            if (contrib.size() >= (1u << 23)) return fail(ABM_ERR_INVALID, "contribution table of a column too large");
-            chunkHdr[c] = maxCnt | int32_t(contrib.size() << 8);
-            for (int t = 0; t < maxCnt; ++t)
-                for (int q = 0; q < W; ++q) {
-                    const int l = c * W + q;
-                    uint16_t v = kNoContrib;
-                    if (l < C && pairs[runs[l].first].k >= 0 && t < int(runs[l].second - runs[l].first)) {
-                        const Pair &pr = pairs[runs[l].first + t];
-                        v = uint16_t((pr.k & 0xff) | ((pr.m & 0xff) << 8));
-                    }
-                    contrib.push_back(v);
-                }
-        }
-        // distinct tree nodes a commit of this column touches (sizes the task list)
-        nodes.clear();
-        for (int l = 0; l < C; ++l) {
-            int a2 = slotU[l];
-            nodes.push_back(a2);
-            while (a2) { a2 &= a2 - 1; nodes.push_back(a2); }
-        }
+        // distinct tree nodes a commit of this column touches (sizes the reference tree's task list)
         std::sort(nodes.begin(), nodes.end());
         {
             const int nn = int(std::unique(nodes.begin(), nodes.end()) - nodes.begin());
@@ -348,36 +393,29 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
         }
         if (staleF.size() > 255) return fail(ABM_ERR_INVALID, "too many stale factors for one column");
         maxSF = std::max(maxSF, int(staleF.size()));
-        const size_t base = rec.size();
-        const size_t contribWord = size_t(4) * n + nChunks + slotU.size();
-        const size_t staleWord = contribWord + (contrib.size() + 1) / 2;
-        if (staleWord >= 65536) return fail(ABM_ERR_INVALID, "column record too large");
         int nEv = 0;
         for (int k = 0; k < n; ++k) nEv += colRow[colPtr[j] + k] < nEvents;
         for (int k = 0; k < nEv; ++k)
             if (colRow[colPtr[j] + k] >= nEvents) return fail(ABM_ERR_INVALID, "internal: event rows are not leading");
-        if (nChunks >= 65536) return fail(ABM_ERR_INVALID, "too many coupled columns");
+        if (C > 2040) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2040 others");
         bool touchesEnd = false;
         for (int k = 0; k < nEv; ++k) touchesEnd = touchesEnd || colRow[colPtr[j] + k] >= (T - 1) * S * kActs;
-        recIdx[j] = make_int4(int32_t(recStart), n | (int32_t(staleF.size()) << 8) | (C << 16),
-                              int32_t(uint32_t(nChunks) | (uint32_t(nEv) << 16) | (touchesEnd ? 0x80000000u : 0u)),
-                              int32_t(uint32_t(contribWord) | (uint32_t(staleWord) << 16)));
+        // header (4 words), rows (2 words each), stale factors, slots, extra pair lists, end-state effects
+        rec.push_back(uint32_t(n) | uint32_t(staleF.size()) << 8 | uint32_t(C) << 16);
+        if (xtra.size() > 0x3fff) return fail(ABM_ERR_INVALID, "pair lists of one column too long");
+        rec.push_back(uint32_t(nEv) | uint32_t(xtra.size()) << 8 | (wide ? 0x40000000u : 0u) | (touchesEnd ? 0x80000000u : 0u));
+        rec.push_back(uint32_t(uBase));
+        rec.push_back(0);
         for (int k = 0; k < n; ++k) {
             const int i = colRow[colPtr[j] + k];
             const int4 rp = rowParam[i];
-            rec.push_back((rp.x & 0xffffff) | (colVal[colPtr[j] + k] << 24));
-            rec.push_back(rp.y);
-            rec.push_back(rp.z);
-            rec.push_back(rp.w);
+            const long L8 = std::max<long>(-128, std::min<long>(127, rp.y)), U8 = std::max<long>(-128, std::min<long>(127, rp.z));
+            rec.push_back(uint32_t(rp.x & 0xffffff) | uint32_t(colVal[colPtr[j] + k] & 0xff) << 24);
+            rec.push_back(uint32_t(rowEBase[i]) | uint32_t(L8 & 0xff) << 16 | uint32_t(U8 & 0xff) << 24);
         }
-        rec.insert(rec.end(), chunkHdr.begin(), chunkHdr.end());
-        rec.insert(rec.end(), slotU.begin(), slotU.end());
-        for (size_t q = 0; q < contrib.size(); q += 2) {
-            const uint32_t lo16 = contrib[q], hi16 = q + 1 < contrib.size() ? contrib[q + 1] : 0;
-            rec.push_back(int32_t(lo16 | (hi16 << 16)));
-        }
-        rec.insert(rec.end(), staleF.begin(), staleF.end());
-        if (rec.size() - base != staleWord + staleF.size()) return fail(ABM_ERR_INVALID, "internal: record layout");
+        for (int sid : staleF) rec.push_back(uint32_t(sid));
+        rec.insert(rec.end(), slots.begin(), slots.end());
+        rec.insert(rec.end(), xtra.begin(), xtra.end());
         // static end-state effect of the column (MODE_SAMPLE), per unit of delta_j: which states of ModelState(traj,T,T) its
         // events of the last timestep feed (PredPreyAgent::consequences, PredPreyAgent.h:98-115) and what that adds to the
         // synopsis squares (FiguresForPaper.h:245-263)
@@ -404,19 +442,23 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
                     }
                 }
             }
-            rec.push_back(int32_t(endFx.size()));
+            rec.push_back(uint32_t(endFx.size()));
             for (int w = 0; w < 2; ++w) {
                 uint32_t pk = 0;
                 for (int z = 0; z < 4; ++z) pk |= uint32_t(synD[4 * w + z] & 0xff) << (8 * z);
-                rec.push_back(int32_t(pk));
+                rec.push_back(pk);
             }
-            rec.insert(rec.end(), endFx.begin(), endFx.end());
+            for (int32_t v : endFx) rec.push_back(uint32_t(v));
         }
-        if (rec.size() / 4 > 0xfffffff0ull) return fail(ABM_ERR_INVALID, "record table too large");
+        while (rec.size() % 4) rec.push_back(0);
+        const size_t words = rec.size() - recStart;
+        maxRecWords = std::max(maxRecWords, words);
+        if (recStart / 4 > 0xfffffff0ull || words * 4 > 0xffffu * 16u) return fail(ABM_ERR_INVALID, "record table too large");
+        recIdx[j] = make_uint2(uint32_t(recStart / 4), uint32_t(words * 4));   // {offset in 16-byte units, bytes (multiple of 16)}
     }
-    while (rec.size() % 4) rec.push_back(0);
-    rec.insert(rec.end(), 64, 0);   // lanes read a record's last list one chunk at a time, past its end
-    if (maxCoupled > 2040) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2040 others");
+    rec.insert(rec.end(), 64, 0);   // speculative reads past a record's last list stay inside the table
+    if (getenv("ABM_VERBOSE")) fprintf(stderr, "abm: %d column records, %.1f MB (+ %.1f MB index), longest %zu bytes; energy tables %zu entries\n", nCols,
+                                       rec.size() * 4e-6, recIdx.size() * 8e-6, maxRecWords * 4, eTab.size());
 
     // [7] lgamma(occ+1), [2][2][6] log(pi/pibar), then the factor log-probability of TrajectoryImportance::refresh
     // (TrajectoryImportance.h:96-108) for every (type, neighbour flag, set of present acts), summed in the reference's order
@@ -466,17 +508,22 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     d.maxAbs = maxAbs;
     d.twoM = 2 * maxAbs;
     d.scrCap = 0;
-    d.nodeCap = (d.blockedTree && !ABM_PHILOX_BLOCK) ? 0 : 32;
+    d.nodeCap = d.blockedTree ? 0 : 32;
     d.t2Cap = 0;
-    if (d.blockedTree) {
+    // the compile-time shared-memory layout (stepKernel<..., FIX>): blocked tree, 16 lanes per chain, unit entries, sizes within
+    // its constants -- true of the paper's PredPrey problems at every size; ABM_FIX_LAYOUT=0 forces the run-time layout
+    d.fixLayout = d.blockedTree && W == 16 && maxAbs == 1 && d.rowsCap <= kFixRowsCap && d.sCap <= kFixSCap && !ABM_T2_SMEM && !ABM_SMEM_SCRATCH;
+    if (const char *e = getenv("ABM_FIX_LAYOUT")) if (!atoi(e)) d.fixLayout = 0;
+    if (d.fixLayout) { d.rowsCap = kFixRowsCap; d.sCap = kFixSCap; }
+    if (d.blockedTree && !d.fixLayout) {
         // what 7 resident CTAs per SM leave to one chain (228 KB per SM, 1 KB reserved per CTA), after the fixed arrays
         const int chainsPerCta = kWarpsPerCta * (32 / W);
         const int budget = (((228 * 1024) / 7 - 1024) / chainsPerCta) & ~15;
 #if ABM_T2_SMEM
-        if (groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs, d.nodeCap, d.t2Len) <= budget) d.t2Cap = d.t2Len;
+        if (groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs, d.nodeCap, d.t2Len, 0) <= budget) d.t2Cap = d.t2Len;
 #endif
 #if ABM_SMEM_SCRATCH
-        const int room = (budget - groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs, d.nodeCap, d.t2Cap)) / 16;
+        const int room = (budget - groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs, d.nodeCap, d.t2Cap, 0)) / 16;
         d.scrCap = std::max(0, std::min(room, d.sCap + W - 1) / W * W);
 #endif
     }
@@ -491,14 +538,14 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     inf.chain_state_bytes = chainStateBytes(d);
     if (hostOnly) {   // what the uploads below would occupy
         auto bytes = [](const auto &v) { return int64_t(v.size() * sizeof(v[0])); };
-        inf.shared_bytes = bytes(recIdx) + bytes(rec) + bytes(facVal) + bytes(impTab) + bytes(colPtr) + bytes(colRow) + bytes(colVal) +
+        inf.shared_bytes = bytes(recIdx) + bytes(rec) + bytes(facVal) + bytes(eTab) + bytes(impTab) + bytes(colPtr) + bytes(colRow) + bytes(colVal) +
                            bytes(rowPtr) + bytes(rowCol) + bytes(rowVal) + bytes(rowF) + bytes(rowParam) + bytes(colEvent);
         *hostOnly = inf;
         return ABM_OK;
     }
     cudaError_t e = cudaSuccess;
     auto up = [&](auto **dst, const auto &v) { if (e == cudaSuccess) e = p->arena.upload(dst, v); };
-    up(&d.recIdx, recIdx); up(&d.rec, rec); up(&d.facVal, facVal); up(&d.impTab, impTab);
+    up(&d.recIdx, recIdx); up(&d.rec, rec); up(&d.facVal, facVal); up(&d.eTab, eTab); up(&d.impTab, impTab);
     up(&d.colPtr, colPtr); up(&d.colRow, colRow); up(&d.colVal, colVal);
     up(&d.rowPtr, rowPtr); up(&d.rowCol, rowCol); up(&d.rowVal, rowVal);
     up(&d.rowF, rowF); up(&d.rowParam, rowParam); up(&d.colEvent, colEvent);
@@ -662,22 +709,32 @@ int abm_chains_init_from_prior(abm_chains *c, const double *actPmf, double pPred
 
 }  // extern "C" (templates below need C++ linkage)
 
-template <int MODE, int W, bool BLK>
-static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
+template <int MODE, int W, bool BLK, bool FIX>
+static cudaError_t launchStepWBF(const abm_chains *c, const RunParams &r) {
     const DevProblem &P = c->p->d;
     constexpr int NG = 32 / W;
     const int chainsPerCta = kWarpsPerCta * NG;
     const int grid = (c->n + chainsPerCta - 1) / chainsPerCta;
-    const size_t smem = size_t(chainsPerCta) * groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs, P.nodeCap, P.t2Cap);
-    cudaError_t e = cudaFuncSetAttribute(stepKernel<MODE, W, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    const size_t smem = size_t(chainsPerCta) * (FIX ? groupSmemBytes(kFixRowsCap, kFixSCap, 0, 0, 1, 0, 0, 0)
+                                                    : groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs, P.nodeCap, P.t2Cap, BLK ? 0 : P.sCap));
+    auto kernel = stepKernel<MODE, W, BLK, FIX>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     static const int carveout = getenv("ABM_SMEM_CARVEOUT") ? atoi(getenv("ABM_SMEM_CARVEOUT")) : -1;   // measurement switch: percent of
     if (carveout >= 0) {                                                                              // the L1/shared array given to shared memory
-        e = cudaFuncSetAttribute(stepKernel<MODE, W, BLK>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
         if (e != cudaSuccess) return e;
     }
-    stepKernel<MODE, W, BLK><<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);
+    kernel<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P, c->d, r);
     return cudaGetLastError();
+}
+
+template <int MODE, int W, bool BLK>
+static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
+    if constexpr (BLK && W == 16) {
+        if (c->p->d.fixLayout) return launchStepWBF<MODE, W, BLK, true>(c, r);
+    }
+    return launchStepWBF<MODE, W, BLK, false>(c, r);
 }
 
 template <int MODE, int W>

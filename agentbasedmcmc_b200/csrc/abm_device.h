@@ -24,18 +24,21 @@ namespace abm {
 
 constexpr int kActs = 6;            // PredPreyAgentBase::actDomainSize(), PredPreyAgent.h:46
 constexpr int kStateBytes = 8;      // bytes reserved per agent state in Xb (6 acts + 2 pad)
-constexpr int kNoContrib = 0xffff;  // empty slot in a contribution plane
 
-// Record of column j (int32 words; W = lanes per chain the problem was built for).  Its header lives in recIdx[j]:
-//   n | nSF << 8 | C << 16     rows in the column; stale factors; coupled columns incl. j itself
-//   nChunks = ceil(C / W)
-//   word offsets (from the record start) of the contribution planes and of the stale-factor list
-//   rows:     n x {xoff | m << 24, L, U, tabBase}
-//   chunkHdr: nChunks x (maxCnt | contribOffset16 << 8)   maxCnt = most shared rows of a column in the chunk
-//   slotU:    nChunks*W x u, ascending, padded with -1
-//   contrib:  per chunk, maxCnt planes of W uint16 {k | m_u << 8} (row k of the column, entry M_{i_k,u}),
-//             plane t holding each slot's t-th shared row in ascending row order; kNoContrib = none
-//   staleF:   nSF x state id, TrajectoryImportance::perturb insertion order, de-duplicated
+// Record of column j: 32-bit words, 16-byte aligned, contiguous, independent of the lanes per chain.  recIdx[j] = {offset in
+// 16-byte units, bytes}.  The step kernel copies the head of a record into shared memory with ONE bulk asynchronous copy
+// (cp.async.bulk, completion on an mbarrier) and parses it there.
+//   w0: n | nSF << 8 | C << 16      rows in the column; stale factors; coupled columns incl. j itself
+//   w1: nEv | nXtra << 8 | wide << 30 | touchesEnd << 31    leading rows that are events; words of extra pair lists;
+//       wide: slots are two words {u, 0 | pair0 << 16 | pair1 << 24} (coupled ids spanning more than 16 bits: 64x64 grids)
+//   w2: uBase                       lowest coupled column id;  w3: reserved
+//   rows:   n x {xoff | M_ij << 24,  eBase | L8 << 16 | U8 << 24}     energy(i, x) = eTab[eBase + x]; bounds clamped to int8
+//   staleF: nSF x state id, TrajectoryImportance::perturb insertion order, de-duplicated
+//   slots:  C x {u - uBase | pair0 << 16 | pair1 << 24}, u ascending; pair = k | code(M_iu) << 5 (row k of the column),
+//           0xff = none; pair0 == 0xfe: the column shares more than two rows, pair1 = word index of its list in xtra
+//   xtra:   lists {count, pair codes ...}, one byte each, padded to words
+//   end-state effects (only if touchesEnd): nEnd, 8 x int8 synopsis change, nEnd x (state | entry << 24)
+constexpr int kPairNone = 0xff, kPairExt = 0xfe;
 struct DevProblem {
     int nRows, nCols, nEvents, xStride;
     int treeDepth;          // D = bit length of nCols-1
@@ -54,10 +57,12 @@ struct DevProblem {
     int scrCap;                // blocked tree: leading coupled columns whose staged {DE', leaf} stay in shared memory (multiple of W)
     int tCapA, tCapB;          // task-list regions: levels >= 10, levels 5..9 (the rest of tCap: levels < 5)
     int nSynopsis;
+    int fixLayout;             // 1: the compile-time shared-memory layout of stepKernel<..., FIX> applies (rowsCap / sCap are its constants)
     double kappa;
-    const int4 *recIdx;     // [nCols] {record offset / 4 words, n | nSF<<8 | C<<16, nChunks, contrib word | stale word << 16}
-    const int32_t *rec;
-    const double *facVal;   // de-duplicated factor tables
+    const uint2 *recIdx;    // [nCols] {record offset in 16-byte units, record bytes}
+    const uint32_t *rec;
+    const double *eTab;     // energy tables of the row classes (step kernel)
+    const double *facVal;   // de-duplicated factor tables (construction kernels)
     const double *impTab;   // [7] lgamma table, then [2][2][6] log ratios
     // construction only
     const int32_t *colPtr, *colRow, *colVal;   // CSR by column (sampler row ids)

@@ -24,15 +24,10 @@ constexpr int kWarpsPerCta = 4;
 #define ABM_IMP_EARLY 0
 #endif
 constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
-// ABM_PHILOX_BLOCK: the lanes of a group draw the Philox blocks of the chain's next min(W,16) iterations at once (one
-// iteration per lane) instead of every lane repeating the block of the current one; same counters, same uniforms.
+// ABM_PHILOX_BLOCK: the lanes of a group draw the Philox blocks of the chain's next W iterations at once (one iteration per
+// lane, handed over by shuffles) instead of every lane repeating the block of the current one; same counters, same uniforms.
 #ifndef ABM_PHILOX_BLOCK
-#define ABM_PHILOX_BLOCK 0
-#endif
-// ABM_PREFETCH: the first coupled-column chunks' lists (1) and the first stale factors (2) are requested together with
-// the column's rows, so these record reads share one memory round trip instead of following each other.
-#ifndef ABM_PREFETCH
-#define ABM_PREFETCH 3
+#define ABM_PHILOX_BLOCK 1
 #endif
 // ABM_SMEM_SCRATCH: blocked tree: the {DE', leaf} pairs a step stages for its commit stay in shared memory for as many
 // leading coupled columns as 7 resident CTAs per SM leave room for (abm_problem_create sizes it); the rest goes through
@@ -47,6 +42,37 @@ constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 // accepted and applied after the commit (its round trip overlaps the commit) instead of through an out-of-line call.
 #ifndef ABM_END_DEFERRED
 #define ABM_END_DEFERRED 1
+#endif
+// ---- measurement switches of the record path (A/B runs of round 2, 32x32x16, 8192 chains, one B200; profiles/r2_ab_*.log)
+// ABM_PIN_IDS: lane / chain ids made opaque to the compiler so that it keeps them instead of re-deriving them from the
+// special registers inside the loop (fewer instructions, but the extra live registers spill: 473 M vs 489 M steps/s)
+#ifndef ABM_PIN_IDS
+#define ABM_PIN_IDS 0
+#endif
+// ABM_REC_BULK: the record window is filled by ONE bulk asynchronous copy (cp.async.bulk, completion on an mbarrier:
+// SASS UBLKCP / SYNCS) instead of two LDG.128 + STS.128 per lane.  Measured slower here (465 M vs 489 M steps/s): the copy
+// engine's latency sits on the dependent chain of a step (column draw -> record -> chain state) and nothing can overlap it.
+#ifndef ABM_REC_BULK
+#define ABM_REC_BULK 0
+#endif
+// ABM_REC_EVICT_LAST (with ABM_REC_BULK): the bulk copy carries an L2 evict_last hint; ABM_STATE_EVICT_FIRST: coupled-column
+// state loads carry an evict_first hint.  Neither changed the L2 hit rate enough to matter (465 / 457 M).
+#ifndef ABM_REC_EVICT_LAST
+#define ABM_REC_EVICT_LAST 0
+#endif
+#ifndef ABM_STATE_EVICT_FIRST
+#define ABM_STATE_EVICT_FIRST 0
+#endif
+// ABM_PF_CHUNKS: with the whole coupled-column list in the shared-memory window, the chain state of EVERY later chunk is
+// prefetched (1: into L2, 2: into L1) as soon as the record has arrived; the chunk loop then finds it on chip instead of
+// exposing a DRAM round trip per chunk.  Costs no registers.  481 -> 489 M steps/s.
+#ifndef ABM_PF_CHUNKS
+#define ABM_PF_CHUNKS 1
+#endif
+// ABM_PF_IMP: the trajectory words the importance change will read (own state and the four neighbours of each stale factor)
+// are prefetched into L2 when the record has arrived; the reads themselves follow the coupled columns (489 -> 491 M)
+#ifndef ABM_PF_IMP
+#define ABM_PF_IMP 1
 #endif
 #ifndef ABM_UNIT_ONLY
 #define ABM_UNIT_ONLY 0
@@ -113,6 +139,58 @@ __device__ __forceinline__ double energyOf(int x, int L, int U, int tabBase, con
 __device__ __forceinline__ int infeasOf(int x, int L, int U) { return x < L ? L - x : (x > U ? x - U : 0); }
 
 __device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// ------------------------------------------------------------------------------------------------
+// Record fetch: one bulk asynchronous copy per proposal (cp.async.bulk: global -> shared memory by the copy engine, no
+// registers, no per-lane address arithmetic) whose completion is counted in bytes on an mbarrier in shared memory.
+constexpr int kRecWinWords = 128, kRecWinBytes = kRecWinWords * 4;   // the head of a record that is staged in shared memory
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void barInit(unsigned long long *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    const uint32_t b = smemAddr(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)), "l"(src),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+}
+// the same copy with an L2 eviction-priority hint (createpolicy): the record table is what every chain re-reads
+__device__ __forceinline__ unsigned long long policyEvictLast() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulkLoadHint(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long pol) {
+    const uint32_t b = smemAddr(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smemAddr(dst)),
+                 "l"(src), "r"(bytes), "r"(b), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned long long policyEvictFirst() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldHint(const double2 *p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void barWait(unsigned long long *bar, unsigned phase) {
+    const uint32_t b = smemAddr(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ABM_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra ABM_WAIT_%=;\n"
+        "}\n" ::"r"(b),
+        "r"(phase)
+        : "memory");
+}
 
 // One out-of-line copy of exp(): the step kernel is bounded by instruction fetch as much as by anything else.
 __device__ __noinline__ double expShared(double x) { return exp(x); }
@@ -193,10 +271,10 @@ __device__ __forceinline__ int groupInclusiveScan(int v, int gl) {
 __device__ __forceinline__ int warpMax(int v) { return __reduce_max_sync(kFull, v); }
 
 // Blocked sum tree: one 32-ary level.  32 entries are spread over the W lanes of a group (lane gl holds entries gl*NG ..
-// gl*NG+NG-1); they are consumed from the highest index down: entry e owns [sum_{e'>e} v, sum_{e'>=e} v).  Returns the
-// entry that owns `target` and rebases target to the start of that entry's interval.
+// gl*NG+NG-1); they are consumed from the highest index down: entry e owns [sum_{e'>e} v, sum_{e'>=e} v).
+// suffixScan: sfx = sum of the entries held by lanes >= gl (the group's total in lane 0).
 template <int W>
-__device__ __forceinline__ int selectDescending(const double (&v)[32 / W], double &target, int gl) {
+__device__ __forceinline__ double suffixScan(const double (&v)[32 / W], int gl) {
     constexpr int NG = 32 / W;
     double own = 0.0;
 #pragma unroll
@@ -207,9 +285,15 @@ __device__ __forceinline__ int selectDescending(const double (&v)[32 / W], doubl
         const double t = __shfl_down_sync(kFull, sfx, o, W);
         if (gl + o < W) sfx = __dadd_rn(sfx, t);
     }
+    return sfx;
+}
+// Returns the entry that owns `target` and rebases target to the start of that entry's interval.
+template <int W>
+__device__ __forceinline__ int selectFromScan(const double (&v)[32 / W], double sfx, double &target, int gl, int gBase) {
+    constexpr int NG = 32 / W;
     const double aboveRaw = __shfl_down_sync(kFull, sfx, 1, W);
     const double above = gl + 1 < W ? aboveRaw : 0.0;             // entries held by higher lanes
-    const unsigned hits = (__ballot_sync(kFull, target < sfx) >> ((threadIdx.x & 31) & ~(W - 1))) & (W == 32 ? 0xffffffffu : ((1u << W) - 1u));
+    const unsigned hits = (__ballot_sync(kFull, target < sfx) >> gBase) & (W == 32 ? 0xffffffffu : ((1u << W) - 1u));   // gBase: the group's first lane
     const int winner = hits ? 31 - __clz(hits) : 0;               // highest lane whose suffix exceeds the target
     int e = gl * NG;                                               // rounding fallback: the lane's lowest entry
     double start = above;
@@ -227,12 +311,17 @@ __device__ __forceinline__ int selectDescending(const double (&v)[32 / W], doubl
     target = hits ? fmax(__dsub_rn(target, start), 0.0) : 0.0;
     return e;
 }
+template <int W>
+__device__ __forceinline__ int selectDescending(const double (&v)[32 / W], double &target, int gl, int gBase) {
+    return selectFromScan<W>(v, suffixScan<W>(v, gl), target, gl, gBase);
+}
 
 // Bytes of shared memory one chain (group) needs; must match the carve-up in stepKernel.
 // nodeCap: 32 doubles of descent / summation staging (reference tree; 0 for the blocked tree); t2Cap: the blocked tree's sums of
 // 1024 leaves when they are kept in shared memory for the launch (0 otherwise)
-__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs, int nodeCap, int t2Cap) {
-    return (scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + sCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
+// suCap: the coupled-column ids of a step (reference tree: sCap; the blocked tree reads them from the record window: 0)
+__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs, int nodeCap, int t2Cap, int suCap) {
+    return (kRecWinBytes + 16 + scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + 8 + 8 * 4 + suCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
 }
 
 // MODE_SAMPLE: an accepted proposal (dj != 0) with events in the last timestep moves the end state ModelState(traj,T,T).
@@ -271,34 +360,63 @@ __device__ __noinline__ void recordSeries(int32_t *series, int seriesThin, int s
 // [sum_{i>j} p_i, sum_{i>=j} p_i)).  The same uniform then selects the same column except when it falls within rounding
 // distance (~1e-13 relative) of a boundary; get(u) is the exact leaf instead of the reference's drifting difference of
 // sums.  An update touches 3 nodes instead of 1 + popcount(u), which removes most of the commit work and traffic.
-template <int MODE, int W, bool BLK>
+// FIX: the per-chain shared-memory layout is fixed at compile time (kFixRowsCap rows, kFixSCap coupled columns, unit tableau
+// entries, blocked tree): every array is then a constant offset from one base register and the per-row tables have constant
+// strides.  With the layout taken from the problem at run time the compiler re-derives the eleven array pointers inside the
+// step loop (12 % of all instructions, profiles/r1d_*).  abm_problem_create selects it whenever the problem fits, which the
+// paper's PredPrey problems do; anything else runs the same code with the run-time layout.
+constexpr int kFixRowsCap = 24, kFixSCap = 176;
+template <int MODE, int W, bool BLK, bool FIX = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P, DevChains S, RunParams R) {
+    static_assert(!FIX || BLK, "the fixed layout exists for the blocked tree only");
     extern __shared__ __align__(16) unsigned char smemRaw[];
     constexpr int NG = 32 / W;
     constexpr bool kMC = MODE != MODE_INIT;   // Metropolis test, importance, counters
     constexpr bool kSample = MODE == MODE_SAMPLE || MODE == MODE_SAMPLE_FIXED;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gl = lane & (W - 1), g = lane / W;
+    int gl = lane & (W - 1);
+    const int g = lane / W;
+    int gBase = lane & ~(W - 1);        // first lane of the group
     const int chain = (blockIdx.x * kWarpsPerCta + warp) * NG + g;
-    const bool chainValid = chain < S.nChains;
-    const int chainC = chainValid ? chain : 0;   // pointer arithmetic only; every access is predicated
+    int validBit = chain < S.nChains ? 1 : 0;
+    int chainC = validBit ? chain : 0;   // pointer arithmetic only; every access is predicated
+#if ABM_PIN_IDS
+    // With 72 registers per thread the compiler otherwise re-derives the lane, the chain and everything that hangs off them
+    // from the special registers wherever they are used in the step loop (14 % of the executed instructions,
+    // profiles/r2c_*): an empty asm makes the three values opaque, so they are kept (or, at worst, reloaded).
+    asm volatile("" : "+r"(gl));
+    asm volatile("" : "+r"(gBase));
+    asm volatile("" : "+r"(validBit));
+    asm volatile("" : "+r"(chainC));
+#endif
+    const bool chainValid = validBit != 0;
 
     // ---- per-chain shared memory
-    const int gBytes = groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs, P.nodeCap, P.t2Cap);
+    const int cRowsCap = FIX ? kFixRowsCap : P.rowsCap, cSCap = FIX ? kFixSCap : P.sCap, cTCap = FIX ? 0 : P.tCap;
+    const int cScrCap = FIX ? 0 : P.scrCap, cNodeCap = FIX ? 0 : P.nodeCap, cT2Cap = FIX ? 0 : P.t2Cap, cMaxAbs = FIX ? 1 : P.maxAbs;
+    const int cSUCap = BLK ? 0 : cSCap;
+    const int gBytes = groupSmemBytes(cRowsCap, cSCap, cTCap, cScrCap, cMaxAbs, cNodeCap, cT2Cap, cSUCap);
     unsigned char *gs = smemRaw + (size_t)(warp * NG + g) * gBytes;
-    double2 *sScr = reinterpret_cast<double2 *>(gs);                     // [scrCap] blocked tree: {DE', signed leaf} of the first
+#if ABM_PIN_IDS
+    asm volatile("" : "+l"(gs));
+#endif
+    uint32_t *sRec = reinterpret_cast<uint32_t *>(gs);                   // [kRecWinWords] head of the proposed column's record
+    unsigned long long *sBar = reinterpret_cast<unsigned long long *>(gs + kRecWinBytes);   // mbarrier of the record copy
+    double2 *sScr = reinterpret_cast<double2 *>(gs + kRecWinBytes + 16);  // [scrCap] blocked tree: {DE', signed leaf} of the first
                                                                          //   coupled columns of a step (the rest: S.scratch)
-    double *sDl = reinterpret_cast<double *>(sScr + P.scrCap);           // [sCap] delta of set() per coupled column
-    double *sG = sDl + P.sCap;                                           // [rowsCap][2 maxAbs] per row: DE' term for a coupled
+    double *sDl = reinterpret_cast<double *>(sScr + cScrCap);            // [sCap] delta of set() per coupled column
+    double *sG = sDl + cSCap;                                            // [rowsCap][2 maxAbs] per row: DE' term for a coupled
                                                                          //   column whose flip moves the row by -maxAbs..-1, 1..maxAbs
-    double *sNode = sG + 2 * P.maxAbs * P.rowsCap;                                  // [32] tree nodes of one descent round
-    double *sT2 = sNode + P.nodeCap;                                     // [t2Cap] blocked tree: sums of 1024 leaves, when they fit
-    double *sTop = sT2 + P.t2Cap;                                        // [32] the chain's highest tree nodes (root = sTop[0])
+    double *sNode = sG + 2 * cMaxAbs * cRowsCap;                         // [32] tree nodes of one descent round
+    double *sT2 = sNode + cNodeCap;                                      // [t2Cap] blocked tree: sums of 1024 leaves, when they fit
+    double *sTop = sT2 + cT2Cap;                                         // [32] the chain's highest tree nodes (root = sTop[0])
     long long *sSyn = reinterpret_cast<long long *>(sTop + 32);          // [2][8] MODE_SAMPLE: synopsis sum / sum of squares
-    int *sU = reinterpret_cast<int *>(sSyn + 16);                        // [sCap] coupled columns, ascending
-    int *sXoff = sU + P.sCap;                                            // [rowsCap] Xb offsets of the rows
-    uint16_t *sTask = reinterpret_cast<uint16_t *>(sXoff + P.rowsCap);   // [tCap] commit tasks
-    uint16_t *sXX = sTask + P.tCap;                                      // [rowsCap] x | xn << 8 (int8 each)
+    unsigned long long *sIter0 = reinterpret_cast<unsigned long long *>(sSyn + 16);   // the chain's Philox counter when the launch began
+    int *sCnt = reinterpret_cast<int *>(sIter0 + 1);                     // [8] this launch's MCMCStatistics counts (lane 0 of the group)
+    int *sU = sCnt + 8;                                                  // [sCap] coupled columns, ascending
+    int *sXoff = sU + cSUCap;                                            // [rowsCap] Xb offsets of the rows
+    uint16_t *sTask = reinterpret_cast<uint16_t *>(sXoff + cRowsCap);    // [tCap] commit tasks
+    uint16_t *sXX = sTask + cTCap;                                       // [rowsCap] x | xn << 8 (int8 each)
 
     Chain ch;
     ch.Xb = S.Xb + (size_t)chainC * P.xStride;
@@ -317,30 +435,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (chainValid && k < nTop) v = BLK ? tier3[k] : ch.tier2[(k << P.topShift) >> 10];
         sTop[k] = v;
     }
-    const bool t2s = BLK && P.t2Cap > 0;   // the second-highest level of the blocked tree lives in shared memory, too
+    const bool t2s = BLK && !FIX && P.t2Cap > 0;   // the second-highest level of the blocked tree lives in shared memory, too
     if (t2s)
         for (int k = gl; k < P.t2Len; k += W) sT2[k] = chainValid ? ch.tier2[k] : 0.0;
     __syncwarp();
     double2 *scratch = S.scratch + (size_t)chainC * P.sCap;
-    const int scrChunks = BLK ? P.scrCap / W : 0;   // chunks of coupled columns whose staged values stay in shared memory
+    const int scrChunks = (BLK && !FIX) ? P.scrCap / W : 0;   // chunks of coupled columns whose staged values stay in shared memory
 
     double logImp = chainValid ? S.logImp[chain] : 0.0;
     int infeas = chainValid ? S.infeas[chain] : 0;
-    unsigned long long iter = chainValid ? S.iter[chain] : 0ull;
-    int cProp[4] = {0, 0, 0, 0}, cAcc[4] = {0, 0, 0, 0};
-    long long itersDone = 0;
-    const unsigned long long chainId = R.firstChain + (unsigned long long)chainC;
+    // Registers are what bounds the residency of this kernel (72 per thread for 28 warps per SM), so what a step does not need in
+    // a register lives in shared memory: the launch's counters, and the Philox counter base (iteration = base + itersDone)
+    if (gl == 0) sIter0[0] = chainValid ? S.iter[chain] : 0ull;
+    if (gl < 8) sCnt[gl] = 0;
+#if ABM_REC_BULK
+    if (gl == 0) {
+        barInit(sBar);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    unsigned barPhase = 0u;             // parity of the record barrier's current phase (one phase per proposal)
+#endif
+#if ABM_REC_EVICT_LAST
+    const unsigned long long recPolicy = policyEvictLast();
+#endif
+    __syncwarp();
+    int itersDone = 0;                  // iterations (init + MH) this chain made in this launch (a launch is at most 2^30 steps)
     const double kappa = P.kappa;
     const double *__restrict__ facVal = P.facVal;
     const int nCols = P.nCols;
-#if ABM_UNIT_ONLY   // measurement switch: unit tableau entries assumed at compile time
-    constexpr int kTwoM = 2, kMaxAbs = 1;
-#else
-    const int kTwoM = P.twoM, kMaxAbs = P.maxAbs;
-#endif
-    constexpr bool kPhBlk = ABM_PHILOX_BLOCK != 0 && BLK;   // the blocked tree leaves sNode free to hold the drawn block
-    constexpr int PB = W < 16 ? W : 16;
+    const int kTwoM = FIX ? 2 : P.twoM, kMaxAbs = FIX ? 1 : P.maxAbs;   // FIX: unit tableau entries (constants after inlining)
+    // ABM_PHILOX_BLOCK: lane gl of a group draws the Philox block of the chain's iteration iter + gl, i.e. W iterations at once,
+    // and every step reads its two uniforms from one lane by shuffle; same counters, same uniforms as one block per step
+    constexpr bool kPhBlk = ABM_PHILOX_BLOCK != 0;
+    constexpr int PB = W;
     int phIdx = PB;                     // next unread iteration of the drawn Philox block (PB: none left)
+    double pu1 = 0.5, pu2 = 0.0;        // this lane's drawn uniforms
 
     // ---- MODE_SAMPLE state: current end-state occupancy ModelState(traj,T,T) (ModelState.h:27-36 via
     // State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115), kept
@@ -354,8 +484,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         __syncwarp();
     }
 
+    const int nStepsLaunch = (int)R.nSteps;
 #pragma unroll 1
-    for (long long s = 0; s < R.nSteps; ++s) {
+    for (int s = 0; s < nStepsLaunch; ++s) {
         const bool act = chainValid && (MODE == MODE_MCMC || MODE == MODE_SAMPLE_FIXED || (MODE == MODE_INIT && infeas > 0) ||
                                         (MODE == MODE_SAMPLE && (long long)nSamp < R.nSamples));
         if ((MODE == MODE_INIT || MODE == MODE_SAMPLE) && !__any_sync(kFull, act)) break;
@@ -364,11 +495,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         double u1 = 0.5, u2 = 0.0;
         if (act) {
             if (R.injU) {
-                const double *up = R.injU + (size_t)chain * R.uStride + R.uOffset;
+                const double *up = R.injU + (size_t)chainC * R.uStride + R.uOffset;
                 if (MODE == MODE_INIT) u1 = up[s];
                 else { u1 = up[2 * s]; u2 = up[2 * s + 1]; }
             } else if constexpr (!kPhBlk) {
                 uint32_t w[4];
+                const unsigned long long iter = sIter0[0] + (unsigned long long)itersDone, chainId = R.firstChain + (unsigned long long)chainC;
                 philox4x32_10((uint32_t)iter, (uint32_t)(iter >> 32), (uint32_t)chainId, (uint32_t)(chainId >> 32),
                               (uint32_t)R.seed, (uint32_t)(R.seed >> 32), w);
                 u1 = canonical_from_words(w[0], w[1]);
@@ -379,22 +511,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             if (!R.injU) {
                 const bool need = act && phIdx >= PB;
                 if (__any_sync(kFull, need)) {
-                    if (need && gl < PB) {   // lane gl: the block of iteration iter + gl
-                        const unsigned long long it = iter + (unsigned long long)gl;
+                    if (need) {   // lane gl: the block of iteration iter + gl
+                        const unsigned long long it = sIter0[0] + (unsigned long long)(itersDone + gl), chainId = R.firstChain + (unsigned long long)chainC;
                         uint32_t w[4];
                         philox4x32_10((uint32_t)it, (uint32_t)(it >> 32), (uint32_t)chainId, (uint32_t)(chainId >> 32),
                                       (uint32_t)R.seed, (uint32_t)(R.seed >> 32), w);
-                        sNode[2 * gl] = canonical_from_words(w[0], w[1]);
-                        sNode[2 * gl + 1] = canonical_from_words(w[2], w[3]);
+                        pu1 = canonical_from_words(w[0], w[1]);
+                        pu2 = canonical_from_words(w[2], w[3]);
+                        phIdx = 0;
                     }
-                    if (need) phIdx = 0;
-                    __syncwarp();
                 }
-                if (act) {
-                    u1 = sNode[2 * phIdx];
-                    u2 = sNode[2 * phIdx + 1];
-                    ++phIdx;
-                }
+                const double s1 = __shfl_sync(kFull, pu1, phIdx & (PB - 1), W), s2 = __shfl_sync(kFull, pu2, phIdx & (PB - 1), W);
+                if (act) { u1 = s1; u2 = s2; ++phIdx; }
             }
         }
 
@@ -405,20 +533,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         double root = 1.0;
         int j = 0;
         if constexpr (BLK) {
-            // total = sum of the top entries, highest first (the order the selection below subtracts them in)
-            double tot = 0.0;
-#pragma unroll 1
-            for (int k = nTop - 1; k >= 0; --k) tot = __dadd_rn(tot, sTop[k]);
+            // top level (sums of 32768 leaves, shared memory): one scan over the group's lanes gives the total and the
+            // selection; absent entries are 0.0 (sTop is zero beyond nTop)
+            double vt[NG];
+#pragma unroll
+            for (int k = 0; k < NG; ++k) vt[k] = sTop[gl * NG + k];
+            const double sfxT = suffixScan<W>(vt, gl);
+            const double tot = __shfl_sync(kFull, sfxT, 0, W);
             if (act) root = tot;
             double target = __dmul_rn(u1, root);
-            // top level: sequential, from shared memory
-            int sel = 0;
-#pragma unroll 1
-            for (int k = nTop - 1; k >= 0; --k) {
-                const double v = sTop[k];
-                if (target < v || k == 0) { sel = k; break; }
-                target = __dsub_rn(target, v);
-            }
+            int sel = selectFromScan<W>(vt, sfxT, target, gl, gBase);
             // three 32-ary levels: tier2 (1024 leaves each), tier1 (32 leaves), leaves
 #pragma unroll
             for (int lvl = 2; lvl >= 0; --lvl) {
@@ -432,7 +556,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     if (act && e < count)   // leaf sign = delta_e; tiers in global memory are updated by L2 reductions
                         v[k] = lvl == 2 ? (t2s ? sT2[e] : __ldcg(ch.tier2 + e)) : (lvl == 1 ? __ldcg(ch.tier1 + e) : fabs(ch.colRec[e].y));
                 }
-                sel = first + selectDescending<W>(v, target, gl);
+                sel = first + selectDescending<W>(v, target, gl, gBase);
             }
             j = min(sel, nCols - 1);
         } else {
@@ -473,95 +597,119 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
         }
         }
-        if (act && R.injJ) j = R.injJ[(size_t)chain * R.nSteps + s];
+        if (act && R.injJ) j = R.injJ[(size_t)chainC * R.nSteps + s];
 
-        // ---- Proposal::Proposal (:288-315): record of column j
-        int4 hdr = make_int4(0, 0, 0, 0);
-        if (act) hdr = __ldg(P.recIdx + j);   // {record offset, n | nSF<<8 | C<<16, nChunks, contrib word | stale word << 16}
-        const int32_t *__restrict__ rec = P.rec + (size_t)(unsigned)hdr.x * 4;
-        const int n = hdr.y & 0xff, nSF = (hdr.y >> 8) & 0xff, C = (hdr.y >> 16) & 0xffff;
-        const int nChunks = hdr.z & 0xffff, nEv = (hdr.z >> 16) & 0xff;   // nEv: leading rows that are events (row id < nEvents)
-        const bool colTouchesEnd = hdr.z < 0;                              // bit 31: the column has an event row in the last timestep
-        const int4 *__restrict__ recRows = reinterpret_cast<const int4 *>(rec);
-        const int32_t *__restrict__ chunkHdr = rec + 4 * n;
-        const int32_t *__restrict__ slotU = chunkHdr + nChunks;
-        const uint16_t *__restrict__ contrib = reinterpret_cast<const uint16_t *>(rec + (hdr.w & 0xffff));
-        const int32_t *__restrict__ staleF = rec + ((unsigned)hdr.w >> 16);
+        // ---- Proposal::Proposal (:288-315): record of column j.  The head of the record -- rows, stale factors, coupled columns --
+        // is staged in the chain's shared-memory window by two coalesced 16-byte loads per lane (or, ABM_REC_BULK, by one bulk
+        // asynchronous copy whose completion is counted on the chain's mbarrier); lists longer than the window (a few per cent
+        // of the proposals) are read from the table itself.
+        uint2 ri = make_uint2(0u, 0u);
+        if (act) ri = __ldg(P.recIdx + j);   // {offset in 16-byte units, bytes}
+        const uint32_t *__restrict__ recG = P.rec + (size_t)ri.x * 4;
+#if !ABM_REC_BULK
+        if (act) {
+            const unsigned nv = min(ri.y, (unsigned)kRecWinBytes) >> 4;
+            for (unsigned q = gl; q < nv; q += W) reinterpret_cast<uint4 *>(sRec)[q] = __ldg(reinterpret_cast<const uint4 *>(recG) + q);
+        }
+#elif ABM_REC_EVICT_LAST
+        if (act && gl == 0) bulkLoadHint(sRec, recG, min(ri.y, (unsigned)kRecWinBytes), sBar, recPolicy);
+#else
+        if (act && gl == 0) bulkLoad(sRec, recG, min(ri.y, (unsigned)kRecWinBytes), sBar);
+#endif
         // BLK: delta_u is the sign bit of the stored leaf p_u (p_u >= 0), so a coupled column costs one 16-byte load
         int dj = 1;
         if (act) dj = BLK ? (__double2hiint(ch.colRec[j].y) < 0 ? -1 : 1) : (int)ch.delta[j];
+#if !ABM_REC_BULK
+        __syncwarp();
+#else
+        if (act) { barWait(sBar, barPhase); barPhase ^= 1u; }
+#endif
+        auto recWord = [&](int i) -> uint32_t { return i < kRecWinWords ? sRec[i] : __ldg(recG + i); };
+        const uint32_t h0 = act ? sRec[0] : 0u, h1 = act ? sRec[1] : 0u;
+        const int n = h0 & 0xff, nSF = (h0 >> 8) & 0xff, C = h0 >> 16;
+        const int nEv = h1 & 0xff, nXt = (h1 >> 8) & 0x3fff;
+        const int wide = (h1 >> 30) & 1;                                    // slots of two words: {u, pairs}                 // nEv: leading rows that are events (row id < nEvents)
+        const bool colTouchesEnd = (int)h1 < 0;                             // the column has an event row in the last timestep
+        const int uBase = act ? (int)sRec[2] : 0;
+        const int staleOff = 4 + 2 * n, slotOff = staleOff + nSF, xtraOff = slotOff + (C << wide), fxOff = xtraOff + nXt;
+        // slot l of the record: its pair word, and the column it names
+        auto slotWord = [&](int l) -> uint32_t { return recWord(slotOff + (l << wide) + wide); };
+        auto slotCol = [&](int l, uint32_t w) -> int { return wide ? (int)recWord(slotOff + 2 * l) : uBase + (int)(w & 0xffffu); };
 
-        // Two-deep software pipeline over the chunks of coupled columns (below): chunk c+1 in uB/chdrB, chunk c+2 in uC/chdrC
-        int uB = -1, chdrB = 0, uC = -1, chdrC = 0;
-        int sidPre = -1;                                              // first stale factor of this lane (ABM_PREFETCH 2)
-        if constexpr (ABM_PREFETCH >= 1) {
-            if (0 < nChunks) { uB = __ldg(slotU + gl); chdrB = __ldg(chunkHdr); }
-            if (1 < nChunks) { uC = __ldg(slotU + W + gl); chdrC = __ldg(chunkHdr + 1); }
-        }
-        if constexpr (ABM_PREFETCH >= 2 && kMC) {
-            if (gl < nSF) sidPre = __ldg(staleF + gl);
-        }
-
-        // rows of the proposed column
+        // rows of the proposed column, and -- requested in the same memory round trip -- the chain state of the first chunk of
+        // coupled columns
         const int nW = warpMax(n);
         int dinf = 0;
-        // ABM_PREFETCH 3: the first W rows and their X are requested, then the chain state of the first chunk of coupled
-        // columns, and only then are the rows evaluated: one memory round trip instead of two in a row
-        int4 r0 = make_int4(0, 0, 0, 0);
+        uint32_t rw0 = 0u, rw1 = 0u;
         int x0 = 0;
+        if (gl < n) {
+            rw0 = sRec[4 + 2 * gl];
+            rw1 = sRec[5 + 2 * gl];
+            x0 = ch.Xb[rw0 & 0xffffff];
+        }
+        uint32_t swN = 0xffff0000u;   // slot word of the coming chunk (0xffff....: no pair)
         double2 crN = make_double2(0.0, 0.0);
-        int duN = 0, ctN0 = kNoContrib, ctN1 = kNoContrib;
-        if constexpr (ABM_PREFETCH >= 3) {
-            if (gl < n) {
-                r0 = __ldg(recRows + gl);
-                x0 = ch.Xb[r0.x & 0xffffff];
-            }
-            if (uB >= 0) {
-                crN = ch.colRec[uB];
-                if constexpr (!BLK) duN = ch.delta[uB];
-                const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
-                if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
-                if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
-            }
+        int duN = 0;
+        bool realN = gl < C;
+        int uN = 0;
+        if (realN) {
+            swN = slotWord(gl);
+            uN = slotCol(gl, swN);
+            crN = ABM_STATE_EVICT_FIRST ? ldHint(ch.colRec + uN, policyEvictFirst()) : ch.colRec[uN];
+            if constexpr (!BLK) duN = ch.delta[uN];
         }
-        if constexpr (ABM_PREFETCH >= 4 && kMC) {
-            // the trajectory words the importance change will read (own state and the four neighbours of the first stale
-            // factors) are pulled into L2 now; the reads themselves follow the coupled columns
-            if (sidPre >= 0 && P.gShift >= 0) {
-                const int G = P.G, GG = G * G;
-                const int psi = sidPre & (P.S - 1), cell = psi & (GG - 1), type = psi >> (2 * P.gShift);
-                const int cy = cell >> P.gShift, cx = cell & (G - 1), ob = (sidPre - psi) + (1 - type) * GG;
-                const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(ch.Xb);
-                prefetchL2(X8 + sidPre);
-                prefetchL2(X8 + ob + ((cx - 1) & (G - 1)) + G * cy);
-                prefetchL2(X8 + ob + ((cx + 1) & (G - 1)) + G * cy);
-                prefetchL2(X8 + ob + cx + G * ((cy + 1) & (G - 1)));
-                prefetchL2(X8 + ob + cx + G * ((cy - 1) & (G - 1)));
-            }
+#if ABM_PF_IMP
+        if (kMC && gl < nSF && P.gShift >= 0) {
+            const int sidP = (int)recWord(staleOff + gl);
+            const int G = P.G, GG = G * G;
+            const int psi = sidP & (P.S - 1), cell = psi & (GG - 1), type = psi >> (2 * P.gShift);
+            const int cy = cell >> P.gShift, cx = cell & (G - 1), ob = (sidP - psi) + (1 - type) * GG;
+            const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(ch.Xb);
+            prefetchL2(X8 + sidP);
+            prefetchL2(X8 + ob + ((cx - 1) & (G - 1)) + G * cy);   // left / right share a line with high probability
+            prefetchL2(X8 + ob + cx + G * ((cy + 1) & (G - 1)));
+            prefetchL2(X8 + ob + cx + G * ((cy - 1) & (G - 1)));
         }
+#endif
+#if ABM_PF_CHUNKS
+        {
+            const int cW = warpMax(C);
+            #pragma unroll 1
+            for (int l = W + gl; l < cW; l += W)
+                if (l < C) {
+                    const double2 *pa = ch.colRec + slotCol(l, wide ? 0u : slotWord(l));
+                    if (ABM_PF_CHUNKS == 2) prefetchL1(pa); else prefetchL2(pa);
+                }
+        }
+#endif
         #pragma unroll 1
         for (int rb = 0; rb < nW; rb += W) {
             const int k = rb + gl;
             if (k < n) {
-                int4 r;
-                int x;
-                if (ABM_PREFETCH >= 3 && rb == 0) { r = r0; x = x0; }
-                else { r = __ldg(recRows + k); x = ch.Xb[r.x & 0xffffff]; }
-                const int xoff = r.x & 0xffffff, m = r.x >> 24;
+                uint32_t w0 = rw0, w1 = rw1;
+                int x = x0;
+                if (rb != 0) { w0 = sRec[4 + 2 * k]; w1 = sRec[5 + 2 * k]; x = ch.Xb[w0 & 0xffffff]; }
+                const int xoff = w0 & 0xffffff, m = (int)w0 >> 24;
+                const int L = (int)(int8_t)(w1 >> 16), U = (int)w1 >> 24;
+                const double *__restrict__ eRow = P.eTab + (w1 & 0xffffu);                   // energy(i, x) = eRow[x]
                 const int xn = x + m * dj;                                                  // :299-300
                 sXoff[k] = xoff;
                 sXX[k] = (uint16_t)((x & 0xff) | ((xn & 0xff) << 8));
                 // dE = energy(x') - energy(x) (:302), and what this row adds to DE' of a coupled column u whose flip would move
                 // the row by s = M_iu delta_u (:309-310): (energy(x'+s) - energy(x+s)) - dE, for s = -maxAbs..-1, 1..maxAbs
                 // (PredPrey tableaux on the paper's problems have unit entries: two values per row)
-                double dE = 0.0;
+                const double dE = __dsub_rn(__ldg(eRow + xn), __ldg(eRow + x));
+                if constexpr (FIX) {
+                    sG[2 * k] = __dsub_rn(__dsub_rn(__ldg(eRow + xn - 1), __ldg(eRow + x - 1)), dE);
+                    sG[2 * k + 1] = __dsub_rn(__dsub_rn(__ldg(eRow + xn + 1), __ldg(eRow + x + 1)), dE);
+                } else {
 #pragma unroll 1
-                for (int d = 0; d <= kTwoM; ++d) {   // shift 0 first (dE itself), then the shifts in ascending order
-                    const int sh = d == 0 ? 0 : (2 * d <= kTwoM ? d - kMaxAbs - 1 : d - kMaxAbs);
-                    const double e = __dsub_rn(energyOf(xn + sh, r.y, r.z, r.w, facVal, kappa), energyOf(x + sh, r.y, r.z, r.w, facVal, kappa));
-                    if (d == 0) dE = e; else sG[kTwoM * k + d - 1] = __dsub_rn(e, dE);
+                    for (int d = 1; d <= kTwoM; ++d) {   // the shifts in ascending order
+                        const int sh = 2 * d <= kTwoM ? d - kMaxAbs - 1 : d - kMaxAbs;
+                        sG[kTwoM * k + d - 1] = __dsub_rn(__dsub_rn(__ldg(eRow + xn + sh), __ldg(eRow + x + sh)), dE);
+                    }
                 }
-                dinf += infeasOf(xn, r.y, r.z) - infeasOf(x, r.y, r.z);                    // :303
+                dinf += infeasOf(xn, L, U) - infeasOf(x, L, U);                              // :303
             }
         }
         const int infN = infeas + groupSumInt<W>(dinf);
@@ -570,22 +718,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // coupled columns, one per lane, ascending.  A column's DE' is currentDE[u] plus one term per shared
         // row in row order -- the order in which the reference's map accumulation visits them (:305-312).
         double changeInSum = 0.0;
-        const int chunksW = warpMax(nChunks);
-        // Two-deep software pipeline over the chunks: the column list of chunk c+2 and the chain state of chunk c+1 (record,
-        // delta, first shared-row entries) are in flight while chunk c is evaluated.
-        if constexpr (ABM_PREFETCH < 1) {
-            if (0 < nChunks) { uB = __ldg(slotU + gl); chdrB = __ldg(chunkHdr); }
-            if (1 < nChunks) { uC = __ldg(slotU + W + gl); chdrC = __ldg(chunkHdr + 1); }
-        }
-        if constexpr (ABM_PREFETCH < 3) {
-            if (uB >= 0) {
-                crN = ch.colRec[uB];
-                if constexpr (!BLK) duN = ch.delta[uB];
-                const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
-                if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
-                if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
-            }
-        }
+        const int chunksW = warpMax((C + W - 1) / W);
         // The importance change (perturb + refresh) can be evaluated between issuing the first chunk's loads and consuming
         // them (ABM_IMP_EARLY), so that its own loads of the trajectory overlap with them, or after the chunks.
         double logImpN = logImp;
@@ -603,7 +736,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     int sid = -1, type = 0, ns[4] = {-1, -1, -1, -1};
                     unsigned long long own = 0ull, nb[4] = {0ull, 0ull, 0ull, 0ull};
                     if (fa) {
-                        sid = (ABM_PREFETCH >= 2 && fb == 0) ? sidPre : __ldg(staleF + f);
+                        sid = (int)recWord(staleOff + f);
                         int cx, cy, ob;
                         if (P.gShift >= 0) {   // power-of-two grids: psi = x + G y + G^2 type (PredPreyAgent.h:59) by shifts
                             const int psi = sid & (P.S - 1), cell = psi & (GG - 1);
@@ -644,11 +777,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                         const bool flN = (posMask(nbN[0]) | posMask(nbN[1]) | posMask(nbN[2]) | posMask(nbN[3])) != 0ull;
                         diff = __dsub_rn(factorLogP(ownN, flN, type, P.impTab), factorLogP(own, fl, type, P.impTab));  // :109
                     }
-                    const int qW = min(W, sfW - fb);
+                    // totalLogProb += newLogP - oldLogP in stale-factor insertion order (:109).  Most factors do not change:
+                    // their difference is exactly +0.0 and x + 0.0 == x bit for bit (the total is never -0.0), so only the
+                    // non-zero differences are added, in the same order.
+                    unsigned nz = (__ballot_sync(kFull, fa && diff != 0.0) >> gBase) & (W == 32 ? 0xffffffffu : ((1u << W) - 1u));
 #pragma unroll 1
-                    for (int q = 0; q < qW; ++q) {   // totalLogProb += ... in stale-factor insertion order
-                        const double dq = __shfl_sync(kFull, diff, q, W);
-                        if (fb + q < nSF) logImpN = __dadd_rn(logImpN, dq);
+                    while (__any_sync(kFull, nz != 0u)) {
+                        const double dq = __shfl_sync(kFull, diff, nz ? __ffs(nz) - 1 : 0, W);
+                        if (nz) logImpN = __dadd_rn(logImpN, dq);
+                        nz &= nz - 1u;
                     }
                 }
             }
@@ -658,25 +795,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         #pragma unroll 1
         for (int c = 0; c < chunksW; ++c) {
             const int slot = c * W + gl;
-            const int u = uB, chdr = chdrB;
+            const uint32_t sw = swN;
             const double2 cr = crN;
+            const bool real = realN;
+            const int u = uN;
             const int du = BLK ? (__double2hiint(cr.y) < 0 ? -1 : 1) : duN;
-            int ct4[2] = {ctN0, ctN1};
-            uB = uC; chdrB = chdrC;
-            uC = -1; chdrC = 0;
-            if (c + 2 < nChunks) { uC = __ldg(slotU + slot + 2 * W); chdrC = __ldg(chunkHdr + c + 2); }
+            // the coming chunk's slot words are in shared memory already; its chain state is requested now
+            swN = 0xffff0000u;
             crN = make_double2(0.0, 0.0);
-            duN = 0; ctN0 = kNoContrib; ctN1 = kNoContrib;
-            if (uB >= 0) {
-                crN = ch.colRec[uB];
-                if constexpr (!BLK) duN = ch.delta[uB];
-                const uint16_t *__restrict__ pl = contrib + (chdrB >> 8) + gl;
-                if ((chdrB & 0xff) > 0) ctN0 = __ldg(pl);
-                if ((chdrB & 0xff) > 1) ctN1 = __ldg(pl + W);
+            duN = 0;
+            realN = slot + W < C;
+            if (realN) {
+                swN = slotWord(slot + W);
+                uN = slotCol(slot + W, swN);
+                crN = ABM_STATE_EVICT_FIRST ? ldHint(ch.colRec + uN, policyEvictFirst()) : ch.colRec[uN];
+                if constexpr (!BLK) duN = ch.delta[uN];
             }
-            const bool real = u >= 0, self = real && u == j;
-            const int maxCnt = chdr & 0xff;
-            const uint16_t *__restrict__ plane = contrib + (chdr >> 8) + gl;
+            const bool self = real && u == j;
             // (reference tree) the nodes get(u) / set(u,.) will read: u + 1, 2, 4, 8, 16 sit in the same 32-record block
             const int nDesc = (!BLK && real) ? (u ? (__ffs(u) - 1) : P.treeDepth) : 0;
             double dn[5];
@@ -688,24 +823,33 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 if (real && (u & 31) == 0) nodeOld = *ch.node(u);
             }
             double acc = cr.x;                                                               // try_emplace(u, currentDE[u])
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int ct = ct4[t];
-                if (ct != kNoContrib) {
-                    const int k = ct & 0xff, mu = (int)(int8_t)(ct >> 8);
+            // the rows u shares with the proposed column, in row order: pair = row k of the column | code of M_iu << 5
+            const unsigned p0 = (sw >> 16) & 0xffu, p1 = sw >> 24;
+            auto rowTerm = [&](unsigned pb) -> double {
+                const int k = pb & 31, code = pb >> 5;
+                if constexpr (FIX) {   // unit entries: the row moves by M_iu delta_u = +-1
+                    const int up = ((code >> 2) & 1) == (du < 0 ? 1 : 0) ? 1 : 0;
+                    return sG[2 * k + up];
+                } else {
+                    const int mu = (code & 4) ? -((code & 3) + 1) : (code & 3) + 1;
                     const int sv = mu * du;                                                  // the row's move if u flipped
-                    acc = __dadd_rn(acc, sG[kTwoM * k + kMaxAbs + sv - (sv > 0 ? 1 : 0)]);     // :308-310
+                    return sG[kTwoM * k + kMaxAbs + sv - (sv > 0 ? 1 : 0)];
                 }
+            };
+            const bool ext = real && p0 == (unsigned)kPairExt;
+            if (real && p0 < (unsigned)kPairExt) {
+                acc = __dadd_rn(acc, rowTerm(p0));                                                // :308-310
+                if (p1 != (unsigned)kPairNone) acc = __dadd_rn(acc, rowTerm(p1));
             }
-            const int tW = warpMax(maxCnt);
+            if (__any_sync(kFull, ext)) {   // columns sharing more than two rows with the proposed one: their pair lists
+                const int lw = xtraOff + (int)p1;
+                const int cnt = ext ? (int)(recWord(lw) & 0xffu) : 0;
+                const int tW = warpMax(cnt);
 #pragma unroll 1
-            for (int t = 2; t < tW; ++t) {
-                if (real && t < maxCnt) {
-                    const int ct = __ldg(plane + t * W);
-                    if (ct != kNoContrib) {
-                        const int k = ct & 0xff, mu = (int)(int8_t)(ct >> 8);
-                        const int sv = mu * du;
-                        acc = __dadd_rn(acc, sG[kTwoM * k + kMaxAbs + sv - (sv > 0 ? 1 : 0)]);
+                for (int t = 0; t < tW; ++t) {
+                    if (t < cnt) {
+                        const int bi = 1 + t;
+                        acc = __dadd_rn(acc, rowTerm((recWord(lw + (bi >> 2)) >> (8 * (bi & 3))) & 0xffu));
                     }
                 }
             }
@@ -750,7 +894,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 base = ssum;
             }
             if (real) {
-                sU[slot] = u;
+                if constexpr (!BLK) sU[slot] = u;
                 sDl[slot] = dlt;
                 // BLK: the stored leaf carries delta_u in its sign; the proposed column's flips on acceptance (:334)
                 if constexpr (BLK) base = ((du < 0) != self) ? -base : base;
@@ -787,14 +931,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             const double acceptance = __dmul_rn(expShared(__dsub_rn(logImpN, logImp)), ratio);
             accept = act && (u2 < acceptance);
             const int ci = (infeas == 0 ? 2 : 0) + (infN == 0 ? 1 : 0);                      // MCMCStatistics.cpp:12-17
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                cProp[q] += (act && q == ci);
-                cAcc[q] += (accept && q == ci);
+            if (act && gl == 0) {
+                sCnt[ci] += 1;
+                if (accept) sCnt[4 + ci] += 1;
             }
         }
         if (R.outJ && act && gl == 0) {
-            const size_t o = (size_t)chain * R.nSteps + s;
+            const size_t o = (size_t)chainC * R.nSteps + s;
             R.outJ[o] = j;
             if (R.outAcc) R.outAcc[o] = accept ? 1 : 0;
             if (R.outInf) R.outInf[o] = infN;
@@ -806,7 +949,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 #if ABM_END_DEFERRED
             // the effect list is requested now and applied after the commit, so its round trip overlaps the commit
             if (accept && colTouchesEnd) {
-                const int32_t *__restrict__ fx = staleF + nSF;
+                const int32_t *__restrict__ fx = reinterpret_cast<const int32_t *>(recG) + fxOff;
                 fxN = __ldg(fx) * dj;                    // nEnd, signed by delta_j (nEnd >= 1 for such a column)
                 fxK = __ldg(fx + 3 + gl);                // speculative beyond nEnd: the record table is padded
                 fxS = __ldg(fx + 1 + (gl >> 2));
@@ -814,7 +957,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
 #else
             if (__any_sync(kFull, accept && colTouchesEnd))
-                syn += endStateEffects(staleF + nSF, (accept && colTouchesEnd) ? dj : 0, P.nSynopsis, S.endRec + (size_t)chainC * P.S, nSamp,
+                syn += endStateEffects(reinterpret_cast<const int32_t *>(recG) + fxOff, (accept && colTouchesEnd) ? dj : 0, P.nSynopsis, S.endRec + (size_t)chainC * P.S, nSamp,
                                        gl, W);
 #endif
         }
@@ -845,14 +988,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             // as a difference of two prefix values.  The run's last slot adds it to the sum (fire-and-forget reductions for
             // the two global tiers: nothing waits on the old value; the top tier is in shared memory).
             constexpr unsigned gMask = W == 32 ? 0xffffffffu : ((1u << W) - 1u);
-            const int gShiftLane = (threadIdx.x & 31) & ~(W - 1);
+            const int gShiftLane = gBase;
             double2 scN = make_double2(0.0, 0.0);   // the staged {DE', signed leaf} of the coming round, one round ahead
             if (gl < Ca) scN = 0 < scrChunks ? sScr[gl] : scratch[gl];
             #pragma unroll 1
             for (int lb = 0; lb < CW; lb += W) {
                 const int l = lb + gl;
                 const bool valid = l < Ca;
-                const unsigned u = valid ? (unsigned)sU[l] : 0x7fffffffu;
+                const unsigned u = valid ? (unsigned)slotCol(l, wide ? 0u : slotWord(l)) : 0x7fffffffu;
                 const double dl = valid ? sDl[l] : 0.0;
                 const double2 sc = scN;
                 if (l + W < Ca) scN = lb + W < scrChunks * W ? sScr[l + W] : scratch[l + W];
@@ -992,12 +1135,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 if (gl < P.nSynopsis) {   // MeanAndVariance::operator(), diagnostics/MeanAndVariance.h:35-45 (exact in int64)
                     sSyn[gl] += syn;
                     sSyn[8 + gl] += (long long)syn * syn;
-                    if (R.series && chain < R.nSeriesChains) recordSeries(R.series, R.seriesThin, R.seriesCap, P.nSynopsis, chain, S.nSamples[chain] + nSamp, gl, syn);
+                    if (R.series && chainC < R.nSeriesChains) recordSeries(R.series, R.seriesThin, R.seriesCap, P.nSynopsis, chainC, S.nSamples[chainC] + nSamp, gl, syn);
                 }
                 ++nSamp;
             }
         }
-        if (act) { ++iter; ++itersDone; }
+        if (act) ++itersDone;
     }
 
     __syncwarp();
@@ -1018,13 +1161,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     if (chainValid && gl == 0) {
         S.logImp[chain] = logImp;
         S.infeas[chain] = infeas;
-        S.iter[chain] = iter;
+        S.iter[chain] = sIter0[0] + (unsigned long long)itersDone;
         if (kMC) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                S.counters[(size_t)chain * 8 + q] += cProp[q];
-                S.counters[(size_t)chain * 8 + 4 + q] += cAcc[q];
-            }
+            for (int q = 0; q < 8; ++q) S.counters[(size_t)chain * 8 + q] += sCnt[q];
         } else if (R.itersOut) {
             R.itersOut[chain] += itersDone;
         }
