@@ -102,6 +102,7 @@ struct abm_chains {
     int64_t *momStage = nullptr;     // pinned: exact, then real
     cudaEvent_t evMom = nullptr;
     bool momPending = false;
+    int launchesSinceRebuild = 0;    // blocked tree: step / sample launches since the sums of 32 leaves were last rebuilt from the leaves
 };
 
 // CUDA events on the chains' stream around a step kernel, so a caller can time the kernel itself
@@ -737,9 +738,22 @@ static cudaError_t launchStepWB(const abm_chains *c, const RunParams &r) {
     return launchStepWBF<MODE, W, BLK, false>(c, r);
 }
 
+constexpr int kTier1RebuildEvery = 256;   // launches between exact rebuilds of the blocked tree's sums of 32 leaves
+
+static void rebuildTier1(const abm_chains *c) {
+    const DevProblem &P = c->p->d;
+    rebuildTier1Kernel<<<dim3(std::min((P.t1Len + 127) / 128, 64), c->n), 128, 0, c->stream>>>(P, c->d);
+}
+
 template <int MODE, int W>
 static cudaError_t launchStepW(const abm_chains *c, const RunParams &r) {
     if (!c->p->d.blockedTree) return launchStepWB<MODE, W, false>(c, r);
+    // before every launch the two upper levels are recomputed from the level below; every kTier1RebuildEvery-th launch the
+    // lowest sums are recomputed from the leaves as well, so no level carries incremental rounding for long
+    if (MODE != MODE_INIT && ++const_cast<abm_chains *>(c)->launchesSinceRebuild >= kTier1RebuildEvery) {
+        const_cast<abm_chains *>(c)->launchesSinceRebuild = 0;
+        rebuildTier1(c);
+    }
     refreshBlockedTopKernel<<<(c->n + 3) / 4, 128, 0, c->stream>>>(c->p->d, c->d);
     return launchStepWB<MODE, W, true>(c, r);
 }
@@ -1251,6 +1265,45 @@ int abm_chains_allreduce_moments(abm_chains *c, abm_comm *comm, int64_t *exact, 
 }
 
 int abm_chains_get_moments(abm_chains *c, int64_t *exact, double *real) { return abm_chains_allreduce_moments(c, nullptr, exact, real); }
+
+// Blocked tree maintenance and its measurement (DESIGN.md "Two storages").
+int abm_chains_rebuild_tree(abm_chains *c) {
+    if (!c) return fail(ABM_ERR_INVALID, "null chains");
+    if (!c->p->d.blockedTree) return ABM_OK;   // the reference tree is the reference's, drift included
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    rebuildTier1(c);
+    refreshBlockedTopKernel<<<(c->n + 3) / 4, 128, 0, c->stream>>>(c->p->d, c->d);
+    CUDA_TRY(cudaGetLastError());
+    c->launchesSinceRebuild = 0;
+    return ABM_OK;
+}
+
+int abm_chains_tree_drift(abm_chains *c, int32_t chain, double out[4]) {
+    if (!c || !out || chain < 0 || chain >= c->n) return fail(ABM_ERR_INVALID, "bad argument");
+    const DevProblem &P = c->p->d;
+    if (!P.blockedTree) return fail(ABM_ERR_INVALID, "the blocked sum tree is not in use");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const size_t ch = size_t(chain);
+    std::vector<double2> cr(P.nCols);
+    std::vector<double> t1(P.t1Len), t2(P.t2Len), t3(32);
+    CUDA_TRY(cudaMemcpy(cr.data(), c->d.colRec + ch * P.nCols, sizeof(double2) * P.nCols, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(t1.data(), c->d.tier1 + ch * P.t1Len, sizeof(double) * P.t1Len, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(t2.data(), c->d.tier2 + ch * P.t2Len, sizeof(double) * P.t2Len, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(t3.data(), c->d.tier3 + ch * 32, sizeof(double) * 32, cudaMemcpyDeviceToHost));
+    auto exact = [&](int lo, int hi) {   // leaves [lo, hi) summed in long double
+        long double v = 0.0L;
+        for (int k = lo; k < std::min(hi, P.nCols); ++k) v += std::fabs(cr[k].y);
+        return v;
+    };
+    const long double root = exact(0, P.nCols);
+    double e1 = 0.0, e2 = 0.0, e3 = 0.0;
+    for (int b = 0; b < P.t1Len; ++b) e1 = std::max(e1, double(fabsl(t1[b] - exact(32 * b, 32 * b + 32))));
+    for (int b = 0; b < P.t2Len; ++b) e2 = std::max(e2, double(fabsl(t2[b] - exact(1024 * b, 1024 * b + 1024))));
+    for (int b = 0; b * 32768 < P.nCols; ++b) e3 = std::max(e3, double(fabsl(t3[b] - exact(32768 * b, 32768 * b + 32768))));
+    out[0] = double(root); out[1] = e1; out[2] = e2; out[3] = e3;
+    return ABM_OK;
+}
 
 // abm_chains_sample with the uniforms injected: exactly nSteps steps, statistics after every step that ends feasible
 int abm_chains_sample_injected(abm_chains *c, int64_t nSteps, const double *uniforms) {

@@ -1417,6 +1417,20 @@ __global__ void refreshBlockedTopKernel(DevProblem P, DevChains S) {
     }
 }
 
+// Blocked sum tree: the lowest sums (of 32 leaves) recomputed from the leaves, highest index first.  The step kernel keeps them
+// incrementally (one rounded add per update); this exact rebuild runs every kTier1RebuildEvery launches and on request
+// (abm_chains_rebuild_tree), so their rounding cannot accumulate over the life of a chain.  One thread per sum.
+__global__ void rebuildTier1Kernel(DevProblem P, DevChains S) {
+    const int chain = blockIdx.y;
+    const double2 *cr = S.colRec + (size_t)chain * P.nCols;
+    double *t1 = S.tier1 + (size_t)chain * P.t1Len;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < P.t1Len; b += gridDim.x * blockDim.x) {
+        double v = 0.0;
+        for (int k = min(32 * b + 31, P.nCols - 1); k >= 32 * b; --k) v = __dadd_rn(v, fabs(cr[k].y));
+        t1[b] = v;
+    }
+}
+
 // ensemble end-state sum: out[psi] += sum over a slice of chains of endRec[chain][psi].acc (out zeroed by the caller)
 constexpr int kReduceSlice = 64;
 __global__ void reduceEndStateKernel(DevProblem P, DevChains S) {

@@ -137,6 +137,57 @@ def rhat_from_moments(n: np.ndarray, s: np.ndarray, sq: np.ndarray):
     return np.sqrt(var_plus / W), W, B, var_plus
 
 
+def ensemble_effective_samples(series: np.ndarray, thin: int, n: np.ndarray, s: np.ndarray, sq: np.ndarray,
+                               max_lag_proportion: float = 0.5, group: int = 1):
+    """Effective sample size of MANY equally long chains, with the reference's estimator
+    (MultiChainStats::effectiveSamples, diagnostics/MultiChainStats.h:81-102; BDA3 ch. 11):
+
+        n_eff = m n / (1 + 2 stride sum_t rho_t),   rho_t = 1 - V_t / (2 var+),   t = 0, stride, 2 stride, ...
+
+    summed while the running minimum of rho_t stays positive.  The reference evaluates the variogram V_t at 200 strided
+    lags from the full series of each sequence (ChainStats.h:66-79); with thousands of chains the full series cannot be
+    kept, but they are not needed either: V_t = E (x_i - x_{i+t})^2 is estimated from every `thin`-th sample of every chain
+    (`series`, [m][k][d], stride = thin), each lag averaged over all chains and all pairs, which with m in the thousands is
+    far more precise than the reference's per-sequence average.  var+ = (n-1)/n W + B/n from the exact per-chain moments
+    (n, s, sq as `rhat_from_moments`).  The estimate is valid when the window (n samples per chain) is long against the
+    autocorrelation time; the lags run to max_lag_proportion * n as in the reference (FiguresForPaper.h:89).
+
+    group > 1 additionally returns the R-hat of `m / group` super-sequences, each the pooled samples of `group` chains:
+    for stationary chains R-hat^2 = 1 + 1 / (effective samples per sequence), so sequences of a few autocorrelation times
+    cannot fall below ~1.05 however well the ensemble has converged; pooled sequences can.
+
+    Returns a dict: n_eff [d] (all chains), tau [d] (samples per effective sample), rho [lags][d], rhat [d], rhat_grouped [d],
+    W, B, var_plus."""
+    x = np.asarray(series, dtype=np.float64)
+    m, k, d = x.shape
+    n = np.asarray(n, dtype=np.float64)
+    rhat, W, B, var_plus = rhat_from_moments(n, s, sq)
+    nbar = float(n.mean())
+    n_lags = max(2, min(k, int(max_lag_proportion * nbar / thin) + 1))
+    V = np.zeros((n_lags, d))
+    for j in range(1, n_lags):
+        diff = x[:, : k - j] - x[:, j:]
+        V[j] = (diff * diff).mean(axis=(0, 1))
+    rho = 1.0 - V / (2.0 * var_plus)
+    n_eff = np.zeros(d)
+    for q in range(d):
+        t, next_s, sumt = 0, 1.0, 0.0
+        while next_s > 0.0:
+            sumt += next_s
+            t += 1
+            next_s = min(next_s, rho[t][q] if t < n_lags else -1.0)
+        n_eff[q] = nbar * m / (1.0 + 2.0 * thin * sumt)
+    out = {"n_eff": n_eff, "tau": nbar * m / n_eff, "rho": rho, "rhat": rhat, "W": W, "B": B, "var_plus": var_plus,
+           "lags": n_lags, "stride": thin}
+    if group > 1:
+        mg = (m // group) * group
+        ng = n[:mg].reshape(-1, group).sum(axis=1)
+        sg = np.asarray(s, dtype=np.float64)[:mg].reshape(-1, group, d).sum(axis=1)
+        qg = np.asarray(sq, dtype=np.float64)[:mg].reshape(-1, group, d).sum(axis=1)
+        out["rhat_grouped"] = rhat_from_moments(ng, sg, qg)[0]
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 class _Reader:
     def __init__(self, raw: bytes):

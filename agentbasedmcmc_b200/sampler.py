@@ -265,6 +265,15 @@ class SparseBasisSampler:
         check(_capi.load().abm_chains_get_series(self.h, _ptr(out, C.c_int32)))
         return out
 
+    def rebuild_tree(self):
+        check(_capi.load().abm_chains_rebuild_tree(self.h))
+
+    def tree_drift(self, chain: int = 0):
+        """(root, max error of the sums of 32 / 1024 / 32768 leaves against the exact sums of their leaves); blocked tree."""
+        out = np.zeros(4, np.float64)
+        check(_capi.load().abm_chains_tree_drift(self.h, chain, _ptr(out, C.c_double)))
+        return out
+
     def last_launch_ms(self) -> float:
         """Device time of the last step / step_traced / sample launch (waits for it)."""
         ms = C.c_float()

@@ -35,6 +35,8 @@ WORKLOADS = {
     "pp16-8": ("pp16-8.abmp.xz", 4096, 5329.0, "PredPrey 16x16 grid, 8 timesteps, 4096 chains/GPU"),
     "pp8-4": ("pp8-4.abmp.xz", 1024, 3567.0, "PredPrey 8x8 grid, 4 timesteps, 1024 chains/GPU"),
 }
+# workload -> (burn-in Metropolis steps per chain before anything is timed, feasible samples per chain of the ESS window)
+STATIONARY = {"pp32-16": (7000000, 1000000), "pp16-8": (1500000, 200000), "pp8-4": (200000, 100000)}
 METRIC = "chain-steps/sec, 32x32 PredPrey (SparseBasisSampler Metropolis steps, all chains, all GPUs)"
 UNIT = "chain-steps/s"
 
@@ -107,6 +109,16 @@ def run_reference_binary(fixture: str, threads: int, samples_per_step: int, warm
         os.unlink(path)
 
 
+def reference_tau(workload: str):
+    """Feasible samples per effective sample of the reference chain (worst synopsis statistic), from the long reference run
+    behind the paper-scale posterior fixture (tests/golden/make_posterior_golden.py); None when there is no such fixture."""
+    p = ROOT / "tests" / "golden" / f"posterior_{workload}.abmp.xz"
+    if not p.exists():
+        return None
+    from agentbasedmcmc_b200.abmp import read_abmp
+    return float(read_abmp(p)["tau_int"].max())
+
+
 def cpu_baseline(workload: str, threads: int, seconds_budget: float = 20.0):
     """Reference CPU sampler on this box's host cores on a bounded sample of the same workload."""
     fixture = WORKLOADS[workload][0]
@@ -115,10 +127,11 @@ def cpu_baseline(workload: str, threads: int, seconds_budget: float = 20.0):
     samples = int(samples * seconds_budget / 20.0)
     res = run_reference_binary(fixture, threads, samples, 0, 1)
     if res is not None:
-        v = res["chain_steps"][0] / res["step_seconds"][0]
+        v = res["steps_per_s"][0]
         return {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
                 "sample": f"{threads} chains (one per host thread) x {samples} feasible samples = {res['chain_steps'][0]} Metropolis steps, "
-                          f"unmodified reference SparseBasisSampler (oracle/_ref/abm_ref), {res['step_seconds'][0]:.1f}s timed"}
+                          f"unmodified reference SparseBasisSampler (oracle/_ref/abm_ref), every thread timed on its own loop, "
+                          f"rates summed, {res['step_seconds'][0]:.1f}s"}
     # the C restatement (single thread) when the compiled reference is not on the box
     from agentbasedmcmc_b200.abmp import read_abmp
     from oracle.oracle import OracleChain, OracleProblem
@@ -142,19 +155,30 @@ def bench_reference(args):
     threads = os.cpu_count() or 1
     samples = {"pp32-16": 20000, "pp16-8": 100000, "pp8-4": 200000}[args.workload]
     res = run_reference_binary(fixture, threads, samples, args.warmup, args.steps)
+    ess = None
     if res is None:
         cb = cpu_baseline(args.workload, 1)
         value, ms, kind, cores, sample = cb["value"], None, cb["kind"], cb["cores"], cb["sample"]
     else:
-        tot_steps, tot_sec = sum(res["chain_steps"]), sum(res["step_seconds"])
-        value, ms = tot_steps / tot_sec, 1e3 * tot_sec / len(res["step_seconds"])
+        # every thread times its own loop and a round's rate is the sum of the per-thread rates (abm_ref bench), so a chain that
+        # needs many steps per feasible sample does not hold the others' clocks
+        value = float(np.mean(res["steps_per_s"]))
+        ms = 1e3 * float(np.mean(res["step_seconds"]))
+        tot_steps = sum(res["chain_steps"])
         kind, cores = "reference", threads
-        sample = f"{threads} chains (one per host thread), {samples} feasible samples per chain per step, {tot_steps} Metropolis steps timed"
+        sample = (f"{threads} chains (one per host thread), {samples} feasible samples per chain per step, {tot_steps} Metropolis steps "
+                  f"timed, per-thread rates summed")
+        tau = reference_tau(args.workload)
+        if tau:
+            sps = threads * samples * len(res["step_seconds"]) / sum(res["step_seconds"])
+            ess = {"value": sps / tau, "unit": "effective samples/s (worst synopsis statistic)", "derived": True,
+                   "how": f"{sps:.0f} feasible samples/s measured here / {tau:.0f} feasible samples per effective sample, the reference "
+                          f"chain's autocorrelation time from the long reference run (tests/golden/posterior_{args.workload}.abmp.xz)"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "host_threads": cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "ess": ess}
     print(json.dumps(line))
     return 0
 
@@ -175,6 +199,8 @@ def bench_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from agentbasedmcmc_b200 import diagnostics as D
+    from agentbasedmcmc_b200 import ensemble as E
     from agentbasedmcmc_b200 import sampler as S
     from agentbasedmcmc_b200.abmp import read_abmp
 
@@ -189,25 +215,61 @@ def bench_ours(args):
     smp = S.SparseBasisSampler(P, n_chains=n_chains, seed=args.seed, first_chain_id=rank * n_chains, stream=stream.cuda_stream,
                                prior_init=True)
     setup_s = time.time() - t_setup
+    # the library's own NCCL communicator (abm_comm_*): the ensemble reduction goes through the C-ABI, as a C++ host's would
+    comm = E.Comm(local_rank) if world > 1 else None
+    n_syn = P.n_synopsis
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: W warm-up launches, then exactly K timed launches
-    for _ in range(args.warmup):
-        smp.step(mh)
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local_rank) as clocks:
+    def timed_launches(n_launch):
+        """n_launch launches of `mh` Metropolis steps, CUDA events on the launch stream; (total ms, per-launch ms)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_launch + 1)]
         ev[0].record(stream)
-        for k in range(args.steps):
+        for k in range(n_launch):
             smp.step(mh)
             ev[k + 1].record(stream)
         barrier()
-    launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    total_ms = ev[0].elapsed_time(ev[-1])
+        return ev[0].elapsed_time(ev[-1]), [ev[k].elapsed_time(ev[k + 1]) for k in range(n_launch)]
+
+    def counters_delta(prev):
+        c = smp.counters().sum(0)
+        d = c - prev
+        prop, acc = d[:4], d[4:]
+        tot = max(int(prop.sum()), 1)
+        return c, float(acc.sum()) / tot, float(prop[0] + acc[2] + prop[1] - acc[1]) / tot   # (counters, acceptance, infeasible fraction)
+
+    # ---- throughput straight after the feasibility search (the chains are far from the posterior: more agents, more infeasible
+    # states), kept for comparison with the stationary figure below
+    for _ in range(3):
+        smp.step(mh)
+    barrier()
+    c0 = smp.counters().sum(0)
+    ms_post_init, _ = timed_launches(5)
+    c0, acc_post_init, inf_post_init = counters_delta(c0)
+    value_post_init = float(n_chains) * mh * 5 / (ms_post_init * 1e-3)
+
+    # ---- burn-in to the stationary state (the reference burns 1e6 feasible samples ~ 3.3e6 steps in, FiguresForPaper.h:89;
+    # the ensemble mean of the synopsis is flat to within 2 % from ~6e6 steps, profiles/r2_relaxation_*.json)
+    t_burn = time.time()
+    done = 0
+    while done < args.burnin_steps:
+        k = min(500000, args.burnin_steps - done)
+        smp.step(k)
+        done += k
+    barrier()
+    burn_s = time.time() - t_burn
+
+    # ---- device-resident throughput at the stationary state: W warm-up launches, then exactly K timed launches
+    for _ in range(args.warmup):
+        smp.step(mh)
+    barrier()
+    c0 = smp.counters().sum(0)
+    with ClockSampler(local_rank) as clocks:
+        total_ms, launch_ms = timed_launches(args.steps)
+    c0, acc_stat, inf_stat = counters_delta(c0)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -215,27 +277,24 @@ def bench_ours(args):
     steps_done = float(world) * n_chains * mh * args.steps
     value = steps_done / (total_ms * 1e-3)
 
-    # ---- end to end through the host-facing API: step + statistics into host buffers, host clock
-    from agentbasedmcmc_b200 import ensemble as E
+    # ---- end to end through the host-facing API: a sampling launch (steps + on-device statistics), the ensemble moments
+    # reduced on the device, summed over the GPUs by NCCL inside the library and copied to host buffers -- every step, host clock.
+    # Launch k+1 is queued behind the reduction of launch k, so the device never waits for the host.
+    smp.reset_statistics()
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
     summary = None
-    # launch k+1 is queued behind the read-back of launch k, so the device never waits for the host: stream order is
-    # sample 0, read-back 0, sample 1, read-back 1, ...; the host collects read-back k while sample k+1 runs
+    d2h = 0
     smp.sample(10 ** 12, max_steps=mh)          # mh Metropolis steps per chain, statistics of every feasible state
-    smp.enqueue_statistics()                    # ensemble reduction + device -> pinned host copies, asynchronous
+    smp.enqueue_moments(comm)                   # device reduction + NCCL all-reduce + copies into pinned host memory, asynchronous
     for k in range(args.steps):
         if k + 1 < args.steps:
             smp.sample(10 ** 12, max_steps=mh)
-        end, ss, sq, ns, c = smp.wait_statistics()   # statistics and counters after launch k, in host buffers
+        exact, real = smp.wait_moments()        # the ensemble's additive moments after launch k, in host buffers
         if k + 1 < args.steps:
-            smp.enqueue_statistics()
-        d2h = end.nbytes + ss.nbytes + sq.nbytes + ns.nbytes + c.nbytes
-        packed = E.pack_local(end, ss, sq, ns, c)
-        if world > 1:
-            packed = packed.cuda()
-        summary = E.allreduce_summary(packed, end.size, ss.shape[1])   # NCCL sum over ranks (world > 1)
+            smp.enqueue_moments(comm)
+        d2h = exact.nbytes + real.nbytes
+        summary = E.summarize_moments(exact, real, n_syn)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -243,44 +302,51 @@ def bench_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = steps_done / float(te.item())
 
-    # ---- ESS/s (the second half of BASELINE.json's metric): reference formula (MultiChainStats::effectiveSamples,
-    # diagnostics/MultiChainStats.h:81-102) on the synopsis series of the first `ess_chains` chains of rank 0, each a
-    # sequence; chains are i.i.d., so the ensemble's effective sample size is the per-chain one times the chain count.
+    # ---- ESS/s and R-hat at the stationary state (the second half of BASELINE.json's metric): every chain takes the same
+    # number of feasible samples (operator() semantics); the reference's estimator (MultiChainStats::effectiveSamples,
+    # diagnostics/MultiChainStats.h:81-102) with its lag grid (200 strided lags to half the sequence, FiguresForPaper.h:89-90),
+    # the variogram averaged over ALL chains from every stride-th sample, var+ from the exact per-chain moments.
     ess = None
-    if args.ess_samples > 0 and rank == 0:
+    if args.ess_samples > 0:
         try:
-            from agentbasedmcmc_b200 import diagnostics as D
-            k = min(args.ess_chains, n_chains)
-            burn = 0
-            while burn < args.ess_burnin:       # relaxation from the first feasible state takes ~3e6 steps at 32x32x16
-                smp.step(min(250000, args.ess_burnin - burn))
-                burn += 250000
+            n_s = args.ess_samples
+            thin = max(1, n_s // 400)
             smp.reset_statistics()
-            smp.record_series(k, 1, args.ess_samples)
-            torch.cuda.synchronize()
+            smp.record_series(n_chains, thin, n_s // thin + 1)
+            barrier()
             t0 = time.perf_counter()
-            smp.sample(args.ess_samples, max_steps=4 * args.ess_samples)   # bounded: a chain deep in the infeasible region must not stall the batch
-            smp.synchronize()
+            smp.sample(n_s, max_steps=12 * n_s)      # bounded: a chain deep in the infeasible region must not stall the batch
+            barrier()
             ess_s = time.perf_counter() - t0
-            ns_k = smp.statistics()[3][:k]
-            n_rec = int(min(np.percentile(ns_k, 25), args.ess_samples))      # sequences must be equally long: keep the upper 75 %
-            use = [c for c in range(k) if ns_k[c] >= n_rec]
-            if n_rec >= 400 and len(use) >= 4:
-                series = smp.series().astype(np.float64)[use, :n_rec]
-                ms = D.MultiChainStats([D.ChainStats.from_series(x, n_lags=200, max_lag_proportion=0.5) for x in series])
-                per_chain = ms.effective_samples(reference_integer_division=False) / len(use)
-                ess = {"value": float(per_chain.min() * n_chains * world / ess_s),
-                       "unit": "effective samples/s (worst synopsis statistic, all chains)",
-                       "n_eff_per_chain": [round(float(x), 2) for x in per_chain], "feasible_samples_per_chain": n_rec,
-                       "sequences_analysed": len(use), "seconds": round(ess_s, 3), "burnin_steps_per_chain": args.ess_burnin,
-                       "rhat": [round(float(x), 4) for x in ms.potential_scale_reduction(reference_integer_division=False)]}
-            else:
-                ess = {"value": None, "note": f"too few feasible samples in {4 * args.ess_samples} steps (25th percentile {n_rec})"}
+            end, ss, sq, ns = smp.statistics()
+            full = ns >= n_s
+            k_pts = n_s // thin
+            series = smp.series()[full, :k_pts].astype(np.float64)
+            r = D.ensemble_effective_samples(series, thin, ns[full], ss[full], sq[full], group=8)
+            half = k_pts // 2
+            drift = (series[:, half:].mean(axis=(0, 1)) - series[:, :half].mean(axis=(0, 1))) / np.sqrt(r["var_plus"])
+            loc = torch.tensor(np.concatenate([r["n_eff"], [float(full.sum()), ess_s]]), dtype=torch.float64, device="cuda")
+            if world > 1:   # independent chains: effective samples add over the ranks; the slowest rank sets the time
+                mx = loc[-1:].clone()
+                dist.all_reduce(loc, op=dist.ReduceOp.SUM)
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                loc[-1] = mx[0]
+            tot = loc.cpu().numpy()
+            n_eff_all, chains_all, ess_s_all = tot[:n_syn], int(tot[n_syn]), float(tot[n_syn + 1])
+            ess = {"value": float(n_eff_all.min() / ess_s_all), "unit": "effective samples/s (worst synopsis statistic, all chains, all GPUs)",
+                   "n_eff": [round(float(x), 1) for x in n_eff_all], "chains": chains_all, "feasible_samples_per_chain": n_s,
+                   "seconds": round(ess_s_all, 2), "samples_per_effective_sample": [round(float(x)) for x in r["tau"]],
+                   "rhat": [round(float(x), 4) for x in r["rhat"]],
+                   "rhat_note": "per-chain sequences, reference formula; for stationary chains R-hat^2 = 1 + 1/(effective samples per sequence)",
+                   "rhat_pooled8": [round(float(x), 4) for x in r["rhat_grouped"]],
+                   "drift_second_minus_first_half_in_sd": [round(float(x), 4) for x in drift],
+                   "synopsis_mean": [round(float(x), 4) for x in (ss[full].sum(0) / ns[full].sum())],
+                   "estimator": "MultiChainStats::effectiveSamples (reference), variogram over all chains at stride %d, lags to n/2" % thin,
+                   "scope": "rank 0's chains for R-hat / drift / mean; n_eff summed over ranks"}
         except Exception as exc:   # the ESS estimate must never take the benchmark line down
             ess = {"value": None, "note": f"ESS estimate failed: {exc!r}"}
     barrier()
 
-    st = smp.stats
     if rank == 0:
         peak, peak_src = measured_peaks()
         kernel_ms = float(np.mean(launch_ms))
@@ -298,20 +364,23 @@ def bench_ours(args):
             "config": {"workload": desc, "chains_per_gpu": n_chains, "mh_steps_per_launch": mh, "rng": "philox4x32-10", "initial_states": "one prior sample per chain, drawn on the device",
                        "l2_policy": f"per-GPU chain state {P.info.chain_state_bytes * n_chains / 1e9:.1f} GB >> 126 MB L2 (inputs larger than L2)",
                        "problem": "reference generator seed 1234, kappa 10 (tests/golden)", "setup_seconds": round(setup_s, 1),
-                       "acceptance": round(st.totalAccepted() / max(st.nSamples(), 1), 4),
-                       "infeasible_fraction": round(st.nInfeasibleSamples() / max(st.nSamples(), 1), 4)},
+                       "state": f"stationary: timed after {args.burnin_steps} burn-in Metropolis steps per chain ({burn_s:.0f} s)",
+                       "acceptance": round(acc_stat, 4), "infeasible_fraction": round(inf_stat, 4),
+                       "post_init": {"value": value_post_init, "acceptance": round(acc_post_init, 4), "infeasible_fraction": round(inf_post_init, 4),
+                                     "what": "this rank's chain-steps/s straight after the feasibility search, before the burn-in"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_chain_step": bytes_per_step, "kernel": "abm::stepKernel<MODE_MCMC>",
                          "kernel_ms_per_launch": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
-                    "what": "abm_chains_sample (steps + on-device end-state/synopsis statistics) + abm_chains_enqueue_statistics / "
-                            "abm_chains_wait_statistics (ensemble reduction, statistics and counters into host buffers) + ensemble "
-                            "all-reduce, host clock, every step; launch k+1 is queued behind the read-back of launch k; inputs of a "
-                            "step are kernel arguments only (the problem and the chain states are uploaded once, at construction)"},
+                    "what": "abm_chains_sample (steps + on-device end-state/synopsis statistics) + abm_chains_enqueue_moments / "
+                            "abm_chains_wait_moments (device reduction of the ensemble moments, NCCL all-reduce inside the library, "
+                            "copy into host buffers), host clock, every step; launch k+1 is queued behind the reduction of launch k; "
+                            "a step has no per-step input to copy in: its inputs are kernel arguments, the problem and the chain "
+                            "states are uploaded once, at construction (h2d_bytes_per_step is 0 by the nature of the workload)"},
             "ensemble": {"chains": summary.n_chains, "feasible_samples": summary.n_samples,
                          "mean_agents_at_T": float(summary.end_state_mean.sum()),
-                         "rhat_synopsis": [round(float(x), 4) for x in summary.rhat]},
+                         "synopsis_mean": [round(float(x), 4) for x in summary.synopsis_mean]},
             "ess": ess,
             # per bench step of the timed region: refreshBlockedTopKernel (0.16 ms) + stepKernel<MODE_MCMC> (profiles/*_bench_launches.csv)
             "gpu_launches": 2 * args.steps,
@@ -321,6 +390,8 @@ def bench_ours(args):
             line["cpu_baseline"] = cpu_baseline(args.workload, os.cpu_count() or 1)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -337,13 +408,17 @@ def main():
     ap.add_argument("--mh-steps", type=int, default=2000, help="Metropolis steps per chain per launch")
     ap.add_argument("--seed", type=int, default=20221)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ess-samples", type=int, default=0,
-                    help="feasible samples per chain for the ESS/s estimate (0 = skip; needs --ess-burnin steps first, ~2 more minutes)")
-    ap.add_argument("--ess-burnin", type=int, default=3000000, help="Metropolis steps per chain before the ESS estimate")
-    ap.add_argument("--ess-chains", type=int, default=64, help="chains whose synopsis series are analysed for ESS/s")
+    ap.add_argument("--burnin-steps", type=int, default=-1,
+                    help="Metropolis steps per chain before anything is timed (the ensemble is stationary from ~6e6 at 32x32x16)")
+    ap.add_argument("--ess-samples", type=int, default=-1,
+                    help="feasible samples per chain of the ESS / R-hat window (0 = skip); ~1 minute per 1e6 at 32x32x16")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.burnin_steps < 0:
+        args.burnin_steps = STATIONARY[args.workload][0]
+    if args.ess_samples < 0:
+        args.ess_samples = STATIONARY[args.workload][1]
     if args.impl == "reference":
         return bench_reference(args)
     return bench_ours(args)

@@ -224,6 +224,13 @@ ABM_API int abm_chains_allreduce_moments(abm_chains *c, abm_comm *comm, int64_t 
 ABM_API int abm_chains_enqueue_moments(abm_chains *c, abm_comm *comm);
 ABM_API int abm_chains_wait_moments(abm_chains *c, int64_t *exact, double *real);
 
+/* Blocked sum tree (ABM_TREE_BLOCKED): its sums are kept incrementally by the step kernel -- the two upper levels are recomputed
+ * from the level below before every launch, the sums of 32 leaves from the leaves every 256th launch.  abm_chains_rebuild_tree
+ * forces that exact rebuild now; abm_chains_tree_drift measures one chain: out = {root, max |sum - exact sum of its leaves| over
+ * the sums of 32, of 1024, of 32768 leaves} (exact sums in extended precision on the host).  Measurement / test aid. */
+ABM_API int abm_chains_rebuild_tree(abm_chains *c);
+ABM_API int abm_chains_tree_drift(abm_chains *c, int32_t chain, double out[4]);
+
 /* Device time of the last abm_chains_step / _step_traced / _sample launch (CUDA events on the chains' stream around the
  * step kernel; waits for it to finish).  For measurements: the traced variant's host copies are outside. */
 ABM_API int abm_chains_last_launch_ms(abm_chains *c, float *ms);

@@ -312,3 +312,23 @@ def test_device_prior_initial_states_match_reference_prior(name):
     for c in range(4):
         delta = smp2.state(c)[1]
         assert np.array_equal(delta == -1, smp2.prior_sample[c][nb_col] > 0)
+
+
+def test_blocked_tree_tracks_reference_tree_and_its_sums_stay_exact():
+    """Short version of scripts/tree_soak.py (1e7 steps: profiles/r2_tree_soak.json): the same chains on the same Philox
+    streams in both storages of basisDistribution draw the same columns and take the same decisions; the blocked tree's
+    incrementally kept sums stay within rounding of the exact sums of their leaves, and an explicit rebuild makes the sums of
+    32 leaves exact."""
+    S = _gpu()
+    p = load_golden("pp16-8.abmp.xz")
+    smp = {t: S.SparseBasisSampler(S.Problem(p, sum_tree=t), n_chains=8, seed=99, first_chain_id=3) for t in TREES}
+    for _ in range(4):
+        tr = {t: smp[t].step_traced(50000) for t in TREES}
+        assert np.array_equal(tr["blocked"][0], tr["reference"][0]) and np.array_equal(tr["blocked"][1], tr["reference"][1])
+    for c in range(8):
+        assert np.array_equal(smp["blocked"].state(c)[0], smp["reference"].state(c)[0])
+    d = smp["blocked"].tree_drift(0)
+    assert d[0] > 0 and np.all(d[1:] <= 1e-11 * d[0])
+    smp["blocked"].rebuild_tree()
+    d2 = smp["blocked"].tree_drift(0)
+    assert d2[1] <= 32 * 2.3e-16 * 32      # sums of 32 leaves (each <= 1) recomputed: ordinary summation rounding only
