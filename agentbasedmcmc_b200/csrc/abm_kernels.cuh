@@ -341,10 +341,12 @@ __device__ __noinline__ int endStateEffects(const int32_t *__restrict__ fx, int 
     return gl < nSynopsis ? dj * (int)(int8_t)(__ldg(fx + 1 + (gl >> 2)) >> (8 * (gl & 3))) : 0;
 }
 
+// every seriesThin-th feasible sample of a chain goes to its series (slot = sample index / seriesThin); the step loop counts
+// the samples down to the next one, so this runs once per seriesThin samples
 __device__ __noinline__ void recordSeries(int32_t *series, int seriesThin, int seriesCap, int nSynopsis, int chain, long long tot,
                                           int gl, int syn) {
-    if (tot % seriesThin == 0 && tot / seriesThin < seriesCap)
-        series[((size_t)chain * seriesCap + tot / seriesThin) * nSynopsis + gl] = syn;
+    const long long slot = tot / seriesThin;
+    if (slot < seriesCap) series[((size_t)chain * seriesCap + slot) * nSynopsis + gl] = syn;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -380,12 +382,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     const int chain = (blockIdx.x * kWarpsPerCta + warp) * NG + g;
     int validBit = chain < S.nChains ? 1 : 0;
     int chainC = validBit ? chain : 0;   // pointer arithmetic only; every access is predicated
-#if ABM_PIN_IDS
+#if ABM_PIN_IDS == 1
     // With 72 registers per thread the compiler otherwise re-derives the lane, the chain and everything that hangs off them
-    // from the special registers wherever they are used in the step loop (14 % of the executed instructions,
-    // profiles/r2c_*): an empty asm makes the three values opaque, so they are kept (or, at worst, reloaded).
+    // from the special registers wherever they are used in the step loop (7 % of the executed instructions,
+    // profiles/r2_stationary_*): an empty asm makes the values opaque, so they are kept (or, at worst, reloaded).
     asm volatile("" : "+r"(gl));
     asm volatile("" : "+r"(gBase));
+    asm volatile("" : "+r"(validBit));
+    asm volatile("" : "+r"(chainC));
+#elif ABM_PIN_IDS == 2
+    asm volatile("" : "+r"(validBit));
+#elif ABM_PIN_IDS == 3
     asm volatile("" : "+r"(validBit));
     asm volatile("" : "+r"(chainC));
 #endif
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     const int cSUCap = BLK ? 0 : cSCap;
     const int gBytes = groupSmemBytes(cRowsCap, cSCap, cTCap, cScrCap, cMaxAbs, cNodeCap, cT2Cap, cSUCap);
     unsigned char *gs = smemRaw + (size_t)(warp * NG + g) * gBytes;
-#if ABM_PIN_IDS
+#if ABM_PIN_IDS == 1
     asm volatile("" : "+l"(gs));
 #endif
     uint32_t *sRec = reinterpret_cast<uint32_t *>(gs);                   // [kRecWinWords] head of the proposed column's record
@@ -478,7 +485,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     int nSamp = 0;                      // feasible samples taken in this launch
     int fxN = 0, fxK = 0, fxS = 0;      // pending end-state effect of an accepted proposal (ABM_END_DEFERRED)
     int syn = 0;                        // lane k < nSynopsis: agents inside the k-th nested square (FiguresForPaper.h:245-263)
+    int serLeft = 0x7fffffff;           // feasible samples until the next one that goes to the thinned series
     if (kSample) {   // end-state occupancy and synopsis were prepared by sampleBeginKernel
+        if (R.series && chainValid && chainC < R.nSeriesChains) {
+            const long long r = S.nSamples[chainC] % R.seriesThin;
+            serLeft = r == 0 ? 0 : (int)(R.seriesThin - r);
+        }
         if (chainValid && gl < P.nSynopsis) syn = S.synNow[(size_t)chain * P.nSynopsis + gl];
         if (gl < 16) sSyn[gl] = 0;
         __syncwarp();
@@ -842,14 +854,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 if (p1 != (unsigned)kPairNone) acc = __dadd_rn(acc, rowTerm(p1));
             }
             if (__any_sync(kFull, ext)) {   // columns sharing more than two rows with the proposed one: their pair lists
+                // {count, pair, pair, ...} one byte each; the first two words (seven pairs) are fetched at once and the pairs
+                // picked out of registers, longer lists (rare) continue from the record
                 const int lw = xtraOff + (int)p1;
-                const int cnt = ext ? (int)(recWord(lw) & 0xffu) : 0;
+                unsigned long long lst = 0ull;
+                if (ext) lst = (unsigned long long)recWord(lw) | ((unsigned long long)recWord(lw + 1) << 32);
+                const int cnt = (int)(lst & 0xffull);
                 const int tW = warpMax(cnt);
 #pragma unroll 1
                 for (int t = 0; t < tW; ++t) {
                     if (t < cnt) {
                         const int bi = 1 + t;
-                        acc = __dadd_rn(acc, rowTerm((recWord(lw + (bi >> 2)) >> (8 * (bi & 3))) & 0xffu));
+                        const unsigned pb = bi < 8 ? (unsigned)(lst >> (8 * bi)) & 0xffu : (recWord(lw + (bi >> 2)) >> (8 * (bi & 3))) & 0xffu;
+                        acc = __dadd_rn(acc, rowTerm(pb));
                     }
                 }
             }
@@ -1135,8 +1152,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 if (gl < P.nSynopsis) {   // MeanAndVariance::operator(), diagnostics/MeanAndVariance.h:35-45 (exact in int64)
                     sSyn[gl] += syn;
                     sSyn[8 + gl] += (long long)syn * syn;
-                    if (R.series && chainC < R.nSeriesChains) recordSeries(R.series, R.seriesThin, R.seriesCap, P.nSynopsis, chainC, S.nSamples[chainC] + nSamp, gl, syn);
+                    if (serLeft == 0) recordSeries(R.series, R.seriesThin, R.seriesCap, P.nSynopsis, chainC, S.nSamples[chainC] + nSamp, gl, syn);
                 }
+                serLeft = serLeft == 0 ? R.seriesThin - 1 : serLeft - 1;
                 ++nSamp;
             }
         }

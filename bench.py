@@ -36,7 +36,7 @@ WORKLOADS = {
     "pp8-4": ("pp8-4.abmp.xz", 1024, 3567.0, "PredPrey 8x8 grid, 4 timesteps, 1024 chains/GPU"),
 }
 # workload -> (burn-in Metropolis steps per chain before anything is timed, feasible samples per chain of the ESS window)
-STATIONARY = {"pp32-16": (7000000, 1000000), "pp16-8": (1500000, 200000), "pp8-4": (200000, 100000)}
+STATIONARY = {"pp32-16": (6000000, 1600000), "pp16-8": (1500000, 300000), "pp8-4": (200000, 100000)}
 METRIC = "chain-steps/sec, 32x32 PredPrey (SparseBasisSampler Metropolis steps, all chains, all GPUs)"
 UNIT = "chain-steps/s"
 
@@ -110,13 +110,15 @@ def run_reference_binary(fixture: str, threads: int, samples_per_step: int, warm
 
 
 def reference_tau(workload: str):
-    """Feasible samples per effective sample of the reference chain (worst synopsis statistic), from the long reference run
-    behind the paper-scale posterior fixture (tests/golden/make_posterior_golden.py); None when there is no such fixture."""
+    """Metropolis steps per effective sample of the stationary reference chain (worst synopsis statistic): its autocorrelation
+    time in feasible samples (reference estimator) x its steps per feasible sample, both from the long reference run behind the
+    paper-scale posterior fixture (tests/golden/make_posterior_golden.py); None when there is no such fixture."""
     p = ROOT / "tests" / "golden" / f"posterior_{workload}.abmp.xz"
     if not p.exists():
         return None
     from agentbasedmcmc_b200.abmp import read_abmp
-    return float(read_abmp(p)["tau_int"].max())
+    f = read_abmp(p)
+    return float(f["tau_int"].max() * f["steps_per_sample"][0])
 
 
 def cpu_baseline(workload: str, threads: int, seconds_budget: float = 20.0):
@@ -170,10 +172,11 @@ def bench_reference(args):
                   f"timed, per-thread rates summed")
         tau = reference_tau(args.workload)
         if tau:
-            sps = threads * samples * len(res["step_seconds"]) / sum(res["step_seconds"])
-            ess = {"value": sps / tau, "unit": "effective samples/s (worst synopsis statistic)", "derived": True,
-                   "how": f"{sps:.0f} feasible samples/s measured here / {tau:.0f} feasible samples per effective sample, the reference "
-                          f"chain's autocorrelation time from the long reference run (tests/golden/posterior_{args.workload}.abmp.xz)"}
+            ess = {"value": value / tau, "unit": "effective samples/s (worst synopsis statistic)", "derived": True,
+                   "how": f"{value:.0f} chain-steps/s measured here / {tau:.0f} Metropolis steps per effective sample of the stationary "
+                          f"reference chain (its autocorrelation time in feasible samples x its steps per feasible sample, from the long "
+                          f"reference run behind tests/golden/posterior_{args.workload}.abmp.xz); the chains timed here are still "
+                          f"relaxing from their start, a short CPU run cannot measure an autocorrelation time of ~1e5 samples"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "host_threads": cores},
@@ -262,6 +265,53 @@ def bench_ours(args):
     barrier()
     burn_s = time.time() - t_burn
 
+    # ---- ESS/s and R-hat at the stationary state (the second half of BASELINE.json's metric): every chain takes the same
+    # number of feasible samples (operator() semantics); the reference's estimator (MultiChainStats::effectiveSamples,
+    # diagnostics/MultiChainStats.h:81-102) with its lag grid (200 strided lags to half the sequence, FiguresForPaper.h:89-90),
+    # the variogram averaged over ALL chains from every stride-th sample, var+ from the exact per-chain moments.
+    ess = None
+    if args.ess_samples > 0:
+        try:
+            n_s = args.ess_samples
+            thin = max(1, n_s // 400)
+            smp.reset_statistics()
+            smp.record_series(n_chains, thin, n_s // thin + 1)
+            barrier()
+            t0 = time.perf_counter()
+            smp.sample(n_s, max_steps=12 * n_s)      # bounded: a chain deep in the infeasible region must not stall the batch
+            barrier()
+            ess_s = time.perf_counter() - t0
+            end, ss, sq, ns = smp.statistics()
+            ser = smp.series()
+            smp.record_series(0, 1, 0)               # stop recording
+            full = ns >= n_s
+            k_pts = n_s // thin
+            series = ser[full, :k_pts].astype(np.float64)
+            r = D.ensemble_effective_samples(series, thin, ns[full], ss[full], sq[full], group=8)
+            half = k_pts // 2
+            drift = (series[:, half:].mean(axis=(0, 1)) - series[:, :half].mean(axis=(0, 1))) / np.sqrt(r["var_plus"])
+            loc = torch.tensor(np.concatenate([r["n_eff"], [float(full.sum()), ess_s]]), dtype=torch.float64, device="cuda")
+            if world > 1:   # independent chains: effective samples add over the ranks; the slowest rank sets the time
+                mx = loc[-1:].clone()
+                dist.all_reduce(loc, op=dist.ReduceOp.SUM)
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                loc[-1] = mx[0]
+            tot = loc.cpu().numpy()
+            n_eff_all, chains_all, ess_s_all = tot[:n_syn], int(tot[n_syn]), float(tot[n_syn + 1])
+            ess = {"value": float(n_eff_all.min() / ess_s_all), "unit": "effective samples/s (worst synopsis statistic, all chains, all GPUs)",
+                   "n_eff": [round(float(x), 1) for x in n_eff_all], "chains": chains_all, "feasible_samples_per_chain": n_s,
+                   "seconds": round(ess_s_all, 2), "samples_per_effective_sample": [round(float(x)) for x in r["tau"]],
+                   "rhat": [round(float(x), 4) for x in r["rhat"]],
+                   "rhat_note": "per-chain sequences, reference formula; for stationary chains R-hat^2 = 1 + 1/(effective samples per sequence)",
+                   "rhat_pooled8": [round(float(x), 4) for x in r["rhat_grouped"]],
+                   "drift_second_minus_first_half_in_sd": [round(float(x), 4) for x in drift],
+                   "synopsis_mean": [round(float(x), 4) for x in (ss[full].sum(0) / ns[full].sum())],
+                   "estimator": "MultiChainStats::effectiveSamples (reference), variogram over all chains at stride %d, lags to n/2" % thin,
+                   "scope": "rank 0's chains for R-hat / drift / mean; n_eff summed over ranks"}
+        except Exception as exc:   # the ESS estimate must never take the benchmark line down
+            ess = {"value": None, "note": f"ESS estimate failed: {exc!r}"}
+    barrier()
+
     # ---- device-resident throughput at the stationary state: W warm-up launches, then exactly K timed launches
     for _ in range(args.warmup):
         smp.step(mh)
@@ -302,51 +352,6 @@ def bench_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = steps_done / float(te.item())
 
-    # ---- ESS/s and R-hat at the stationary state (the second half of BASELINE.json's metric): every chain takes the same
-    # number of feasible samples (operator() semantics); the reference's estimator (MultiChainStats::effectiveSamples,
-    # diagnostics/MultiChainStats.h:81-102) with its lag grid (200 strided lags to half the sequence, FiguresForPaper.h:89-90),
-    # the variogram averaged over ALL chains from every stride-th sample, var+ from the exact per-chain moments.
-    ess = None
-    if args.ess_samples > 0:
-        try:
-            n_s = args.ess_samples
-            thin = max(1, n_s // 400)
-            smp.reset_statistics()
-            smp.record_series(n_chains, thin, n_s // thin + 1)
-            barrier()
-            t0 = time.perf_counter()
-            smp.sample(n_s, max_steps=12 * n_s)      # bounded: a chain deep in the infeasible region must not stall the batch
-            barrier()
-            ess_s = time.perf_counter() - t0
-            end, ss, sq, ns = smp.statistics()
-            full = ns >= n_s
-            k_pts = n_s // thin
-            series = smp.series()[full, :k_pts].astype(np.float64)
-            r = D.ensemble_effective_samples(series, thin, ns[full], ss[full], sq[full], group=8)
-            half = k_pts // 2
-            drift = (series[:, half:].mean(axis=(0, 1)) - series[:, :half].mean(axis=(0, 1))) / np.sqrt(r["var_plus"])
-            loc = torch.tensor(np.concatenate([r["n_eff"], [float(full.sum()), ess_s]]), dtype=torch.float64, device="cuda")
-            if world > 1:   # independent chains: effective samples add over the ranks; the slowest rank sets the time
-                mx = loc[-1:].clone()
-                dist.all_reduce(loc, op=dist.ReduceOp.SUM)
-                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-                loc[-1] = mx[0]
-            tot = loc.cpu().numpy()
-            n_eff_all, chains_all, ess_s_all = tot[:n_syn], int(tot[n_syn]), float(tot[n_syn + 1])
-            ess = {"value": float(n_eff_all.min() / ess_s_all), "unit": "effective samples/s (worst synopsis statistic, all chains, all GPUs)",
-                   "n_eff": [round(float(x), 1) for x in n_eff_all], "chains": chains_all, "feasible_samples_per_chain": n_s,
-                   "seconds": round(ess_s_all, 2), "samples_per_effective_sample": [round(float(x)) for x in r["tau"]],
-                   "rhat": [round(float(x), 4) for x in r["rhat"]],
-                   "rhat_note": "per-chain sequences, reference formula; for stationary chains R-hat^2 = 1 + 1/(effective samples per sequence)",
-                   "rhat_pooled8": [round(float(x), 4) for x in r["rhat_grouped"]],
-                   "drift_second_minus_first_half_in_sd": [round(float(x), 4) for x in drift],
-                   "synopsis_mean": [round(float(x), 4) for x in (ss[full].sum(0) / ns[full].sum())],
-                   "estimator": "MultiChainStats::effectiveSamples (reference), variogram over all chains at stride %d, lags to n/2" % thin,
-                   "scope": "rank 0's chains for R-hat / drift / mean; n_eff summed over ranks"}
-        except Exception as exc:   # the ESS estimate must never take the benchmark line down
-            ess = {"value": None, "note": f"ESS estimate failed: {exc!r}"}
-    barrier()
-
     if rank == 0:
         peak, peak_src = measured_peaks()
         kernel_ms = float(np.mean(launch_ms))
@@ -364,7 +369,8 @@ def bench_ours(args):
             "config": {"workload": desc, "chains_per_gpu": n_chains, "mh_steps_per_launch": mh, "rng": "philox4x32-10", "initial_states": "one prior sample per chain, drawn on the device",
                        "l2_policy": f"per-GPU chain state {P.info.chain_state_bytes * n_chains / 1e9:.1f} GB >> 126 MB L2 (inputs larger than L2)",
                        "problem": "reference generator seed 1234, kappa 10 (tests/golden)", "setup_seconds": round(setup_s, 1),
-                       "state": f"stationary: timed after {args.burnin_steps} burn-in Metropolis steps per chain ({burn_s:.0f} s)",
+                       "state": f"stationary: timed after {args.burnin_steps} burn-in Metropolis steps per chain ({burn_s:.0f} s) and the ESS window "
+                                f"({args.ess_samples} feasible samples per chain)",
                        "acceptance": round(acc_stat, 4), "infeasible_fraction": round(inf_stat, 4),
                        "post_init": {"value": value_post_init, "acceptance": round(acc_post_init, 4), "infeasible_fraction": round(inf_post_init, 4),
                                      "what": "this rank's chain-steps/s straight after the feasibility search, before the burn-in"}},

@@ -482,7 +482,7 @@ int cmdBench(const AbmpFile &f, int nThreads, long samplesPerStep, int warmup, i
     double setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
     // Every thread times its own loop: a round's Metropolis-step rate is the SUM of the per-thread rates (steps per feasible
     // sample vary widely between chains, so joining the threads and dividing by the slowest would under-report the CPU).
-    std::vector<double> secs, rates;
+    std::vector<double> secs, rates, sampleRates;
     std::vector<long> stepCounts;
     for (int r = 0; r < warmup + steps; ++r) {
         std::vector<double> tSec(nThreads, 0.0);
@@ -502,11 +502,12 @@ int cmdBench(const AbmpFile &f, int nThreads, long samplesPerStep, int warmup, i
         for (auto &x : fut) x.wait();
         double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (r >= warmup) {
-            double rate = 0.0;
+            double rate = 0.0, srate = 0.0;
             long st = 0;
-            for (int t = 0; t < nThreads; ++t) { rate += tSteps[t] / tSec[t]; st += tSteps[t]; }
+            for (int t = 0; t < nThreads; ++t) { rate += tSteps[t] / tSec[t]; srate += samplesPerStep / tSec[t]; st += tSteps[t]; }
             secs.push_back(dt);
             rates.push_back(rate);
+            sampleRates.push_back(srate);
             stepCounts.push_back(st);
         }
     }
@@ -516,6 +517,8 @@ int cmdBench(const AbmpFile &f, int nThreads, long samplesPerStep, int warmup, i
     for (size_t k = 0; k < stepCounts.size(); ++k) printf("%s%ld", k ? ", " : "", stepCounts[k]);
     printf("], \"steps_per_s\": [");
     for (size_t k = 0; k < rates.size(); ++k) printf("%s%.3f", k ? ", " : "", rates[k]);
+    printf("], \"samples_per_s\": [");
+    for (size_t k = 0; k < sampleRates.size(); ++k) printf("%s%.3f", k ? ", " : "", sampleRates[k]);
     printf("]}\n");
     return 0;
 }

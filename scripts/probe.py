@@ -26,6 +26,13 @@ def main():
     dt = time.time() - t0
     it = smp.init_iterations
     print(f"init: {dt:.2f}s, iterations mean={it.mean():.0f} max={it.max()} -> {it.sum()/dt/1e6:.2f} M it/s", flush=True)
+    burn = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--burnin=")]
+    if burn:   # bring the ensemble to its stationary state first (bench.py does the same before it times anything)
+        t0 = time.time()
+        for _ in range(burn[0] // 250000):
+            smp.step(250000)
+        smp.synchronize()
+        print(f"burn-in: {burn[0]} steps in {time.time()-t0:.1f}s", flush=True)
     smp.step(n_steps)
     smp.synchronize()
     for r in range(reps):
