@@ -125,92 +125,92 @@ struct Tableau {
         if (liveRows.contains(i)) liveRows.erase(i);
     }
 
-    // findMarkowitzPivot (:252-285); maxVectorsToTest = 10 (:57)
+    // Pivot selection.  Semantics (and only the semantics) of TableauNormMinimiser::findMarkowitzPivot (:252-285): candidates
+    // are visited by increasing sparsity k -- first the columns with k entries, each paired with its sparsest eligible row,
+    // then the rows with k entries, each paired with its sparsest eligible column -- the candidate with the strictly smallest
+    // Markowitz count (r - 1)(c - 1) so far is kept, and the search stops at once when that count cannot be beaten any more
+    // at this sparsity ((k - 1)^2), or after ten candidates (:57).  The visiting order is what makes the basis the
+    // reference's, so it is kept; the bucket lists hold eligible vectors only, which is where the speed comes from.
     std::pair<int, int> findMarkowitzPivot() {
-        const int maxVectorsToTest = 10;
-        int k = 1, lowestScore = INT_MAX, vectorsTested = 0;
-        std::pair<int, int> bestPivot(-1, -1);
-        while (k < colsBySparsity.size && k < rowsBySparsity.size) {
-            for (int j = liveCols.first(k); j >= 0; j = liveCols.next[j]) {
-                const int bestRow = sparsestRowInCol(j);
-                if (bestRow != -1) {
-                    const int score = ((int)rows[bestRow].size() - 1) * ((int)cols[j].size() - 1);
-                    if (score < lowestScore) {
-                        bestPivot = std::make_pair(bestRow, j);
-                        if (score <= (k - 1) * (k - 1)) return bestPivot;
-                        lowestScore = score;
-                    }
-                    if (++vectorsTested >= maxVectorsToTest) return bestPivot;
-                }
+        constexpr int kCandidateLimit = 10;
+        std::pair<int, int> chosen(-1, -1);
+        int chosenCount = INT_MAX, seen = 0;
+        bool done = false;
+        // returns true when the search is over
+        auto consider = [&](int row, int col, int k) {
+            const int count = ((int)rows[row].size() - 1) * ((int)cols[col].size() - 1);
+            if (count < chosenCount) {
+                chosen = std::make_pair(row, col);
+                if (count <= (k - 1) * (k - 1)) return true;
+                chosenCount = count;
             }
-            for (int i = liveRows.first(k); i >= 0; i = liveRows.next[i]) {
-                const int bestCol = sparsestColInRow(i);
-                if (bestCol != -1) {
-                    const int score = ((int)rows[i].size() - 1) * ((int)cols[bestCol].size() - 1);
-                    if (score < lowestScore) {
-                        bestPivot = std::make_pair(i, bestCol);
-                        if (score <= (k - 1) * (k - 1)) return bestPivot;
-                        lowestScore = score;
-                    }
-                    if (++vectorsTested >= maxVectorsToTest) return bestPivot;
-                }
+            return ++seen >= kCandidateLimit;
+        };
+        for (int k = 1; !done && k < colsBySparsity.size && k < rowsBySparsity.size; ++k) {
+            for (int col = liveCols.first(k); !done && col >= 0; col = liveCols.next[col]) {
+                const int row = sparsestRowInCol(col);
+                if (row != -1) done = consider(row, col, k);
             }
-            ++k;
+            for (int row = liveRows.first(k); !done && row >= 0; row = liveRows.next[row]) {
+                const int col = sparsestColInRow(row);
+                if (col != -1) done = consider(row, col, k);
+            }
         }
-        return bestPivot;
+        return chosen;
     }
 
-    // pivot (:288-335).  T is an integer type in the reference (ABM::occupation_type), pivots have unit magnitude, so
-    // `-1.0 / Mpipj` converts to -1 or +1 exactly.
-    void pivot(int pi, int pj) {
-        const int Mpipj = at(pi, pj);
-        for (const Entry &e : rows[pi]) removeCol(e.first);
-        const int c = (int)(-1.0 / Mpipj);
-        for (Entry &e : rows[pi]) e.second *= c;
-        F[pi] = (int)(F[pi] * (-1.0 / Mpipj));
-        const std::vector<Entry> &prow = rows[pi];
-        for (int i : cols[pj]) {
-            if (i == pi) continue;
+    // One elimination step (what TableauNormMinimiser::pivot does, :288-335): the pivot row is scaled so that its pivot entry
+    // becomes -1, then added to every other row of the pivot column so that the column keeps its pivot entry only.  Entries are
+    // integers and pivots have unit magnitude (ABM::occupation_type in the reference), so the scale factor is exactly -1 or +1.
+    void pivot(int prow, int pcol) {
+        const int pivotEntry = at(prow, pcol);
+        for (const Entry &e : rows[prow]) removeCol(e.first);
+        const int scale = (int)(-1.0 / pivotEntry);
+        for (Entry &e : rows[prow]) e.second *= scale;
+        F[prow] = (int)(F[prow] * (-1.0 / pivotEntry));
+        const std::vector<Entry> &src = rows[prow];
+        for (int i : cols[pcol]) {
+            if (i == prow) continue;
             if (rowActive[i]) removeRow(i);
-            const int Mipj = at(i, pj);
-            std::vector<Entry> &ri = rows[i];
-            for (const Entry &pe : prow) {
+            const int factor = at(i, pcol);
+            std::vector<Entry> &dst = rows[i];
+            for (const Entry &pe : src) {
                 const int j = pe.first;
-                if (j == pj) continue;
-                auto it = findIn(ri, j);
-                if (it == ri.end() || it->first != j) {   // fill-in
-                    ri.insert(it, Entry(j, Mipj * pe.second));
+                if (j == pcol) continue;
+                auto it = findIn(dst, j);
+                if (it == dst.end() || it->first != j) {          // the row gains an entry in column j
+                    dst.insert(it, Entry(j, factor * pe.second));
                     insertSorted(cols[j], i);
                 } else {
-                    it->second += Mipj * pe.second;
-                    if (it->second == 0) {                // drop-out
+                    it->second += factor * pe.second;
+                    if (it->second == 0) {                        // the entry cancels
                         eraseSorted(cols[j], i);
-                        ri.erase(it);
+                        dst.erase(it);
                     }
                 }
             }
-            F[i] += Mipj * F[pi];
+            F[i] += factor * F[prow];
         }
-        for (int i : cols[pj]) {
-            if (i == pi) continue;
-            std::vector<Entry> &ri = rows[i];
-            auto it = findIn(ri, pj);
-            if (it != ri.end() && it->first == pj) ri.erase(it);
+        for (int i : cols[pcol]) {
+            if (i == prow) continue;
+            std::vector<Entry> &dst = rows[i];
+            auto it = findIn(dst, pcol);
+            if (it != dst.end() && it->first == pcol) dst.erase(it);
         }
         // the column becomes basic before the rows are re-listed: a row's eligibility looks at colBasic, and the reference's
-        // rows no longer contain pj at that point either
-        colBasic[pj] = 1;
-        for (int i : cols[pj])
-            if (i != pi && rowActive[i]) addRow(i);
-        cols[pj].assign(1, pi);   // setColBasic (:396-402)
-        basis[pi] = pj;
+        // rows no longer contain pcol at that point either
+        colBasic[pcol] = 1;
+        for (int i : cols[pcol])
+            if (i != prow && rowActive[i]) addRow(i);
+        cols[pcol].assign(1, prow);   // setColBasic (:396-402)
+        basis[prow] = pcol;
         // the pivot row stops being active before its columns are re-listed: their eligibility must not count it, exactly as
         // the reference's later sparsestRowInCol() calls would not
-        removeRow(pi);            // inactivateRow (:404-409)
-        rowActive[pi] = 0;
-        for (const Entry &pe : rows[pi]) {
-            if (pe.first == pj) continue;
-            eraseSorted(cols[pe.first], pi);   // cols[] only stores non-reduced rows
+        removeRow(prow);              // inactivateRow (:404-409)
+        rowActive[prow] = 0;
+        for (const Entry &pe : rows[prow]) {
+            if (pe.first == pcol) continue;
+            eraseSorted(cols[pe.first], prow);   // column lists hold the rows that are still to be reduced
             addCol(pe.first);
         }
     }

@@ -74,6 +74,17 @@ constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 #ifndef ABM_PF_IMP
 #define ABM_PF_IMP 1
 #endif
+// ABM_POOL: measurement switch: the two chains of a warp share their lanes over the coupled-column chunks and over the commit
+// rounds: while both have chunks left each half-warp serves its own chain, afterwards both serve the longer list, two
+// adjacent chunks per round, so a round is as long as HALF the two lists together instead of the longer one (3.9 -> 2.9
+// rounds per warp-step at the stationary state of 32x32x16).  Every chunk is still handled by 16 consecutive lanes and the
+// sums receive their deltas in ascending chunk order, so the arithmetic is bit for bit that of the unpooled loops (the GPU
+// suite passes with it).  Measured SLOWER (32x32x16: 436 vs 487 M steps/s; 16x16x8 stationary: 429 vs 478,
+// profiles/r2_ab_m_pool.log): serving the partner's chain puts two more dependent shared-memory reads (its header fields,
+// then the slot word) in front of every chunk's chain-state load, and that costs more than the saved rounds.  Off.
+#ifndef ABM_POOL
+#define ABM_POOL 0
+#endif
 #ifndef ABM_UNIT_ONLY
 #define ABM_UNIT_ONLY 0
 #endif
@@ -321,7 +332,7 @@ __device__ __forceinline__ int selectDescending(const double (&v)[32 / W], doubl
 // 1024 leaves when they are kept in shared memory for the launch (0 otherwise)
 // suCap: the coupled-column ids of a step (reference tree: sCap; the blocked tree reads them from the record window: 0)
 __host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs, int nodeCap, int t2Cap, int suCap) {
-    return (kRecWinBytes + 16 + scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + 8 + 8 * 4 + suCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
+    return (kRecWinBytes + 16 + 32 + scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + 8 + 8 * 4 + suCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
 }
 
 // MODE_SAMPLE: an accepted proposal (dj != 0) with events in the last timestep moves the end state ModelState(traj,T,T).
@@ -409,7 +420,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 #endif
     uint32_t *sRec = reinterpret_cast<uint32_t *>(gs);                   // [kRecWinWords] head of the proposed column's record
     unsigned long long *sBar = reinterpret_cast<unsigned long long *>(gs + kRecWinBytes);   // mbarrier of the record copy
-    double2 *sScr = reinterpret_cast<double2 *>(gs + kRecWinBytes + 16);  // [scrCap] blocked tree: {DE', signed leaf} of the first
+    int *sCtx = reinterpret_cast<int *>(gs + kRecWinBytes + 16);          // [8] this step's record header fields, for the partner
+                                                                         //   half-warp when it serves this chain (ABM_POOL)
+    double2 *sScr = reinterpret_cast<double2 *>(gs + kRecWinBytes + 16 + 32);  // [scrCap] blocked tree: {DE', signed leaf} of the first
                                                                          //   coupled columns of a step (the rest: S.scratch)
     double *sDl = reinterpret_cast<double *>(sScr + cScrCap);            // [sCap] delta of set() per coupled column
     double *sG = sDl + cSCap;                                            // [rowsCap][2 maxAbs] per row: DE' term for a coupled
@@ -468,8 +481,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 #endif
     __syncwarp();
     int itersDone = 0;                  // iterations (init + MH) this chain made in this launch (a launch is at most 2^30 steps)
-    const double kappa = P.kappa;
-    const double *__restrict__ facVal = P.facVal;
+    constexpr bool kPool = FIX && W == 16 && ABM_POOL != 0;
+    // a pointer into this group's shared memory, moved to the same array of group `grp` of the warp
+    auto ofGroup = [&](auto *ptr, int grp) { return reinterpret_cast<decltype(ptr)>(reinterpret_cast<unsigned char *>(ptr) + (grp - g) * gBytes); };
+    const int chainBase0 = (blockIdx.x * kWarpsPerCta + warp) * NG;   // the chain of the warp's group 0
     const int nCols = P.nCols;
     const int kTwoM = FIX ? 2 : P.twoM, kMaxAbs = FIX ? 1 : P.maxAbs;   // FIX: unit tableau entries (constants after inlining)
     // ABM_PHILOX_BLOCK: lane gl of a group draws the Philox block of the chain's iteration iter + gl, i.e. W iterations at once,
@@ -725,6 +740,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
         }
         const int infN = infeas + groupSumInt<W>(dinf);
+        if constexpr (kPool) {
+            if (gl == 0) {
+                sCtx[0] = C; sCtx[1] = slotOff; sCtx[2] = uBase; sCtx[3] = wide; sCtx[4] = xtraOff; sCtx[5] = j; sCtx[6] = (int)ri.x;
+            }
+        }
         __syncwarp();
 
         // coupled columns, one per lane, ascending.  A column's DE' is currentDE[u] plus one term per shared
@@ -804,6 +824,111 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         };
         if (kMC && kImpEarly) importance();
         double csLane = 0.0;   // BLK: this lane's share of changeInSum
+        // chunks of 16 coupled columns: mine, the partner group's, and how the two half-warps share them (ABM_POOL)
+        const int nChMine = (C + W - 1) / W;
+        int nChOth = 0, nChBoth = 0, poolRounds = 0;
+        bool poolMineLong = false;
+        if constexpr (kPool) {
+            nChOth = __shfl_xor_sync(kFull, nChMine, W);
+            nChBoth = min(nChMine, nChOth);
+            poolMineLong = nChMine > nChOth;
+            poolRounds = nChBoth + ((max(nChMine, nChOth) - nChBoth + 1) >> 1);
+        }
+        // round r: (chain group, chunk) this half-warp serves, or nothing
+        auto poolAssign = [&](int r, int nMine_, int nOth_, int nBoth_, bool mineLong_, int &grp, int &c) -> bool {
+            if (r < nBoth_) { grp = g; c = r; return true; }
+            const int k = r - nBoth_;
+            if (mineLong_) { grp = g; c = nBoth_ + 2 * k; return c < nMine_; }
+            grp = 1 - g; c = nBoth_ + 2 * k + 1;
+            return c < nOth_;
+        };
+        if constexpr (kPool) {
+            const double2 *colRec0 = S.colRec + (size_t)chainBase0 * nCols;
+            double2 *scratch0 = S.scratch + (size_t)chainBase0 * P.sCap;
+            // the slot a lane handles in round r: its pair word, column and chain state (requested one round ahead)
+            auto fetch = [&](int r, uint32_t &sw_, int &u_, double2 &cr_, bool &real_) {
+                sw_ = 0xffff0000u; u_ = 0; cr_ = make_double2(0.0, 0.0); real_ = false;
+                int grp, c;
+                if (r < poolRounds && poolAssign(r, nChMine, nChOth, nChBoth, poolMineLong, grp, c)) {
+                    const int *cx = ofGroup(sCtx, grp);
+                    const int slot = c * W + gl;
+                    if (slot < cx[0]) {
+                        const uint32_t *recX = ofGroup(sRec, grp);
+                        const uint32_t *recGX = P.rec + (size_t)(unsigned)cx[6] * 4;
+                        const int so = cx[1], wd = cx[3];
+                        auto rw = [&](int i) -> uint32_t { return i < kRecWinWords ? recX[i] : __ldg(recGX + i); };
+                        sw_ = rw(so + (slot << wd) + wd);
+                        u_ = wd ? (int)rw(so + 2 * slot) : cx[2] + (int)(sw_ & 0xffffu);
+                        cr_ = (colRec0 + (size_t)grp * nCols)[u_];
+                        real_ = true;
+                    }
+                }
+            };
+            // round 0 is this half-warp's own first chunk, requested before the rows were evaluated (swN, uN, crN, realN) --
+            // unless its chain proposes nothing in this step and it serves the partner's from the start
+            if (nChMine == 0) fetch(0, swN, uN, crN, realN);
+            #pragma unroll 1
+            for (int r = 0; r < poolRounds; ++r) {
+                const uint32_t sw = swN;
+                const double2 cr = crN;
+                const bool real = realN;
+                const int u = uN;
+                fetch(r + 1, swN, uN, crN, realN);
+                int grp = g, c = 0;
+                poolAssign(r, nChMine, nChOth, nChBoth, poolMineLong, grp, c);
+                const int slot = c * W + gl;
+                const int *cx = ofGroup(sCtx, grp);
+                const double *sGX = ofGroup(sG, grp);
+                const int du = __double2hiint(cr.y) < 0 ? -1 : 1;
+                const bool self = real && u == cx[5];
+                const double nodeOld = fabs(cr.y);
+                double acc = cr.x;                                                           // try_emplace(u, currentDE[u])
+                const unsigned p0 = (sw >> 16) & 0xffu, p1 = sw >> 24;
+                auto rowTerm = [&](unsigned pb) -> double {   // unit entries: the row moves by M_iu delta_u = +-1
+                    const int k = pb & 31, code = pb >> 5;
+                    return sGX[2 * k + (((code >> 2) & 1) == (du < 0 ? 1 : 0) ? 1 : 0)];
+                };
+                const bool ext = real && p0 == (unsigned)kPairExt;
+                if (real && p0 < (unsigned)kPairExt) {
+                    acc = __dadd_rn(acc, rowTerm(p0));                                        // :308-310
+                    if (p1 != (unsigned)kPairNone) acc = __dadd_rn(acc, rowTerm(p1));
+                }
+                if (__any_sync(kFull, ext)) {   // pair lists of columns sharing more than two rows with the proposed one
+                    const uint32_t *recX = ofGroup(sRec, grp);
+                    const uint32_t *recGX = P.rec + (size_t)(unsigned)cx[6] * 4;
+                    auto rw = [&](int i) -> uint32_t { return i < kRecWinWords ? recX[i] : __ldg(recGX + i); };
+                    const int lw = cx[4] + (int)p1;
+                    unsigned long long lst = 0ull;
+                    if (ext) lst = (unsigned long long)rw(lw) | ((unsigned long long)rw(lw + 1) << 32);
+                    const int cnt = (int)(lst & 0xffull);
+                    const int tW = warpMax(cnt);
+#pragma unroll 1
+                    for (int t = 0; t < tW; ++t) {
+                        if (t < cnt) {
+                            const int bi = 1 + t;
+                            const unsigned pb = bi < 8 ? (unsigned)(lst >> (8 * bi)) & 0xffu : (rw(lw + (bi >> 2)) >> (8 * (bi & 3))) & 0xffu;
+                            acc = __dadd_rn(acc, rowTerm(pb));
+                        }
+                    }
+                }
+                if (self) acc = -cr.x;                                                       // :294
+                const double newP = real ? DEtoBasisProb(acc) : 0.0;
+                if (real) {
+                    ofGroup(sDl, grp)[slot] = __dsub_rn(newP, nodeOld);   // get(u) is the stored leaf: the change of the leaf
+                    // the stored leaf carries delta_u in its sign; the proposed column's flips on acceptance (:334)
+                    (scratch0 + (size_t)grp * P.sCap)[slot] = make_double2(acc, ((du < 0) != self) ? -newP : newP);
+                }
+            }
+            __syncwarp();
+            // changeInSum: this chain's leaf changes, summed exactly as the unpooled loop sums them (lane, then chunk order)
+            if (kMC) {
+#pragma unroll 1
+                for (int c = 0; c < nChMine; ++c) {
+                    const int slot = c * W + gl;
+                    csLane = __dadd_rn(csLane, slot < C ? sDl[slot] : 0.0);
+                }
+            }
+        } else {
         #pragma unroll 1
         for (int c = 0; c < chunksW; ++c) {
             const int slot = c * W + gl;
@@ -933,6 +1058,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 }
             }
         }
+        }
         if constexpr (BLK && kMC) {
 #pragma unroll
             for (int o = W / 2; o > 0; o >>= 1) csLane = __dadd_rn(csLane, __shfl_xor_sync(kFull, csLane, o));
@@ -998,7 +1124,83 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // ascending list, namely those sharing u >> b.
         const int Ca = accept ? C : 0;
         const int CW = warpMax(Ca);
-        if constexpr (BLK) {
+        if constexpr (kPool) {
+            // The blocked tree's commit (below) with the two half-warps sharing the rounds of the accepted proposals.  While both
+            // chains have chunks left each half-warp commits its own; then both commit the longer list, chunks 2k and 2k+1 in
+            // one round, and add their deltas to the sums one after the other (lower chunk first), so that every sum receives
+            // its deltas in ascending chunk order exactly as in the unpooled loop.
+            constexpr unsigned gMask = (1u << W) - 1u;
+            const int nAMine = (Ca + W - 1) / W, nAOth = __shfl_xor_sync(kFull, nAMine, W), CaOth = __shfl_xor_sync(kFull, Ca, W);
+            const int nABoth = min(nAMine, nAOth);
+            const bool aMineLong = nAMine > nAOth;
+            const int roundsA = nABoth + ((max(nAMine, nAOth) - nABoth + 1) >> 1);
+            double2 *colRec0 = S.colRec + (size_t)chainBase0 * nCols;
+            const double2 *scratch0 = S.scratch + (size_t)chainBase0 * P.sCap;
+            double *tier10 = S.tier1 + (size_t)chainBase0 * P.t1Len, *tier20 = S.tier2 + (size_t)chainBase0 * P.t2Len;
+            double2 scN = make_double2(0.0, 0.0);   // the staged {DE', signed leaf} of the coming round, one round ahead
+            auto fetchStaged = [&](int r) {
+                int grp, c;
+                scN = make_double2(0.0, 0.0);
+                if (r < roundsA && poolAssign(r, nAMine, nAOth, nABoth, aMineLong, grp, c)) {
+                    const int l = c * W + gl;
+                    if (l < (grp == g ? Ca : CaOth)) scN = (scratch0 + (size_t)grp * P.sCap)[l];
+                }
+            };
+            fetchStaged(0);
+            #pragma unroll 1
+            for (int r = 0; r < roundsA; ++r) {
+                int grp = g, c = 0;
+                const bool has = poolAssign(r, nAMine, nAOth, nABoth, aMineLong, grp, c);
+                const int l = c * W + gl;
+                const bool valid = has && l < (grp == g ? Ca : CaOth);
+                const int *cx = ofGroup(sCtx, grp);
+                unsigned u = 0x7fffffffu;
+                if (valid) {
+                    const uint32_t *recX = ofGroup(sRec, grp);
+                    const uint32_t *recGX = P.rec + (size_t)(unsigned)cx[6] * 4;
+                    const int so = cx[1], wd = cx[3];
+                    auto rw = [&](int i) -> uint32_t { return i < kRecWinWords ? recX[i] : __ldg(recGX + i); };
+                    u = wd ? rw(so + 2 * l) : (unsigned)cx[2] + (rw(so + l) & 0xffffu);
+                }
+                const double dl = valid ? ofGroup(sDl, grp)[l] : 0.0;
+                const double2 sc = scN;
+                fetchStaged(r + 1);
+                if (valid) (colRec0 + (size_t)grp * nCols)[u] = sc;
+                double pin = dl;
+#pragma unroll
+                for (int o = 1; o < W; o <<= 1) {
+                    const double t = __shfl_up_sync(kFull, pin, o, W);
+                    if (gl >= o) pin = __dadd_rn(pin, t);
+                }
+                const double pexRaw = __shfl_up_sync(kFull, pin, 1, W);
+                const double pex = gl ? pexRaw : 0.0;
+                const unsigned prevU = __shfl_up_sync(kFull, u, 1, W), nextU = __shfl_down_sync(kFull, u, 1, W);
+                double seg[3];
+                bool emit[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int lv = 5 + 5 * q;
+                    const bool head = gl == 0 || (prevU >> lv) != (u >> lv);
+                    const bool tail = gl == W - 1 || (nextU >> lv) != (u >> lv);
+                    const unsigned hm = (__ballot_sync(kFull, head) >> gBase) & gMask & ((2u << gl) - 1u);
+                    const int start = 31 - __clz(hm);                          // first slot of this slot's run (bit 0 is always set)
+                    seg[q] = __dsub_rn(pin, __shfl_sync(kFull, pex, start, W));
+                    emit[q] = valid && tail;
+                }
+                // both half-warps on one chain (r >= nABoth): the lower chunk (its owner's) adds first
+                const bool shared = r >= nABoth;
+                double *sTopX = ofGroup(sTop, grp);
+#pragma unroll 1
+                for (int ph = 0; ph < (shared ? 2 : 1); ++ph) {
+                    if (!shared || ph == (grp == g ? 0 : 1)) {
+                        if (emit[0]) atomicAdd(tier10 + (size_t)grp * P.t1Len + (u >> 5), seg[0]);
+                        if (emit[1]) atomicAdd(tier20 + (size_t)grp * P.t2Len + (u >> 10), seg[1]);
+                        if (emit[2]) sTopX[u >> 15] = __dadd_rn(sTopX[u >> 15], seg[2]);
+                    }
+                    __syncwarp();   // a run may continue in the next chunk: its two updates of one sum stay ordered
+                }
+            }
+        } else if constexpr (BLK) {
             // Blocked tree: currentDE[u] and the signed leaf in one 16-byte store; then every sum of 32 / 1024 / 32768 leaves
             // that covers changed columns receives the sum of their leaf changes.  The columns are ascending, so the entries
             // under one sum are consecutive slots: one inclusive prefix sum over the W slots of a round gives every such run

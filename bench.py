@@ -331,6 +331,8 @@ def bench_ours(args):
     # reduced on the device, summed over the GPUs by NCCL inside the library and copied to host buffers -- every step, host clock.
     # Launch k+1 is queued behind the reduction of launch k, so the device never waits for the host.
     smp.reset_statistics()
+    smp.enqueue_moments(comm)   # untimed: the communicator's first collective sets up its connections
+    smp.wait_moments()
     barrier()
     t0 = time.perf_counter()
     summary = None

@@ -61,3 +61,28 @@ def test_single_process_summary_without_process_group():
     end, ss, sq, n, ctr = _fake_stats(3, 10)
     s = E.allreduce_summary(E.pack_local(end, ss, sq, n, ctr), end.size, ss.shape[1])
     assert s.n_chains == 10 and np.allclose(s.synopsis_mean, ss.sum(0) / n.sum())
+
+
+def test_summarize_moments_equals_the_packed_route():
+    """The vectors abm_chains_get_moments returns (layout of include/abmcmc_b200.h, restated here on synthetic per-chain
+    tables) give the same W, B, var+, R-hat and marginals as the per-chain tables packed on the host."""
+    import numpy as np
+    from agentbasedmcmc_b200 import ensemble as E
+    m, d, S = 37, 3, 32
+    end, ss, sq, n, ctr = _fake_stats(7, m, S, d)
+    n = n.copy()
+    n[3], ss[3], sq[3] = 1, ss[3] // 500, sq[3] // 500        # a chain with a single sample contributes to no moment
+    ok = n > 1
+    exact = np.zeros(26 + S, np.int64)
+    exact[0], exact[1], exact[2:10] = ok.sum(), n.sum(), ctr.sum(0)
+    exact[10:10 + d], exact[18:18 + d], exact[26:] = ss.sum(0), sq.sum(0), end
+    real = np.zeros(24)
+    mean = ss[ok] * (1.0 / n[ok, None])
+    var = (sq[ok] - ss[ok].astype(np.float64) * ss[ok] * (1.0 / n[ok, None])) * (1.0 / (n[ok, None] - 1))
+    real[0:d], real[8:8 + d], real[16:16 + d] = mean.sum(0), (mean * mean).sum(0), var.sum(0)
+    a = E.summarize_moments(exact, real, d)
+    b = E.summarize(E.pack_local(end, ss, sq, n, ctr), S, d)
+    assert a.n_chains == b.n_chains and a.n_samples == b.n_samples and np.array_equal(a.counters, b.counters)
+    for x, y in ((a.W, b.W), (a.B, b.B), (a.var_plus, b.var_plus), (a.rhat, b.rhat), (a.end_state_mean, b.end_state_mean),
+                 (a.synopsis_mean, b.synopsis_mean)):
+        assert np.allclose(x, y, rtol=1e-10)
