@@ -36,7 +36,7 @@ WORKLOADS = {
     "pp8-4": ("pp8-4.abmp.xz", 1024, 3567.0, "PredPrey 8x8 grid, 4 timesteps, 1024 chains/GPU"),
 }
 # workload -> (burn-in Metropolis steps per chain before anything is timed, feasible samples per chain of the ESS window)
-STATIONARY = {"pp32-16": (6000000, 1600000), "pp16-8": (1500000, 300000), "pp8-4": (200000, 100000)}
+STATIONARY = {"pp32-16": (8000000, 1600000), "pp16-8": (1500000, 300000), "pp8-4": (200000, 100000)}
 METRIC = "chain-steps/sec, 32x32 PredPrey (SparseBasisSampler Metropolis steps, all chains, all GPUs)"
 UNIT = "chain-steps/s"
 
