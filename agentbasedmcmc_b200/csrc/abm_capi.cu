@@ -716,7 +716,7 @@ static cudaError_t launchStepWBF(const abm_chains *c, const RunParams &r) {
     constexpr int NG = 32 / W;
     const int chainsPerCta = kWarpsPerCta * NG;
     const int grid = (c->n + chainsPerCta - 1) / chainsPerCta;
-    const size_t smem = size_t(chainsPerCta) * (FIX ? groupSmemBytes(kFixRowsCap, kFixSCap, 0, 0, 1, 0, 0, 0)
+    const size_t smem = size_t(chainsPerCta) * (FIX ? groupSmemBytes(kFixRowsCap, kFixSCap, 0, kFixScrCap, 1, 0, 0, 0)
                                                     : groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs, P.nodeCap, P.t2Cap, BLK ? 0 : P.sCap));
     auto kernel = stepKernel<MODE, W, BLK, FIX>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

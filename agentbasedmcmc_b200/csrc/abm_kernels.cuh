@@ -74,6 +74,18 @@ constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 #ifndef ABM_PF_IMP
 #define ABM_PF_IMP 1
 #endif
+// ABM_DRAW_RECIDX: the leaf level of the column draw also fetches the record index entries of its 32 candidate columns (and
+// keeps their signed leaves), so the drawn column's record address and delta_j are in registers when the draw completes: one
+// L2 round trip (the index) and one L1 hit (the leaf's sign) leave the dependent chain of a step (16x16x8 stationary: 478 ->
+// 485 M steps/s, profiles/r2_ab_p_hops.log)
+#ifndef ABM_DRAW_RECIDX
+#define ABM_DRAW_RECIDX 1
+#endif
+// ABM_RATIO_EARLY: measurement switch: root / (root + changeInSum) issued before the importance change instead of after it
+// (16x16x8 stationary: 467 vs 478 M steps/s; off)
+#ifndef ABM_RATIO_EARLY
+#define ABM_RATIO_EARLY 0
+#endif
 // ABM_POOL: measurement switch: the two chains of a warp share their lanes over the coupled-column chunks and over the commit
 // rounds: while both have chunks left each half-warp serves its own chain, afterwards both serve the longer list, two
 // adjacent chunks per round, so a round is as long as HALF the two lists together instead of the longer one (3.9 -> 2.9
@@ -379,6 +391,13 @@ __device__ __noinline__ void recordSeries(int32_t *series, int seriesThin, int s
 // step loop (12 % of all instructions, profiles/r1d_*).  abm_problem_create selects it whenever the problem fits, which the
 // paper's PredPrey problems do; anything else runs the same code with the run-time layout.
 constexpr int kFixRowsCap = 24, kFixSCap = 176;
+// ABM_FIX_SCR: measurement switch: coupled columns whose staged {DE', leaf} stay in shared memory between the proposal and its
+// commit (16 = the first chunk: the commit's first round starts from shared memory instead of an L2 round trip; 16x16x8
+// stationary: 472 vs 478 M steps/s; off)
+#ifndef ABM_FIX_SCR
+#define ABM_FIX_SCR 0
+#endif
+constexpr int kFixScrCap = ABM_POOL ? 0 : ABM_FIX_SCR;
 template <int MODE, int W, bool BLK, bool FIX = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P, DevChains S, RunParams R) {
     static_assert(!FIX || BLK, "the fixed layout exists for the blocked tree only");
@@ -411,7 +430,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 
     // ---- per-chain shared memory
     const int cRowsCap = FIX ? kFixRowsCap : P.rowsCap, cSCap = FIX ? kFixSCap : P.sCap, cTCap = FIX ? 0 : P.tCap;
-    const int cScrCap = FIX ? 0 : P.scrCap, cNodeCap = FIX ? 0 : P.nodeCap, cT2Cap = FIX ? 0 : P.t2Cap, cMaxAbs = FIX ? 1 : P.maxAbs;
+    const int cScrCap = FIX ? kFixScrCap : P.scrCap, cNodeCap = FIX ? 0 : P.nodeCap, cT2Cap = FIX ? 0 : P.t2Cap, cMaxAbs = FIX ? 1 : P.maxAbs;
     const int cSUCap = BLK ? 0 : cSCap;
     const int gBytes = groupSmemBytes(cRowsCap, cSCap, cTCap, cScrCap, cMaxAbs, cNodeCap, cT2Cap, cSUCap);
     unsigned char *gs = smemRaw + (size_t)(warp * NG + g) * gBytes;
@@ -460,7 +479,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         for (int k = gl; k < P.t2Len; k += W) sT2[k] = chainValid ? ch.tier2[k] : 0.0;
     __syncwarp();
     double2 *scratch = S.scratch + (size_t)chainC * P.sCap;
-    const int scrChunks = (BLK && !FIX) ? P.scrCap / W : 0;   // chunks of coupled columns whose staged values stay in shared memory
+    const int scrChunks = !BLK ? 0 : (FIX ? kFixScrCap / W : P.scrCap / W);   // chunks of coupled columns whose staged values stay in shared memory
 
     double logImp = chainValid ? S.logImp[chain] : 0.0;
     int infeas = chainValid ? S.infeas[chain] : 0;
@@ -559,6 +578,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // holds 0.0: "0.0 > target" is false and "target - 0.0" is a no-op, which is the reference's skip.
         double root = 1.0;
         int j = 0;
+        uint2 drawnRi[NG], drawnRiSel = make_uint2(0u, 0u);   // ABM_DRAW_RECIDX: index entries of the leaf level's candidates
+        int drawnLeafSign[NG], drawnSign = 0;
+        bool drawnOk = false;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) { drawnRi[k] = make_uint2(0u, 0u); drawnLeafSign[k] = 0; }
         if constexpr (BLK) {
             // top level (sums of 32768 leaves, shared memory): one scan over the group's lanes gives the total and the
             // selection; absent entries are 0.0 (sTop is zero beyond nTop)
@@ -580,10 +604,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 for (int k = 0; k < NG; ++k) {
                     const int e = first + gl * NG + k;
                     v[k] = 0.0;
-                    if (act && e < count)   // leaf sign = delta_e; tiers in global memory are updated by L2 reductions
-                        v[k] = lvl == 2 ? (t2s ? sT2[e] : __ldcg(ch.tier2 + e)) : (lvl == 1 ? __ldcg(ch.tier1 + e) : fabs(ch.colRec[e].y));
+                    if (act && e < count) {   // leaf sign = delta_e; tiers in global memory are updated by L2 reductions
+                        if (lvl == 0) {
+                            const double leaf = ch.colRec[e].y;
+                            v[k] = fabs(leaf);
+                            if constexpr (ABM_DRAW_RECIDX != 0) {
+                                drawnLeafSign[k] = __double2hiint(leaf);
+                                drawnRi[k] = __ldg(P.recIdx + e);
+                            }
+                        } else {
+                            v[k] = lvl == 2 ? (t2s ? sT2[e] : __ldcg(ch.tier2 + e)) : __ldcg(ch.tier1 + e);
+                        }
+                    }
                 }
-                sel = first + selectDescending<W>(v, target, gl, gBase);
+                const int w = selectDescending<W>(v, target, gl, gBase);
+                if constexpr (ABM_DRAW_RECIDX != 0) {
+                    if (lvl == 0) {   // the winner's index entry and leaf sign, from the lane that loaded them
+                        unsigned rx = drawnRi[0].x, ry = drawnRi[0].y;
+                        int sg = drawnLeafSign[0];
+#pragma unroll
+                        for (int k = 1; k < NG; ++k)
+                            if ((w % NG) == k) { rx = drawnRi[k].x; ry = drawnRi[k].y; sg = drawnLeafSign[k]; }
+                        drawnRiSel.x = __shfl_sync(kFull, rx, w / NG, W);
+                        drawnRiSel.y = __shfl_sync(kFull, ry, w / NG, W);
+                        drawnSign = __shfl_sync(kFull, sg, w / NG, W);
+                        drawnOk = first + w < nCols;
+                    }
+                }
+                sel = first + w;
             }
             j = min(sel, nCols - 1);
         } else {
@@ -631,7 +679,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         // asynchronous copy whose completion is counted on the chain's mbarrier); lists longer than the window (a few per cent
         // of the proposals) are read from the table itself.
         uint2 ri = make_uint2(0u, 0u);
-        if (act) ri = __ldg(P.recIdx + j);   // {offset in 16-byte units, bytes}
+        const bool haveDrawn = BLK && ABM_DRAW_RECIDX != 0 && drawnOk && !R.injJ;
+        if (act) ri = haveDrawn ? drawnRiSel : __ldg(P.recIdx + j);   // {offset in 16-byte units, bytes}
         const uint32_t *__restrict__ recG = P.rec + (size_t)ri.x * 4;
 #if !ABM_REC_BULK
         if (act) {
@@ -645,7 +694,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 #endif
         // BLK: delta_u is the sign bit of the stored leaf p_u (p_u >= 0), so a coupled column costs one 16-byte load
         int dj = 1;
-        if (act) dj = BLK ? (__double2hiint(ch.colRec[j].y) < 0 ? -1 : 1) : (int)ch.delta[j];
+        if (act) dj = BLK ? ((haveDrawn ? drawnSign : __double2hiint(ch.colRec[j].y)) < 0 ? -1 : 1) : (int)ch.delta[j];
 #if !ABM_REC_BULK
         __syncwarp();
 #else
@@ -823,6 +872,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
         };
         if (kMC && kImpEarly) importance();
+        double ratioEarly = 1.0;
         double csLane = 0.0;   // BLK: this lane's share of changeInSum
         // chunks of 16 coupled columns: mine, the partner group's, and how the two half-warps share them (ABM_POOL)
         const int nChMine = (C + W - 1) / W;
@@ -1068,9 +1118,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 
         bool accept = act;
         if (kMC) {
+            if constexpr (ABM_RATIO_EARLY != 0) ratioEarly = root / __dadd_rn(root, changeInSum);
             if (!kImpEarly) importance();
             // ---- calcRatioOfSums (:276-284) and the Metropolis test (:232-234)
-            const double ratio = root / __dadd_rn(root, changeInSum);
+            const double ratio = ABM_RATIO_EARLY != 0 ? ratioEarly : root / __dadd_rn(root, changeInSum);
             const double acceptance = __dmul_rn(expShared(__dsub_rn(logImpN, logImp)), ratio);
             accept = act && (u2 < acceptance);
             const int ci = (infeas == 0 ? 2 : 0) + (infN == 0 ? 1 : 0);                      // MCMCStatistics.cpp:12-17
