@@ -312,7 +312,10 @@ def bench_ours(args):
             ess = {"value": None, "note": f"ESS estimate failed: {exc!r}"}
     barrier()
 
-    # ---- device-resident throughput at the stationary state: W warm-up launches, then exactly K timed launches
+    # ---- device-resident throughput at the stationary state: W warm-up launches, then exactly K timed launches.  The ESS window
+    # stops every chain AT a feasible state (operator() semantics); 2e5 steps let the feasible / infeasible mix settle again.
+    if args.ess_samples > 0:
+        smp.step(200000)
     for _ in range(args.warmup):
         smp.step(mh)
     barrier()
