@@ -22,7 +22,7 @@ SYMBOLS = [
     "abm_chains_record_series", "abm_chains_get_series",
     "abm_chains_sample_injected", "abm_comm_unique_id", "abm_comm_create", "abm_comm_from_nccl", "abm_comm_destroy",
     "abm_chains_get_moments", "abm_chains_allreduce_moments", "abm_chains_enqueue_moments", "abm_chains_wait_moments",
-    "abm_chains_rebuild_tree", "abm_chains_tree_drift",
+    "abm_chains_rebuild_tree", "abm_chains_tree_drift", "abm_chains_series_variogram",
     "abm_chains_last_launch_ms", "abm_basis_minimise", "abm_basis_destroy", "abm_basis_get_dims", "abm_basis_get", "abm_basis_get_rows",
 ]
 
@@ -96,6 +96,7 @@ def load():
     L.abm_chains_get_series.argtypes = [vp, i32p]
     L.abm_chains_last_launch_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.abm_chains_sample_injected.argtypes = [vp, C.c_int64, f64p]
+    L.abm_chains_series_variogram.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int64, i64p, i64p]
     L.abm_chains_rebuild_tree.argtypes = [vp]
     L.abm_chains_tree_drift.argtypes = [vp, C.c_int32, f64p]
     L.abm_comm_unique_id.argtypes = [u8p]

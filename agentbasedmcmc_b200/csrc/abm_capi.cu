@@ -800,6 +800,15 @@ int abm_chains_find_feasible(abm_chains *c, int64_t maxIterations, const double 
     std::vector<int32_t> inf(n);
     int64_t done = 0;
     bool allFeasible = false;
+    // The search ends when the SLOWEST chain is feasible (32x32x16: 2.4e6 iterations against a mean of 4.9e5), and a chain's
+    // search is sequential, so the tail is a handful of chains running at the latency of one iteration.  With few chains
+    // left, a whole warp per chain (32 lanes: half the rounds per iteration) has the lower latency (7.9 against 11.3 us per
+    // iteration at 256 chains), so the tail of a large ensemble's search runs on the 32-lane kernel; the records do not depend
+    // on the lanes per chain.  ABM_INIT_TAIL = 0 / 1 switches it off / on for every size (tests); ABM_GROUP_WIDTH overrides.
+    constexpr int64_t kTailChains = 2048;
+    const int tailMode = getenv("ABM_INIT_TAIL") ? atoi(getenv("ABM_INIT_TAIL")) : -1;
+    const bool widthForced = getenv("ABM_GROUP_WIDTH") != nullptr;
+    int64_t unfinished = int64_t(n);
     while (done < maxIterations) {
         const int64_t chunk = std::min<int64_t>(maxIterations - done, 1 << 16);
         RunParams r = baseParams(c);
@@ -808,11 +817,14 @@ int abm_chains_find_feasible(abm_chains *c, int64_t maxIterations, const double 
         r.uStride = nUniforms;
         r.uOffset = done;   // valid because with injected uniforms all chains advance in lock step per launch
         r.itersOut = dIters;
-        CUDA_TRY(launchStep<MODE_INIT>(c, r));
+        const bool wide = !widthForced && (tailMode == 1 || (tailMode != 0 && int64_t(n) > kTailChains && unfinished <= kTailChains));
+        if (wide) CUDA_TRY((launchStepW<MODE_INIT, 32>(c, r)));
+        else CUDA_TRY(launchStep<MODE_INIT>(c, r));
         CUDA_TRY(cudaMemcpyAsync(inf.data(), c->d.infeas, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         done += chunk;
-        allFeasible = std::all_of(inf.begin(), inf.end(), [](int32_t v) { return v == 0; });
+        unfinished = std::count_if(inf.begin(), inf.end(), [](int32_t v) { return v != 0; });
+        allFeasible = unfinished == 0;
         if (allFeasible) break;
     }
     if (iterationsOut) {
@@ -1302,6 +1314,34 @@ int abm_chains_tree_drift(abm_chains *c, int32_t chain, double out[4]) {
     for (int b = 0; b < P.t2Len; ++b) e2 = std::max(e2, double(fabsl(t2[b] - exact(1024 * b, 1024 * b + 1024))));
     for (int b = 0; b * 32768 < P.nCols; ++b) e3 = std::max(e3, double(fabsl(t3[b] - exact(32768 * b, 32768 * b + 32768))));
     out[0] = double(root); out[1] = e1; out[2] = e2; out[3] = e3;
+    return ABM_OK;
+}
+
+// Variogram sums of the recorded series over all chains of all ranks (exact integers), see variogramKernel
+int abm_chains_series_variogram(abm_chains *c, abm_comm *comm, int32_t nPoints, int32_t nLags, int64_t minSamples, int64_t *sums,
+                                int64_t *nChainsOut) {
+    if (!c || !sums || nPoints <= 0 || nLags <= 0 || nLags > nPoints) return fail(ABM_ERR_INVALID, "bad argument");
+    if (!c->series || nPoints > c->seriesCap) return fail(ABM_ERR_STATE, "no series of that length is being recorded");
+    CUDA_TRY(cudaSetDevice(c->p->device));
+    const int nSyn = c->p->d.nSynopsis;
+    DeviceArena tmp;
+    long long *dOut = nullptr;
+    const size_t words = size_t(nLags) * 8 + 1;
+    CUDA_TRY(tmp.alloc(&dOut, words));
+    CUDA_TRY(cudaMemsetAsync(dOut, 0, words * sizeof(long long), c->stream));
+    variogramKernel<<<dim3(nLags, (c->nSeriesChains + kVarioSlice - 1) / kVarioSlice), 128, 0, c->stream>>>(
+        c->d, c->series, c->seriesCap, c->nSeriesChains, nSyn, nPoints, minSamples, dOut, dOut + size_t(nLags) * 8);
+    CUDA_TRY(cudaGetLastError());
+    if (comm && comm->nccl) {
+        NcclApi *a = ncclApi();
+        NCCL_TRY(a, a->AllReduce(dOut, dOut, words, kNcclInt64, kNcclSum, comm->nccl, c->stream));
+    }
+    std::vector<long long> host(words);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), dOut, words * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < nLags; ++j)
+        for (int k = 0; k < nSyn; ++k) sums[size_t(j) * nSyn + k] = host[size_t(j) * 8 + k];
+    if (nChainsOut) *nChainsOut = host[size_t(nLags) * 8];
     return ABM_OK;
 }
 

@@ -1713,6 +1713,42 @@ __global__ void reduceEndStateKernel(DevProblem P, DevChains S) {
     atomicAdd(reinterpret_cast<unsigned long long *>(S.endStateSum) + psi, (unsigned long long)acc);
 }
 
+// Variogram of the thinned synopsis series over all chains (diagnostics/ChainStats.h:66-79, V_t = mean_i (x_i - x_{i+t})^2 at
+// strided lags), as exact integer sums: out[j][k] += sum over chains with a full window and positions i < nPoints - j of
+// (x_i - x_{i+j})^2 for synopsis statistic k; the synopsis values are integers, so the sums are exact, order-independent and
+// additive across GPUs.  out[nLags][8] int64, zeroed by the caller; chainsOut counts the contributing chains.
+// grid (nLags, chain slices), one lag per block column.
+constexpr int kVarioSlice = 32;
+__global__ void __launch_bounds__(128) variogramKernel(DevChains S, const int32_t *__restrict__ series, int seriesCap, int nSeriesChains,
+                                                       int nSyn, int nPoints, long long minSamples, long long *__restrict__ out,
+                                                       long long *__restrict__ chainsOut) {
+    const int j = blockIdx.x;
+    const int c0 = blockIdx.y * kVarioSlice, c1 = min(c0 + kVarioSlice, nSeriesChains);
+    long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int nc = 0;
+    for (int c = c0; c < c1; ++c) {
+        if (S.nSamples[c] < minSamples) continue;
+        ++nc;
+        const int32_t *x = series + (size_t)c * seriesCap * nSyn;
+        for (int i = threadIdx.x; i + j < nPoints; i += blockDim.x) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < nSyn) {
+                    const long long d = (long long)x[(size_t)i * nSyn + k] - (long long)x[(size_t)(i + j) * nSyn + k];
+                    acc[k] += d * d;
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        long long v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if ((threadIdx.x & 31) == 0 && k < nSyn && v) atomicAdd(reinterpret_cast<unsigned long long *>(out) + (size_t)j * 8 + k, (unsigned long long)v);
+    }
+    if (j == 0 && threadIdx.x == 0 && nc) atomicAdd(reinterpret_cast<unsigned long long *>(chainsOut), (unsigned long long)nc);
+}
+
 // Per-GPU additive moments of the ensemble, reduced on the device (the reference sums its
 // threads' results in a serial loop over std::futures, FiguresForPaper.h:62-65).  Everything a multi-GPU SUM all-reduce needs
 // to rebuild the marginals and W, B, var+, R-hat (diagnostics/MultiChainStats.h:141-181):

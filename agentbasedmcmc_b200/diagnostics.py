@@ -137,6 +137,24 @@ def rhat_from_moments(n: np.ndarray, s: np.ndarray, sq: np.ndarray):
     return np.sqrt(var_plus / W), W, B, var_plus
 
 
+def effective_samples_from_variogram(V: np.ndarray, var_plus: np.ndarray, n_per_chain: float, n_chains: float, stride: int):
+    """MultiChainStats::effectiveSamples (:81-102) from a mean variogram V [lags][d] at lags 0, stride, 2 stride, ...:
+    n_eff = m n / (1 + 2 stride sum_t rho_t), rho_t = 1 - V_t / (2 var+), summed while the running minimum of rho is positive.
+    Returns (n_eff [d], rho [lags][d])."""
+    V = np.asarray(V, dtype=np.float64)
+    rho = 1.0 - V / (2.0 * np.asarray(var_plus, dtype=np.float64))
+    n_lags, d = V.shape
+    n_eff = np.zeros(d)
+    for q in range(d):
+        t, next_s, sumt = 0, 1.0 - V[0][q] / (2.0 * var_plus[q]), 0.0
+        while next_s > 0.0:
+            sumt += next_s
+            t += 1
+            next_s = min(next_s, rho[t][q] if t < n_lags else -1.0)
+        n_eff[q] = n_per_chain * n_chains / (1.0 + 2.0 * stride * sumt)
+    return n_eff, rho
+
+
 def ensemble_effective_samples(series: np.ndarray, thin: int, n: np.ndarray, s: np.ndarray, sq: np.ndarray,
                                max_lag_proportion: float = 0.5, group: int = 1):
     """Effective sample size of MANY equally long chains, with the reference's estimator
@@ -168,15 +186,7 @@ def ensemble_effective_samples(series: np.ndarray, thin: int, n: np.ndarray, s: 
     for j in range(1, n_lags):
         diff = x[:, : k - j] - x[:, j:]
         V[j] = (diff * diff).mean(axis=(0, 1))
-    rho = 1.0 - V / (2.0 * var_plus)
-    n_eff = np.zeros(d)
-    for q in range(d):
-        t, next_s, sumt = 0, 1.0, 0.0
-        while next_s > 0.0:
-            sumt += next_s
-            t += 1
-            next_s = min(next_s, rho[t][q] if t < n_lags else -1.0)
-        n_eff[q] = nbar * m / (1.0 + 2.0 * thin * sumt)
+    n_eff, rho = effective_samples_from_variogram(V, var_plus, nbar, m, thin)
     out = {"n_eff": n_eff, "tau": nbar * m / n_eff, "rho": rho, "rhat": rhat, "W": W, "B": B, "var_plus": var_plus,
            "lags": n_lags, "stride": thin}
     if group > 1:

@@ -274,6 +274,14 @@ class SparseBasisSampler:
         check(_capi.load().abm_chains_tree_drift(self.h, chain, _ptr(out, C.c_double)))
         return out
 
+    def series_variogram(self, n_points: int, n_lags: int, min_samples: int, comm=None):
+        """(sums int64 [n_lags][n_synopsis], contributing chains) of abm_chains_series_variogram, summed over `comm`'s ranks."""
+        sums = np.zeros((n_lags, self.problem.n_synopsis), np.int64)
+        n = C.c_int64()
+        check(_capi.load().abm_chains_series_variogram(self.h, comm.h if comm is not None else None, n_points, n_lags, min_samples,
+                                                       _ptr(sums, C.c_int64), C.byref(n)))
+        return sums, int(n.value)
+
     def last_launch_ms(self) -> float:
         """Device time of the last step / step_traced / sample launch (waits for it)."""
         ms = C.c_float()

@@ -281,33 +281,41 @@ def bench_ours(args):
             smp.sample(n_s, max_steps=12 * n_s)      # bounded: a chain deep in the infeasible region must not stall the batch
             barrier()
             ess_s = time.perf_counter() - t0
+            k_pts = n_s // thin
+            n_lags = max(2, min(k_pts, int(0.5 * n_s / thin) + 1))
+            # the ensemble's figures, over ALL chains of ALL GPUs, reduced on the devices: exact variogram sums and the additive
+            # moments, both summed over the ranks by NCCL inside the library
+            vsum, m_full = smp.series_variogram(k_pts, n_lags, n_s, comm)
+            exact, real = smp.moments(comm)
+            summ = E.summarize_moments(exact, real, n_syn)
+            V = vsum.astype(np.float64) / (max(m_full, 1) * (k_pts - np.arange(n_lags))[:, None])
+            n_eff_all, rho = D.effective_samples_from_variogram(V, summ.var_plus, summ.n_samples / max(summ.n_chains, 1), summ.n_chains, thin)
+            # rank 0's own chains: R-hat of pooled sequences and the drift between the halves of the window
             end, ss, sq, ns = smp.statistics()
             ser = smp.series()
             smp.record_series(0, 1, 0)               # stop recording
             full = ns >= n_s
-            k_pts = n_s // thin
             series = ser[full, :k_pts].astype(np.float64)
             r = D.ensemble_effective_samples(series, thin, ns[full], ss[full], sq[full], group=8)
             half = k_pts // 2
             drift = (series[:, half:].mean(axis=(0, 1)) - series[:, :half].mean(axis=(0, 1))) / np.sqrt(r["var_plus"])
-            loc = torch.tensor(np.concatenate([r["n_eff"], [float(full.sum()), ess_s]]), dtype=torch.float64, device="cuda")
-            if world > 1:   # independent chains: effective samples add over the ranks; the slowest rank sets the time
-                mx = loc[-1:].clone()
-                dist.all_reduce(loc, op=dist.ReduceOp.SUM)
-                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-                loc[-1] = mx[0]
-            tot = loc.cpu().numpy()
-            n_eff_all, chains_all, ess_s_all = tot[:n_syn], int(tot[n_syn]), float(tot[n_syn + 1])
+            te_ = torch.tensor([ess_s], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te_, op=dist.ReduceOp.MAX)   # the slowest rank sets the time
+            ess_s_all = float(te_.item())
             ess = {"value": float(n_eff_all.min() / ess_s_all), "unit": "effective samples/s (worst synopsis statistic, all chains, all GPUs)",
-                   "n_eff": [round(float(x), 1) for x in n_eff_all], "chains": chains_all, "feasible_samples_per_chain": n_s,
-                   "seconds": round(ess_s_all, 2), "samples_per_effective_sample": [round(float(x)) for x in r["tau"]],
-                   "rhat": [round(float(x), 4) for x in r["rhat"]],
-                   "rhat_note": "per-chain sequences, reference formula; for stationary chains R-hat^2 = 1 + 1/(effective samples per sequence)",
+                   "n_eff": [round(float(x), 1) for x in n_eff_all], "chains": int(summ.n_chains), "chains_with_full_window": int(m_full),
+                   "feasible_samples_per_chain": n_s, "seconds": round(ess_s_all, 2),
+                   "samples_per_effective_sample": [round(float(x)) for x in summ.n_samples / n_eff_all],
+                   "rhat": [round(float(x), 4) for x in summ.rhat],
+                   "rhat_note": "per-chain sequences of all GPUs, reference formula; for stationary chains R-hat^2 = 1 + 1/(effective samples per sequence)",
                    "rhat_pooled8": [round(float(x), 4) for x in r["rhat_grouped"]],
                    "drift_second_minus_first_half_in_sd": [round(float(x), 4) for x in drift],
-                   "synopsis_mean": [round(float(x), 4) for x in (ss[full].sum(0) / ns[full].sum())],
-                   "estimator": "MultiChainStats::effectiveSamples (reference), variogram over all chains at stride %d, lags to n/2" % thin,
-                   "scope": "rank 0's chains for R-hat / drift / mean; n_eff summed over ranks"}
+                   "synopsis_mean": [round(float(x), 4) for x in summ.synopsis_mean],
+                   "estimator": "MultiChainStats::effectiveSamples (reference); variogram (abm_chains_series_variogram, exact integer sums on the "
+                                "devices) over all chains at stride %d, lags to n/2; var+ from the device-reduced moments; both summed over the "
+                                "GPUs by NCCL inside the library" % thin,
+                   "scope": "all chains of all GPUs; rhat_pooled8 and the drift: rank 0's chains"}
         except Exception as exc:   # the ESS estimate must never take the benchmark line down
             ess = {"value": None, "note": f"ESS estimate failed: {exc!r}"}
     barrier()

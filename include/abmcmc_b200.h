@@ -224,6 +224,14 @@ ABM_API int abm_chains_allreduce_moments(abm_chains *c, abm_comm *comm, int64_t 
 ABM_API int abm_chains_enqueue_moments(abm_chains *c, abm_comm *comm);
 ABM_API int abm_chains_wait_moments(abm_chains *c, int64_t *exact, double *real);
 
+/* Variogram of the recorded synopsis series over ALL chains (ChainStats::variogram, diagnostics/ChainStats.h:66-79, at the lags
+ * j * thin, j < n_lags, of the series' first n_points points), reduced on the device and summed over the ranks of `comm` (NULL:
+ * this GPU only): sums[j][k] = sum over the chains with at least min_samples feasible samples, and over the positions
+ * i < n_points - j, of (x_i - x_{i+j})^2 for synopsis statistic k -- exact integers; V = sums / (n_chains * (n_points - j)).
+ * Together with the moments it is everything MultiChainStats::effectiveSamples (MultiChainStats.h:81-102) needs. */
+ABM_API int abm_chains_series_variogram(abm_chains *c, abm_comm *comm, int32_t n_points, int32_t n_lags, int64_t min_samples,
+                                        int64_t *sums /* [n_lags][n_synopsis] */, int64_t *n_chains_out);
+
 /* Blocked sum tree (ABM_TREE_BLOCKED): its sums are kept incrementally by the step kernel -- the two upper levels are recomputed
  * from the level below before every launch, the sums of 32 leaves from the leaves every 256th launch.  abm_chains_rebuild_tree
  * forces that exact rebuild now; abm_chains_tree_drift measures one chain: out = {root, max |sum - exact sum of its leaves| over

@@ -115,3 +115,25 @@ def test_paper_scale_problem_matches_oracle(tree):
         assert np.array_equal(X, oc.X) and np.array_equal(delta, oc.delta) and infeas == oc.infeasibility
         assert np.allclose(DE, oc.DE, rtol=1e-9, atol=1e-12) and np.allclose(tr, oc.tree, rtol=1e-9, atol=1e-11 * tr[0])
         assert np.isclose(logimp, oc.log_importance, rtol=1e-9)
+
+
+def test_feasibility_search_tail_on_the_wide_kernel(monkeypatch):
+    """The tail of a large ensemble's feasibility search runs on the 32-lanes-per-chain kernel (abm_chains_find_feasible);
+    forced on here for a small ensemble: iteration counts and first feasible states equal the oracle's, and the Metropolis steps
+    that follow (16-lane kernel) continue from them."""
+    from oracle.oracle import OracleChain, OracleProblem
+    monkeypatch.setenv("ABM_INIT_TAIL", "1")
+    S = _S()
+    p = load_golden("pp16-8.abmp.xz")
+    P = S.Problem(p)
+    smp = S.SparseBasisSampler(P, n_chains=5, seed=21, first_chain_id=2)
+    monkeypatch.delenv("ABM_INIT_TAIL")
+    j, acc, inf = smp.step_traced(600)
+    OP = OracleProblem(p)
+    for c in range(5):
+        oc = OracleChain(OP)
+        oc.seed_philox(21, 2 + c)
+        assert oc.find_feasible() == int(smp.init_iterations[c])
+        oj, oacc, oinf = oc.step(600, trace=True)
+        assert np.array_equal(j[c], oj) and np.array_equal(acc[c], oacc) and np.array_equal(inf[c], oinf)
+        assert np.array_equal(smp.state(c)[0], oc.X)

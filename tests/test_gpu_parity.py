@@ -332,3 +332,36 @@ def test_blocked_tree_tracks_reference_tree_and_its_sums_stay_exact():
     smp["blocked"].rebuild_tree()
     d2 = smp["blocked"].tree_drift(0)
     assert d2[1] <= 32 * 2.3e-16 * 32      # sums of 32 leaves (each <= 1) recomputed: ordinary summation rounding only
+
+
+def test_device_variogram_and_ensemble_ess_match_the_host_route():
+    """abm_chains_series_variogram (exact integer sums over all chains, on the device) against numpy on the same recorded
+    series, and the effective sample size built from it and from the device-reduced moments against
+    diagnostics.ensemble_effective_samples on the per-chain tables (rows a17 / f3)."""
+    from agentbasedmcmc_b200 import diagnostics as D
+    from agentbasedmcmc_b200 import ensemble as E
+    S = _gpu()
+    p = load_golden("pp8-4.abmp.xz")
+    P = S.Problem(p)
+    m, n_s, thin = 96, 6000, 25
+    smp = S.SparseBasisSampler(P, n_chains=m, seed=5150)
+    smp.step(20000)
+    smp.reset_statistics()
+    k = n_s // thin
+    smp.record_series(m, thin, k + 1)
+    smp.sample(n_s, max_steps=40 * n_s)
+    end, ss, sq, ns = smp.statistics()
+    assert np.all(ns == n_s)
+    x = smp.series()[:, :k].astype(np.int64)
+    n_lags = k // 2 + 1
+    vs, mc = smp.series_variogram(k, n_lags, n_s)
+    assert mc == m
+    for j in (0, 1, 7, n_lags - 1):
+        d = x[:, : k - j] - x[:, j:]
+        assert np.array_equal(vs[j], (d * d).sum(axis=(0, 1)))
+    ex, re = smp.moments()
+    summ = E.summarize_moments(ex, re, P.n_synopsis)
+    V = vs / (mc * (k - np.arange(n_lags))[:, None])
+    n_eff, _ = D.effective_samples_from_variogram(V, summ.var_plus, n_s, mc, thin)
+    r = D.ensemble_effective_samples(x.astype(np.float64), thin, ns, ss, sq)
+    assert np.allclose(n_eff, r["n_eff"], rtol=1e-9) and np.allclose(summ.rhat, r["rhat"], rtol=1e-9)
