@@ -84,3 +84,33 @@ def test_bad_problems_are_rejected_on_the_host():
         S.validate_problem(broken(tab_F=lambda a: a.__setitem__(int(np.flatnonzero(p["tab_L"] != p["tab_U"])[0]), 1000)))
     with pytest.raises(S.AbmError, match="bad factor id"):
         S.validate_problem(broken(fac_id=lambda a: a.__setitem__(int(np.flatnonzero(p["tab_L"] != p["tab_U"])[0]), 10 ** 6)))
+
+
+def test_malformed_descriptors_are_rejected_not_dereferenced():
+    """abm_problem_validate on descriptors with missing arrays or inconsistent pointers returns ABM_ERR_INVALID instead of
+    crashing: null arrays, nb_ptr not starting at 0 or decreasing, no factor tables, ut_off not increasing."""
+    import ctypes as C
+    from agentbasedmcmc_b200 import _capi
+    from agentbasedmcmc_b200.sampler import _problem_desc
+    S = _S()
+    L = _capi.load()
+    p = load_golden("pp8-4.abmp.xz")
+
+    def status(mutate):
+        d, keep = _problem_desc(p)
+        mutate(d, keep)
+        info = _capi.ProblemInfo()
+        rc = L.abm_problem_validate(C.byref(d), C.byref(info))
+        del keep
+        return rc
+
+    null32 = C.POINTER(C.c_int32)()
+    assert status(lambda d, k: None) == 0
+    for field in ("tab_L", "tab_U", "tab_F", "nb_col", "nb_ptr", "nb_row", "nb_val", "fac_id", "ut_lo", "ut_off"):
+        assert status(lambda d, k, f=field: setattr(d, f, null32)) == -1, field
+    assert status(lambda d, k: setattr(d, "ut_val", C.POINTER(C.c_double)())) == -1
+    assert status(lambda d, k: setattr(d, "n_tables", 0)) == -1
+    assert status(lambda d, k: k["nb_ptr"].__setitem__(0, 1)) == -1
+    assert status(lambda d, k: k["nb_ptr"].__setitem__(5, int(k["nb_ptr"][4]) - 1)) == -1
+    assert status(lambda d, k: k["ut_off"].__setitem__(1, 0)) == -1
+    assert L.abm_problem_validate(None, None) == -1
