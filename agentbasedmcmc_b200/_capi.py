@@ -45,6 +45,10 @@ class ProblemDesc(C.Structure):
         ("grid_size", C.c_int32), ("n_timesteps", C.c_int32),
         ("imp_lgamma", C.POINTER(C.c_double)), ("imp_logratio", C.POINTER(C.c_double)),
         ("sum_tree", C.c_int32),
+        ("n_agent_states", C.c_int32), ("n_acts", C.c_int32), ("n_agent_classes", C.c_int32),
+        ("agent_class", C.POINTER(C.c_int32)), ("agent_influencers", C.POINTER(C.c_int32)),
+        ("agent_nb_ptr", C.POINTER(C.c_int32)), ("agent_nb", C.POINTER(C.c_int32)),
+        ("agent_cq_ptr", C.POINTER(C.c_int32)), ("agent_cq", C.POINTER(C.c_int32)),
     ]
 
 

@@ -121,7 +121,7 @@ extern "C" {
 static int zeroStatistics(abm_chains *c);
 
 const char *abm_last_error(void) { return g_err.c_str(); }
-int abm_version(void) { return 1; }
+int abm_version(void) { return 2; }   // 2: abm_problem_desc gained the agent_* tables
 int abm_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -171,9 +171,63 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
         if (desc->tab_L[i] != desc->tab_U[i]) rowOf[i] = nRows++;
     const int nnz = desc->nb_ptr[nCols];
     const int G = desc->grid_size, T = desc->n_timesteps;
-    const int S = 2 * G * G, nStates = T * S, nEvents = nStates * kActs;
-    if (G > 0) {
-        if (nEvents > nRows) return fail(ABM_ERR_INVALID, "PredPrey importance needs one row per event");
+    // the agent: PredPrey by its grid geometry, or any other agent type by tables (abmcmc_b200.h); either way the host works
+    // from the same four tables: class, influencers, neighbours(), consequences()
+    const bool tableAgent = G == 0 && desc->n_agent_states > 0;
+    const int A = tableAgent ? desc->n_acts : kActs;
+    const int S = tableAgent ? desc->n_agent_states : 2 * G * G, nStates = T * S, nEvents = nStates * A;
+    const int nCls = tableAgent ? desc->n_agent_classes : 2;
+    std::vector<int32_t> agCls(std::max(S, 0)), agInfl(size_t(std::max(S, 0)) * 4, -1), agNbPtr(std::max(S, 0) + 1, 0), agNb,
+        agCqPtr(size_t(std::max(S, 0)) * A + 1, 0), agCq;
+    if (tableAgent) {
+        if (A < 1 || A > kActs || T < 1 || nCls < 1 || nCls > 1024) return fail(ABM_ERR_INVALID, "agent tables: 1..6 acts, at least one timestep and class");
+        if (!desc->agent_class || !desc->agent_influencers || !desc->agent_nb_ptr || !desc->agent_cq_ptr)
+            return fail(ABM_ERR_INVALID, "null array in the agent tables");
+        if (desc->agent_nb_ptr[0] != 0 || desc->agent_cq_ptr[0] != 0) return fail(ABM_ERR_INVALID, "agent tables: CSR pointers must start at 0");
+        for (int q = 0; q < S; ++q) {
+            if (desc->agent_class[q] < 0 || desc->agent_class[q] >= nCls) return fail(ABM_ERR_INVALID, "agent tables: class out of range");
+            agCls[q] = desc->agent_class[q];
+            for (int k = 0; k < 4; ++k) {
+                const int v = desc->agent_influencers[4 * q + k];
+                if (v < -1 || v >= S) return fail(ABM_ERR_INVALID, "agent tables: influencer out of range");
+                agInfl[4 * q + k] = v;
+            }
+            if (desc->agent_nb_ptr[q + 1] < desc->agent_nb_ptr[q]) return fail(ABM_ERR_INVALID, "agent tables: neighbour pointers must be non-decreasing");
+        }
+        for (int q = 0; q < S * A; ++q)
+            if (desc->agent_cq_ptr[q + 1] < desc->agent_cq_ptr[q]) return fail(ABM_ERR_INVALID, "agent tables: consequence pointers must be non-decreasing");
+        if ((desc->agent_nb_ptr[S] > 0 && !desc->agent_nb) || (desc->agent_cq_ptr[S * A] > 0 && !desc->agent_cq))
+            return fail(ABM_ERR_INVALID, "null array in the agent tables");
+        agNbPtr.assign(desc->agent_nb_ptr, desc->agent_nb_ptr + S + 1);
+        agNb.assign(desc->agent_nb, desc->agent_nb + agNbPtr[S]);
+        agCqPtr.assign(desc->agent_cq_ptr, desc->agent_cq_ptr + S * A + 1);
+        agCq.assign(desc->agent_cq, desc->agent_cq + agCqPtr[S * A]);
+        for (int v : agNb) if (v < 0 || v >= S) return fail(ABM_ERR_INVALID, "agent tables: neighbour out of range");
+        for (int v : agCq) if (v < 0 || v >= S) return fail(ABM_ERR_INVALID, "agent tables: consequence out of range");
+    } else if (G > 0) {
+        const int GG = G * G;
+        for (int psi = 0; psi < S; ++psi) {
+            const int type = psi / GG, cell = psi % GG, cy = cell / G, cx = cell % G;
+            const int ob = (1 - type) * GG, tb = type * GG;
+            const int xl = (cx + G - 1) % G, xr = (cx + 1) % G, yu = (cy + 1) % G, yd = (cy + G - 1) % G;
+            agCls[psi] = type;
+            // PredPreyAgent.h:199-207 (neighbours: left, right, up, down of the other species) -- also what timestep() reads (:124-157)
+            const int nb4[4] = {ob + xl + G * cy, ob + xr + G * cy, ob + cx + G * yu, ob + cx + G * yd};
+            for (int k = 0; k < 4; ++k) { agInfl[4 * psi + k] = nb4[k]; agNb.push_back(nb4[k]); }
+            agNbPtr[psi + 1] = int32_t(agNb.size());
+            // PredPreyAgent::consequences (PredPreyAgent.h:98-115): die -> nothing; the four moves; give birth -> parent and child
+            for (int a2 = 0; a2 < kActs; ++a2) {
+                if (a2 == 1) agCq.push_back(tb + xl + G * cy);
+                else if (a2 == 2) agCq.push_back(tb + xr + G * cy);
+                else if (a2 == 3) agCq.push_back(tb + cx + G * yu);
+                else if (a2 == 4) agCq.push_back(tb + cx + G * yd);
+                else if (a2 == 5) { agCq.push_back(tb + cx + G * cy); agCq.push_back(tb + xr + G * cy); }
+                agCqPtr[psi * kActs + a2 + 1] = int32_t(agCq.size());
+            }
+        }
+    }
+    if (G > 0 || tableAgent) {
+        if (nEvents > nRows) return fail(ABM_ERR_INVALID, "the trajectory importance needs one row per event");
         for (int i = 0; i < nEvents; ++i)
             if (rowOf[i] != i) return fail(ABM_ERR_INVALID, "event rows must be the first, non-equality tableau rows");
         if (!desc->imp_lgamma || !desc->imp_logratio) return fail(ABM_ERR_INVALID, "missing importance tables");
@@ -218,10 +272,13 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     }
 
     // physical layout of X: event rows 8 bytes per agent state, then the remaining rows
-    const int evBytes = nStates * kStateBytes;
+    // (with the kernels' table path -- grids that are not a power of two, table agents -- one more, always-zero state word follows:
+    // the word an unused influencer slot reads)
+    const bool pow2Grid = G > 0 && (G & (G - 1)) == 0;
+    const int evBytes = (nStates + (nStates > 0 && !pow2Grid ? 1 : 0)) * kStateBytes;
     std::vector<int32_t> xoff(nRows);
     for (int i = 0; i < nRows; ++i)
-        xoff[i] = i < nEvents ? (i / kActs) * kStateBytes + i % kActs : evBytes + (i - nEvents);
+        xoff[i] = i < nEvents ? (i / A) * kStateBytes + i % A : evBytes + (i - nEvents);
     const int xStride = ((evBytes + (nRows - nEvents)) + 15) & ~15;
     if (xStride >= (1 << 24)) return fail(ABM_ERR_INVALID, "too many rows");
 
@@ -376,19 +433,14 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
         }
         // stale factors in TrajectoryImportance::perturb insertion order (TrajectoryImportance.h:41-53)
         staleF.clear();
-        if (G > 0) {
+        if (nStates > 0) {
             auto ins = [&](int sid) { if (!seen[sid]) { seen[sid] = 1; staleF.push_back(sid); } };
             for (int k = 0; k < n; ++k) {
                 const int i = colRow[colPtr[j] + k];
                 if (i >= nEvents) continue;
-                const int sid = i / kActs, t = sid / S, psi = sid % S;
-                const int x = psi % G, y = (psi / G) % G, other = 1 - psi / (G * G);
-                const int base = t * S + other * G * G;
+                const int sid = i / A, t = sid / S, psi = sid % S;
                 ins(sid);
-                ins(base + (x + G - 1) % G + G * y);
-                ins(base + (x + 1) % G + G * y);
-                ins(base + x + G * ((y + 1) % G));
-                ins(base + x + G * ((y + G - 1) % G));
+                for (int q = agNbPtr[psi]; q < agNbPtr[psi + 1]; ++q) ins(t * S + agNb[q]);
             }
             for (int sid : staleF) seen[sid] = 0;
         }
@@ -400,7 +452,7 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
             if (colRow[colPtr[j] + k] >= nEvents) return fail(ABM_ERR_INVALID, "internal: event rows are not leading");
         if (C > 2040) return fail(ABM_ERR_INVALID, "a column is coupled to more than 2040 others");
         bool touchesEnd = false;
-        for (int k = 0; k < nEv; ++k) touchesEnd = touchesEnd || colRow[colPtr[j] + k] >= (T - 1) * S * kActs;
+        for (int k = 0; k < nEv; ++k) touchesEnd = touchesEnd || colRow[colPtr[j] + k] >= (T - 1) * S * A;
         // header (4 words), rows (2 words each), stale factors, slots, extra pair lists, end-state effects
         rec.push_back(uint32_t(n) | uint32_t(staleF.size()) << 8 | uint32_t(C) << 16);
         if (xtra.size() > 0x3fff) return fail(ABM_ERR_INVALID, "pair lists of one column too long");
@@ -425,21 +477,17 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
             int synD[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int k = 0; k < nEv; ++k) {
                 const int i = colRow[colPtr[j] + k];
-                if (i < (T - 1) * S * kActs) continue;
-                const int a2 = i % kActs, psi = (i / kActs) % S, m = colVal[colPtr[j] + k];
-                const int type = psi / (G * G), cell = psi % (G * G), cy = cell / G, cx = cell % G, tb = type * G * G;
-                int tx[2] = {-1, -1}, ty[2] = {cy, cy};
-                if (a2 == 1) tx[0] = (cx + G - 1) % G;
-                else if (a2 == 2) tx[0] = (cx + 1) % G;
-                else if (a2 == 3) { tx[0] = cx; ty[0] = (cy + 1) % G; }
-                else if (a2 == 4) { tx[0] = cx; ty[0] = (cy + G - 1) % G; }
-                else if (a2 == 5) { tx[0] = cx; tx[1] = (cx + 1) % G; }
-                for (int q = 0; q < 2; ++q) {
-                    if (tx[q] < 0) continue;
-                    endFx.push_back(int32_t(uint32_t(tb + tx[q] + G * ty[q]) | (uint32_t(m & 0xff) << 24)));
-                    for (int z = 0; z < nSyn; ++z) {
-                        const int sz = G >> (z + 1), org = G - 2 * sz;
-                        if (tx[q] >= org && tx[q] < org + sz && ty[q] >= org && ty[q] < org + sz) synD[z] += m;
+                if (i < (T - 1) * S * A) continue;
+                const int a2 = i % A, psi = (i / A) % S, m = colVal[colPtr[j] + k];
+                for (int q = agCqPtr[psi * A + a2]; q < agCqPtr[psi * A + a2 + 1]; ++q) {
+                    const int to = agCq[q];
+                    endFx.push_back(int32_t(uint32_t(to) | (uint32_t(m & 0xff) << 24)));
+                    if (G > 0) {
+                        const int cell = to % (G * G), tx = cell % G, ty = cell / G;
+                        for (int z = 0; z < nSyn; ++z) {
+                            const int sz = G >> (z + 1), org = G - 2 * sz;
+                            if (tx >= org && tx < org + sz && ty >= org && ty < org + sz) synD[z] += m;
+                        }
                     }
                 }
             }
@@ -463,18 +511,43 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
 
     // [7] lgamma(occ+1), [2][2][6] log(pi/pibar), then the factor log-probability of TrajectoryImportance::refresh
     // (TrajectoryImportance.h:96-108) for every (type, neighbour flag, set of present acts), summed in the reference's order
-    std::vector<double> impTab(7 + 24 + 4 * 64, 0.0);
-    if (G > 0) {
+    // (classes: the two agent types of PredPrey, or the table agent's)
+    std::vector<double> impTab(7 + 24 + size_t(2 * nCls) * 64, 0.0);
+    if (nStates > 0) {
         std::copy(desc->imp_lgamma, desc->imp_lgamma + 7, impTab.begin());
-        std::copy(desc->imp_logratio, desc->imp_logratio + 24, impTab.begin() + 7);
-        for (int tn = 0; tn < 4; ++tn)
-            for (int bits = 0; bits < 64; ++bits) {
+        if (!tableAgent) std::copy(desc->imp_logratio, desc->imp_logratio + 24, impTab.begin() + 7);
+        for (int tn = 0; tn < 2 * nCls; ++tn)
+            for (int bits = 0; bits < (1 << A); ++bits) {
                 const int occ = __builtin_popcount(bits);
                 volatile double pv = occ > 1 ? impTab[occ] : 0.0;   // volatile: one rounded add per act, no reassociation
-                for (int a2 = 0; a2 < kActs; ++a2)
-                    if ((bits >> a2) & 1) pv = pv + impTab[7 + tn * kActs + a2];
+                for (int a2 = 0; a2 < A; ++a2)
+                    if ((bits >> a2) & 1) pv = pv + desc->imp_logratio[tn * A + a2];
                 impTab[31 + tn * 64 + bits] = pv;
             }
+    }
+    // device tables: {class, 4 influencers} per agent state for the kernels' table path (grids that are not a power of two and
+    // table agents), and for table agents the events feeding each state of the next timestep (byte offsets into a timestep of Xb)
+    std::vector<int32_t> agentTab, endInPtr, endIn;
+    int gShift = -1;
+    for (int k = 0; k < 30; ++k) if (G == (1 << k)) gShift = k;
+    if (nStates > 0 && gShift < 0) {
+        agentTab.resize(size_t(S) * 5 + 3);
+        for (int q = 0; q < S; ++q) {
+            agentTab[5 * q] = agCls[q];
+            for (int k = 0; k < 4; ++k) agentTab[5 * q + 1 + k] = agInfl[4 * q + k];
+        }
+    }
+    if (tableAgent) {
+        std::vector<std::vector<int32_t>> in(S);
+        for (int psi = 0; psi < S; ++psi)
+            for (int a2 = 0; a2 < A; ++a2)
+                for (int q = agCqPtr[psi * A + a2]; q < agCqPtr[psi * A + a2 + 1]; ++q) in[agCq[q]].push_back(psi * kStateBytes + a2);
+        endInPtr.push_back(0);
+        for (int q = 0; q < S; ++q) {
+            endIn.insert(endIn.end(), in[q].begin(), in[q].end());
+            endInPtr.push_back(int32_t(endIn.size()));
+        }
+        endIn.push_back(0);
     }
 
     std::unique_ptr<abm_problem> owner(new abm_problem());
@@ -497,8 +570,7 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     d.blockedTree = desc->sum_tree == ABM_TREE_REFERENCE ? 0 : 1;
     if (const char *e = getenv("ABM_TREE")) d.blockedTree = std::string(e) != "reference";
     if (d.blockedTree && nCols > (1 << 20)) return fail(ABM_ERR_INVALID, "blocked tree supports up to 2^20 columns");
-    d.gShift = -1;
-    for (int k = 0; k < 30; ++k) if (G == (1 << k)) d.gShift = k;
+    d.gShift = gShift;
     d.groupWidth = W;
     d.rowsCap = (maxColNnz + 7) & ~7;
     d.sCap = (maxCoupled + 7) & ~7;
@@ -540,13 +612,16 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     if (hostOnly) {   // what the uploads below would occupy
         auto bytes = [](const auto &v) { return int64_t(v.size() * sizeof(v[0])); };
         inf.shared_bytes = bytes(recIdx) + bytes(rec) + bytes(facVal) + bytes(eTab) + bytes(impTab) + bytes(colPtr) + bytes(colRow) + bytes(colVal) +
-                           bytes(rowPtr) + bytes(rowCol) + bytes(rowVal) + bytes(rowF) + bytes(rowParam) + bytes(colEvent);
+                           bytes(rowPtr) + bytes(rowCol) + bytes(rowVal) + bytes(rowF) + bytes(rowParam) + bytes(colEvent) + bytes(agentTab) +
+                           bytes(endInPtr) + bytes(endIn);
         *hostOnly = inf;
         return ABM_OK;
     }
     cudaError_t e = cudaSuccess;
     auto up = [&](auto **dst, const auto &v) { if (e == cudaSuccess) e = p->arena.upload(dst, v); };
     up(&d.recIdx, recIdx); up(&d.rec, rec); up(&d.facVal, facVal); up(&d.eTab, eTab); up(&d.impTab, impTab);
+    if (!agentTab.empty()) up(&d.agentTab, agentTab);
+    if (!endInPtr.empty()) { up(&d.endInPtr, endInPtr); up(&d.endIn, endIn); }
     up(&d.colPtr, colPtr); up(&d.colRow, colRow); up(&d.colVal, colVal);
     up(&d.rowPtr, rowPtr); up(&d.rowCol, rowCol); up(&d.rowVal, rowVal);
     up(&d.rowF, rowF); up(&d.rowParam, rowParam); up(&d.colEvent, colEvent);
@@ -918,7 +993,7 @@ static int zeroStatistics(abm_chains *c) {
 int abm_chains_sample(abm_chains *c, int64_t nSamples, int64_t maxSteps) {
     if (!c || nSamples < 0 || (nSamples == 0 && maxSteps <= 0)) return fail(ABM_ERR_INVALID, "bad argument");
     if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
-    if (c->p->d.G <= 0) return fail(ABM_ERR_INVALID, "sample statistics need the PredPrey geometry");
+    if (c->p->d.nStates <= 0) return fail(ABM_ERR_INVALID, "sample statistics need an agent description (PredPrey grid or agent tables)");
     CUDA_TRY(cudaSetDevice(c->p->device));
     // per-launch step and sample counts live in 32-bit registers: one call is one launch of at most 2^30 steps / samples
     if (nSamples > kMaxStepsPerLaunch && (maxSteps <= 0 || maxSteps > kMaxStepsPerLaunch))
@@ -1350,7 +1425,7 @@ int abm_chains_sample_injected(abm_chains *c, int64_t nSteps, const double *unif
     if (!c || nSteps <= 0 || !uniforms) return fail(ABM_ERR_INVALID, "bad argument");
     if (nSteps > INT32_MAX) return fail(ABM_ERR_INVALID, "at most 2^31-1 steps per launch");
     if (!c->feasible) return fail(ABM_ERR_STATE, "chains have no feasible start (call abm_chains_find_feasible)");
-    if (c->p->d.G <= 0) return fail(ABM_ERR_INVALID, "sample statistics need the PredPrey geometry");
+    if (c->p->d.nStates <= 0) return fail(ABM_ERR_INVALID, "sample statistics need an agent description (PredPrey grid or agent tables)");
     CUDA_TRY(cudaSetDevice(c->p->device));
     const size_t n = size_t(c->n), ns = size_t(nSteps);
     DeviceArena tmp;

@@ -45,7 +45,7 @@ struct DevProblem {
     int t1Len, t2Len;
     int topShift, nTop;     // nodes whose index is a multiple of 2^topShift (<= 32 of them) are held in shared memory by the step kernel
     int evBytes;            // bytes of the padded event region of Xb = nStates * kStateBytes
-    int G, S, T, nStates;   // PredPrey geometry (G == 0: no importance)
+    int G, S, T, nStates;   // PredPrey grid (0: none), agent states per timestep, timesteps, T * S (0: no importance function)
     int gShift;             // log2(G) when G is a power of two, else -1
     int blockedTree;        // 1: 32-ary blocked sum tree (colRec.y = leaf p_u), 0: the reference's binary sum tree
     int groupWidth;         // W
@@ -63,7 +63,12 @@ struct DevProblem {
     const uint32_t *rec;
     const double *eTab;     // energy tables of the row classes (step kernel)
     const double *facVal;   // de-duplicated factor tables (construction kernels)
-    const double *impTab;   // [7] lgamma table, then [2][2][6] log ratios
+    const double *impTab;   // [7] lgamma table, [2][2][6] log ratios (PredPrey), then at 31 + ((class * 2 + flag) << 6 | present acts) the
+                            // factor log-probability of TrajectoryImportance::refresh
+    const int32_t *agentTab;   // [S][5] {class, 4 influencer agent states (-1: unused)}: grids that are not a power of two and agents
+                               // described by tables (abmcmc_b200.h); null on power-of-two PredPrey grids (geometry by shifts)
+    const int32_t *endInPtr, *endIn;   // table agents: per agent state, the byte offsets (state * 8 + act) of the events of the previous
+                                       // timestep that feed it (State::backwardOccupation, State.h:57-63); null for PredPrey
     // construction only
     const int32_t *colPtr, *colRow, *colVal;   // CSR by column (sampler row ids)
     const int32_t *rowPtr, *rowCol, *rowVal;   // CSR by row

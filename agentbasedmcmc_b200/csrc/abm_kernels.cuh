@@ -258,16 +258,18 @@ __device__ __forceinline__ double factorLogP(unsigned long long own, bool neighb
     return __ldg(impTab + 31 + ((type * 2 + (neighbour ? 1 : 0)) << 6) + presentActs(posMask(own)));
 }
 
-// (type, x, y) of a state id and the base index of the opposite species at the same time, for grids that are not a
-// power of two (cold path; the hot path uses shifts)
-__device__ __noinline__ void stateGeometry(int sid, int S, int G, int &type, int &cx, int &cy, int &ob) {
-    const int GG = G * G;
-    const int t = sid / S, psi = sid - t * S;
-    type = psi / GG;
-    const int cell = psi - type * GG;
-    cy = cell / G;
-    cx = cell - cy * G;
-    ob = t * S + (1 - type) * GG;
+// Class and influencer state ids of a state id from the agent table (DevProblem::agentTab) -- grids that are not a power of two
+// and agents described by tables; cold path, the paper's grids use shifts.  An unused influencer slot reads the always-zero
+// state word that follows the trajectory (index nStates).
+struct StateInfo { int cls, n0, n1, n2, n3; };
+__device__ __noinline__ StateInfo stateFromTable(int sid, int S, int nStates, const int32_t *__restrict__ tab) {
+    const int t = sid / S, psi = sid - t * S, base = sid - psi;
+    const int32_t *e = tab + 5 * psi;
+    auto at = [&](int k) { const int v = __ldg(e + 1 + k); return v >= 0 ? base + v : nStates; };
+    StateInfo r;
+    r.cls = __ldg(e);
+    r.n0 = at(0); r.n1 = at(1); r.n2 = at(2); r.n3 = at(3);
+    return r;
 }
 
 __device__ __forceinline__ int warpSumInt(int v) {
@@ -818,22 +820,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     unsigned long long own = 0ull, nb[4] = {0ull, 0ull, 0ull, 0ull};
                     if (fa) {
                         sid = (int)recWord(staleOff + f);
-                        int cx, cy, ob;
                         if (P.gShift >= 0) {   // power-of-two grids: psi = x + G y + G^2 type (PredPreyAgent.h:59) by shifts
                             const int psi = sid & (P.S - 1), cell = psi & (GG - 1);
                             type = psi >> (2 * P.gShift);
-                            cy = cell >> P.gShift; cx = cell & (G - 1);
-                            ob = (sid - psi) + (1 - type) * GG;
-                        } else {
-                            stateGeometry(sid, P.S, G, type, cx, cy, ob);
+                            const int cy = cell >> P.gShift, cx = cell & (G - 1);
+                            const int ob = (sid - psi) + (1 - type) * GG;
+                            // PredPreyAgent.h:199-207: left, right, up, down, opposite species, torus
+                            const int xl = cx == 0 ? G - 1 : cx - 1, xr = cx == G - 1 ? 0 : cx + 1;
+                            const int yu = cy == G - 1 ? 0 : cy + 1, yd = cy == 0 ? G - 1 : cy - 1;
+                            ns[0] = ob + xl + G * cy;
+                            ns[1] = ob + xr + G * cy;
+                            ns[2] = ob + cx + G * yu;
+                            ns[3] = ob + cx + G * yd;
+                        } else {               // any other grid, any other agent: the states timestep() reads, from the table
+                            const StateInfo si = stateFromTable(sid, P.S, P.nStates, P.agentTab);
+                            type = si.cls;
+                            ns[0] = si.n0; ns[1] = si.n1; ns[2] = si.n2; ns[3] = si.n3;
                         }
-                        // PredPreyAgent.h:199-207: left, right, up, down, opposite species, torus
-                        const int xl = cx == 0 ? G - 1 : cx - 1, xr = cx == G - 1 ? 0 : cx + 1;
-                        const int yu = cy == G - 1 ? 0 : cy + 1, yd = cy == 0 ? G - 1 : cy - 1;
-                        ns[0] = ob + xl + G * cy;
-                        ns[1] = ob + xr + G * cy;
-                        ns[2] = ob + cx + G * yu;
-                        ns[3] = ob + cx + G * yd;
                         own = X8[sid];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) nb[q] = X8[ns[q]];
@@ -1579,7 +1582,7 @@ __global__ void setStateKernel(DevProblem P, DevChains S) {
     const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (chain >= S.nChains) return;
     double total = 0.0;
-    if (P.G > 0) {
+    if (P.nStates > 0) {
         const unsigned long long *X8 = reinterpret_cast<const unsigned long long *>(S.Xb + (size_t)chain * P.xStride);
         const int G = P.G, GG = G * G;
         for (int sb = 0; sb < P.nStates; sb += 32) {
@@ -1589,13 +1592,19 @@ __global__ void setStateKernel(DevProblem P, DevChains S) {
             if (sid < P.nStates) {
                 const unsigned long long own = X8[sid];
                 if (posMask(own)) {
-                    const int t = sid / P.S, psi = sid - t * P.S;
-                    const int type = psi / GG, cell = psi - type * GG;
-                    const int cy = cell / G, cx = cell - cy * G;
-                    const int ob = t * P.S + (1 - type) * GG;
-                    const unsigned long long nbm = posMask(X8[ob + (cx + G - 1) % G + G * cy]) | posMask(X8[ob + (cx + 1) % G + G * cy]) |
-                                                   posMask(X8[ob + cx + G * ((cy + 1) % G)]) | posMask(X8[ob + cx + G * ((cy + G - 1) % G)]);
-                    v = factorLogP(own, nbm != 0ull, type, P.impTab);
+                    if (P.agentTab) {
+                        const StateInfo si = stateFromTable(sid, P.S, P.nStates, P.agentTab);
+                        const unsigned long long nbm = posMask(X8[si.n0]) | posMask(X8[si.n1]) | posMask(X8[si.n2]) | posMask(X8[si.n3]);
+                        v = factorLogP(own, nbm != 0ull, si.cls, P.impTab);
+                    } else {
+                        const int t = sid / P.S, psi = sid - t * P.S;
+                        const int type = psi / GG, cell = psi - type * GG;
+                        const int cy = cell / G, cx = cell - cy * G;
+                        const int ob = t * P.S + (1 - type) * GG;
+                        const unsigned long long nbm = posMask(X8[ob + (cx + G - 1) % G + G * cy]) | posMask(X8[ob + (cx + 1) % G + G * cy]) |
+                                                       posMask(X8[ob + cx + G * ((cy + 1) % G)]) | posMask(X8[ob + cx + G * ((cy + G - 1) % G)]);
+                        v = factorLogP(own, nbm != 0ull, type, P.impTab);
+                    }
                     nz = true;
                 }
             }
@@ -1629,6 +1638,14 @@ __device__ __forceinline__ int endOccupancy(const int8_t *__restrict__ Xl, int p
     return act(X8[right], 1) + act(wl, 2) + act(X8[down], 3) + act(X8[up], 4) + act(X8[psi], 5) + act(wl, 5);
 }
 
+// The same for an agent described by tables: the events of the last timestep listed for the state (DevProblem::endIn)
+__device__ __forceinline__ int endOccupancyTab(const int8_t *__restrict__ Xl, int psi, const int32_t *__restrict__ ptr,
+                                               const int32_t *__restrict__ list) {
+    int occ = 0;
+    for (int q = __ldg(ptr + psi); q < __ldg(ptr + psi + 1); ++q) occ += Xl[__ldg(list + q)];
+    return occ;
+}
+
 // Before a sampling launch: the synopsis (FiguresForPaper.h:245-263) of every chain's current end state, from which
 // stepKernel<MODE_SAMPLE> proceeds incrementally.  One warp per chain.
 __global__ void sampleBeginKernel(DevProblem P, DevChains S) {
@@ -1658,7 +1675,8 @@ __global__ void sampleEndKernel(DevProblem P, DevChains S) {   // one CTA per ch
     longlong2 *rec = reinterpret_cast<longlong2 *>(S.endRec + (size_t)chain * P.S);   // {acc, pend}
     for (int psi = threadIdx.x; psi < P.S; psi += blockDim.x) {
         longlong2 e = rec[psi];
-        e.x += (long long)endOccupancy(Xl, psi, P.G, P.gShift) * nSamp - e.y;
+        const int occ = P.endInPtr ? endOccupancyTab(Xl, psi, P.endInPtr, P.endIn) : endOccupancy(Xl, psi, P.G, P.gShift);
+        e.x += (long long)occ * nSamp - e.y;
         e.y = 0;
         rec[psi] = e;
     }

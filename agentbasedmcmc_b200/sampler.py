@@ -36,6 +36,14 @@ def _problem_desc(abmp: dict, with_importance: bool = True, sum_tree: str = "blo
     use_imp = with_importance and "pp_meta" in abmp
     d.grid_size = int(abmp["pp_meta"][0]) if use_imp else 0
     d.n_timesteps = int(abmp["pp_meta"][1]) if use_imp else 0
+    if with_importance and "ag_meta" in abmp:   # an agent type other than PredPrey, by tables (reference_flatten.hpp)
+        d.n_agent_states, d.n_acts, d.n_timesteps, d.n_agent_classes = (int(v) for v in abmp["ag_meta"][:4])
+        for name, field in (("ag_class", "agent_class"), ("ag_infl", "agent_influencers"), ("ag_nb_ptr", "agent_nb_ptr"),
+                            ("ag_nb", "agent_nb"), ("ag_cq_ptr", "agent_cq_ptr"), ("ag_cq", "agent_cq")):
+            k[name] = np.ascontiguousarray(abmp[name], dtype=np.int32)
+            if k[name].size == 0:   # an empty list still needs an address
+                k[name] = np.zeros(1, np.int32)
+            setattr(d, field, _ptr(k[name], C.c_int32))
     d.imp_lgamma = _ptr(k["imp_lgamma"], C.c_double)
     d.imp_logratio = _ptr(k["imp_logratio"], C.c_double)
     d.sum_tree = {"blocked": 0, "reference": 1}[sum_tree]
@@ -74,6 +82,8 @@ class Problem:
         self.info = info
         self.n_rows, self.n_cols, self.n_events = info.n_rows, info.n_cols, info.n_events
         self.grid_size, self.n_timesteps = d.grid_size, d.n_timesteps
+        # agent states per timestep (ModelState's length): PredPrey's two species on the grid, or the table agent's domain
+        self.n_agent_states = d.n_agent_states if d.grid_size == 0 else 2 * d.grid_size ** 2
         self.n_synopsis = L.abm_problem_n_synopsis(self.h)
 
     def close(self):
@@ -197,8 +207,7 @@ class SparseBasisSampler:
     def statistics(self):
         """(end_state_sum[S] summed over chains, syn_sum[n_chains][d], syn_sumsq[n_chains][d], n_samples[n_chains])."""
         P = self.problem
-        S = 2 * P.grid_size ** 2
-        end = np.zeros(S, np.int64)
+        end = np.zeros(P.n_agent_states, np.int64)
         ss = np.zeros((self.n_chains, P.n_synopsis), np.int64)
         sq = np.zeros((self.n_chains, P.n_synopsis), np.int64)
         ns = np.zeros(self.n_chains, np.int64)
@@ -214,7 +223,7 @@ class SparseBasisSampler:
     def wait_statistics(self):
         """(end_state_sum, syn_sum, syn_sumsq, n_samples, counters[n_chains][8]) of the last `enqueue_statistics`."""
         P = self.problem
-        end = np.zeros(2 * P.grid_size ** 2, np.int64)
+        end = np.zeros(P.n_agent_states, np.int64)
         ss = np.zeros((self.n_chains, P.n_synopsis), np.int64)
         sq = np.zeros((self.n_chains, P.n_synopsis), np.int64)
         ns = np.zeros(self.n_chains, np.int64)
@@ -230,7 +239,7 @@ class SparseBasisSampler:
 
     # ---- ensemble moments reduced on the device (abm_chains_get_moments & co., include/abmcmc_b200.h)
     def _moment_buffers(self):
-        S = 2 * self.problem.grid_size ** 2
+        S = self.problem.n_agent_states
         return np.zeros(_capi.MOMENTS_EXACT_HEAD + S, np.int64), np.zeros(_capi.MOMENTS_REAL, np.float64)
 
     def moments(self, comm=None):

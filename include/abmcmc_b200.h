@@ -56,12 +56,30 @@ typedef struct {
     const int32_t *ut_off;   /* [n_tables+1] offsets into ut_val                                  */
     const double *ut_val;    /* factor values f(x), x = lo .. lo+len-1 (clamp of reachable range) */
     double kappa;            /* SparseBasisSampler::kappa (:33)                                   */
-    int32_t grid_size;       /* PredPrey GRIDSIZE; 0 = no importance function (log W == 0)        */
+    int32_t grid_size;       /* PredPrey GRIDSIZE; 0 = another agent (agent_* below) or, without those, no importance function (log W == 0) */
     int32_t n_timesteps;
     const double *imp_lgamma;   /* [7]  lgamma(occ+1) for occ>1 else 0 (TrajectoryImportance.h:96) */
     const double *imp_logratio; /* [2][2][6] log(pi/pibar) by type, has-neighbour flag, act (:105) */
     int32_t sum_tree;        /* storage of basisDistribution (MutableCategoricalArray): ABM_TREE_BLOCKED (0, default) or
                               * ABM_TREE_REFERENCE; the environment variable ABM_TREE=blocked|reference overrides it */
+    /* TrajectoryImportance<AGENT> for an agent type OTHER than PredPreyAgent (grid_size == 0, n_agent_states > 0; all zero /
+     * null otherwise), described by tables of the agent's own functions (reference_flatten.hpp fills them by calling
+     * AGENT::timestep / marginalTimestep / neighbours / consequences on the host).  The form covered is the one every agent
+     * of the reference has: timestep() of an agent state reads the other states only through "is any of up to four given
+     * states (its influencers) occupied" (PredPreyAgent.h:124-157 -- the four adjacent cells of the other species;
+     * CatMouseAgent.cpp:8-24 -- the cat at the mouse's position; BinomialAgent.h:33 -- none).  Event ids are
+     * (t * n_agent_states + state) * n_acts + act (Event.h:18-19), state ids t * n_agent_states + state (State.h:40-42). */
+    int32_t n_agent_states;            /* AGENT::domainSize()                                                  */
+    int32_t n_acts;                    /* AGENT::actDomainSize(), at most 6                                    */
+    int32_t n_agent_classes;           /* agent states with the same log-ratio rows share a class              */
+    const int32_t *agent_class;        /* [n_agent_states]                                                     */
+    const int32_t *agent_influencers;  /* [n_agent_states][4] agent states, -1 = unused                        */
+    const int32_t *agent_nb_ptr;       /* [n_agent_states+1] AGENT::neighbours() in its own order: the states whose  */
+    const int32_t *agent_nb;           /*   factor TrajectoryImportance::perturb marks stale (:48-51)           */
+    const int32_t *agent_cq_ptr;       /* [n_agent_states*n_acts+1] AGENT::consequences(act): the states an event feeds */
+    const int32_t *agent_cq;           /*   at the next timestep (ModelState.h:27-36 end-state statistics)      */
+    /* with agent tables: imp_lgamma is [7] as above and imp_logratio is [n_agent_classes][2][n_acts] (class, any influencer
+     * occupied, act) */
 } abm_problem_desc;
 
 /* ABM_TREE_REFERENCE keeps the reference's binary sum tree node for node and add for add (every double of the tree
@@ -76,7 +94,7 @@ typedef struct {
     int32_t n_rows, n_cols, nnz, n_events;
     int32_t max_col_nnz, max_coupled; /* longest column; most columns sharing a row with one column */
     int32_t tree_depth;               /* bit length of n_cols-1 (MutableCategoricalArray.cpp:41-48) */
-    int32_t n_states;                 /* T * 2 * G * G (0 without importance)                    */
+    int32_t n_states;                 /* T * agent states per timestep: 2 * G * G for PredPrey (0 without importance) */
     int64_t chain_state_bytes;        /* HBM bytes of one chain (everything abm_chains_create allocates per chain) */
     int64_t shared_bytes;             /* HBM bytes of the shared structure                        */
 } abm_problem_info;
@@ -89,7 +107,7 @@ typedef struct {
 } abm_mcmc_counters;
 
 ABM_API const char *abm_last_error(void);
-ABM_API int abm_version(void);
+ABM_API int abm_version(void);   /* 2 since abm_problem_desc carries the agent_* tables: zero-initialise the struct (`abm_problem_desc d = {0}`) */
 ABM_API int abm_device_count(void); /* 0 when no CUDA device is usable */
 
 /* ---- problem: replaces the tableau-copy half of SparseBasisSampler::SparseBasisSampler (:121-158) */

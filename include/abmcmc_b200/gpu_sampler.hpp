@@ -6,6 +6,10 @@
 // The constructor keeps the reference signature: the CPU code still builds the basis (TableauNormMinimiser) and the
 // factor closures; this class flattens them (reference_flatten.hpp), uploads them and runs the chain on the GPU.
 //
+// Agent types: PredPreyAgent<G> (G in ABMCMC_PREDPREY_GRIDS) by its grid geometry; CatMouseAgent and BinomialAgent<2..8> by
+// tables when agents/CatMouseAgent.h / agents/BinomialAgent.h were included BEFORE this header; any further agent type listed in
+// ABMCMC_TABLE_AGENTS (comma-separated) -- see flattenAgentImportance in reference_flatten.hpp for the form an agent must have.
+//
 // Two ways to drive it:
 //   * operator()()  -- exact drop-in: one feasible sample per call, consuming the reference's own generator
 //     Random::gen exactly like SparseBasisSampler does (one generate_canonical double per feasibility iteration, two
@@ -46,6 +50,39 @@ bool detectPredPrey(PerturbableFunction<T, double> *f, AbmpFile &out, PredPreyGr
     return detectPredPrey<T>(f, out, PredPreyGrids<REST...>{});
 }
 
+// Any other agent type, by tables (flattenAgentImportance): the candidates are the agent classes of the reference whose
+// headers the program has included, plus whatever ABMCMC_TABLE_AGENTS names (a comma-separated list of agent types).
+template <class... AGENTS>
+struct TableAgents {};
+
+template <class T>
+bool detectTableAgent(PerturbableFunction<T, double> *, AbmpFile &, TableAgents<>) { return false; }
+
+template <class T, class AGENT, class... REST>
+bool detectTableAgent(PerturbableFunction<T, double> *f, AbmpFile &out, TableAgents<AGENT, REST...>) {
+    if (auto *imp = dynamic_cast<TrajectoryImportance<AGENT> *>(f)) {
+        flattenAgentImportance<AGENT>(out, imp->nTimesteps());
+        return true;
+    }
+    return detectTableAgent<T>(f, out, TableAgents<REST...>{});
+}
+
+template <class T>
+bool detectKnownTableAgents(PerturbableFunction<T, double> *f, AbmpFile &out) {
+    bool found = false;
+#ifdef GLPKTEST_CATMOUSEAGENT_H   // agents/CatMouseAgent.h
+    found = found || detectTableAgent<T>(f, out, TableAgents<CatMouseAgent>{});
+#endif
+#ifdef GLPKTEST_BINOMIALAGENT_H   // agents/BinomialAgent.h
+    found = found || detectTableAgent<T>(f, out, TableAgents<BinomialAgent<2>, BinomialAgent<3>, BinomialAgent<4>, BinomialAgent<5>,
+                                                             BinomialAgent<6>, BinomialAgent<7>, BinomialAgent<8>>{});
+#endif
+#ifdef ABMCMC_TABLE_AGENTS
+    found = found || detectTableAgent<T>(f, out, TableAgents<ABMCMC_TABLE_AGENTS>{});
+#endif
+    return found;
+}
+
 // libstdc++ generate_canonical<double,53> on a 32-bit engine, as Random::nextDouble() /
 // MutableCategoricalArray::uniformDist produce it (Random.h:21-23, MutableCategoricalArray.cpp:8)
 template <class GEN>
@@ -71,8 +108,10 @@ public:
         : kappa(Kappa) {
         AbmpFile f;
         flattenTableau<TableauNormMinimiser<T>, T>(f, tableau, tableauFactors, Kappa);
-        bool pp = detail::detectPredPrey<T>(importanceFunc.get(), f, detail::PredPreyGrids<ABMCMC_PREDPREY_GRIDS>{});
-        if (!pp) throw std::runtime_error("GpuSparseBasisSampler: the importance function must be TrajectoryImportance<PredPreyAgent<G>>");
+        const bool pp = detail::detectPredPrey<T>(importanceFunc.get(), f, detail::PredPreyGrids<ABMCMC_PREDPREY_GRIDS>{});
+        if (!pp && !detail::detectKnownTableAgents<T>(importanceFunc.get(), f))
+            throw std::runtime_error("GpuSparseBasisSampler: the importance function must be TrajectoryImportance<AGENT> for PredPreyAgent<G> "
+                                     "(G in ABMCMC_PREDPREY_GRIDS), CatMouseAgent, BinomialAgent<2..8> or a type listed in ABMCMC_TABLE_AGENTS");
         abm_problem_desc d{};
         const auto &dims = f.I("dims");
         d.n_tab_rows = dims[0];
@@ -83,8 +122,16 @@ public:
         d.n_tables = int32_t(f.I("ut_lo").size());
         d.ut_lo = f.I("ut_lo").data(); d.ut_off = f.I("ut_off").data(); d.ut_val = f.D("ut_val").data();
         d.kappa = Kappa;
-        d.grid_size = f.I("pp_meta")[0];
-        d.n_timesteps = f.I("pp_meta")[1];
+        if (pp) {
+            d.grid_size = f.I("pp_meta")[0];
+            d.n_timesteps = f.I("pp_meta")[1];
+        } else {
+            const auto &meta = f.I("ag_meta");
+            d.n_agent_states = meta[0]; d.n_acts = meta[1]; d.n_timesteps = meta[2]; d.n_agent_classes = meta[3];
+            d.agent_class = f.I("ag_class").data(); d.agent_influencers = f.I("ag_infl").data();
+            d.agent_nb_ptr = f.I("ag_nb_ptr").data(); d.agent_nb = f.I("ag_nb").data();
+            d.agent_cq_ptr = f.I("ag_cq_ptr").data(); d.agent_cq = f.I("ag_cq").data();
+        }
         d.imp_lgamma = f.D("imp_lgamma").data();
         d.imp_logratio = f.D("imp_logratio").data();
         d.sum_tree = sumTree;
@@ -94,7 +141,7 @@ public:
         nRows_ = info.n_rows;
         nCols_ = info.n_cols;
         init_.assign(initialState.begin(), initialState.end());
-        actPmf_ = f.D("pp_actpmf");
+        if (pp) actPmf_ = f.D("pp_actpmf");
         // the reference constructs one chain here, including findInitialFeasibleSolution() on Random::gen (:181)
         createChains(1, 0, /*exact=*/true);
     }
@@ -143,6 +190,7 @@ public:
     // ... or each chain from its own prior sample drawn on the device (what FiguresForPaper.h:56 gives every chain);
     // pPredator / pPrey are the start-state probabilities (Bernoulli) or rates (Poisson) of the problem (PredPreyProblem.h:36-37)
     void batchedFromPrior(int nChains, uint64_t seed, double pPredator, double pPrey, int startKind = ABM_START_BERNOULLI) {
+        if (actPmf_.empty()) throw std::logic_error("GpuSparseBasisSampler::batchedFromPrior: the device-side prior is PredPrey's; use batched()");
         if (chains_) { abm_chains_destroy(chains_); chains_ = nullptr; }
         nChains_ = nChains;
         detail::check(abm_chains_create(problem_, nChains, seed, 0, nullptr, &chains_), "abm_chains_create");

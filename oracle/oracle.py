@@ -33,6 +33,7 @@ def lib():
         L.orc_problem_create.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p, i32p, i32p, i32p, i32p, f64p,
                                          C.c_double, C.c_int, C.c_int, f64p, f64p]
         L.orc_problem_destroy.argtypes = [vp]
+        L.orc_problem_set_agent.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p, f64p, f64p]
         for f in ("orc_problem_nrows", "orc_problem_ncols", "orc_problem_nnz"):
             getattr(L, f).restype = C.c_int
             getattr(L, f).argtypes = [vp]
@@ -100,6 +101,17 @@ class OracleProblem:
         self.n_rows = L.orc_problem_nrows(self.h)
         self.n_cols = L.orc_problem_ncols(self.h)
         self.n_events = int(abmp["pp_meta"][2]) if "pp_meta" in abmp else 0
+        self.n_agent_states = 2 * G * G
+        if with_importance and "ag_meta" in abmp:   # an agent type other than PredPrey, by tables
+            S, A, T, n_cls = (int(v) for v in abmp["ag_meta"][:4])
+            for k in ("ag_class", "ag_infl", "ag_nb_ptr", "ag_nb", "ag_cq_ptr", "ag_cq"):
+                keep[k] = np.ascontiguousarray(abmp[k], dtype=np.int32)
+                if keep[k].size == 0:
+                    keep[k] = np.zeros(1, np.int32)
+            L.orc_problem_set_agent(self.h, S, A, T, n_cls, *(_p(keep[k], i32) for k in ("ag_class", "ag_infl", "ag_nb_ptr", "ag_nb",
+                                                                                          "ag_cq_ptr", "ag_cq")),
+                                    _p(keep["imp_lgamma"], C.c_double), _p(keep["imp_logratio"], C.c_double))
+            self.T, self.n_events, self.n_agent_states = T, T * S * A, S
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -190,7 +202,7 @@ class OracleChain:
 
     @property
     def end_state(self):
-        out = np.empty(2 * self.problem.G ** 2, np.int32)
+        out = np.empty(self.problem.n_agent_states, np.int32)
         lib().orc_chain_end_state(self.h, _p(out, C.c_int32))
         return out
 

@@ -260,18 +260,18 @@ struct SilenceStdout {  // the reference prints progress lines to std::cout from
 //   per step: tr_j i32, tr_acc u8, tr_inf i32 (proposal infeasibility);
 //   checkpoints every `every` steps: ck_hash (two i32 per u64), ck_logimp f64, ck_sum f64, ck_inf i32;
 //   final: X, delta, DE, leaf, counters.
-template <int G>
-int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int every, const std::string &out) {
-    PredPreyProblem<G> problem = importProblem<G>(f);
-    Random::gen.seed(initSeed);
-    std::vector<occ_t> init = priorSample<G>(problem);
+// (the body works for any agent type: `synopsis` maps an end state to the statistics of FiguresForPaper.h:245-263 where the
+// agent has them -- PredPrey -- and to nothing otherwise)
+template <class Agent, class SYNOPSIS>
+int traceSampler(const TableauNormMinimiser<occ_t> &tableau, const std::vector<std::function<double(occ_t)>> &factors,
+                 std::unique_ptr<PerturbableFunction<occ_t, double>> importance, const std::vector<occ_t> &init, double kappa, int T,
+                 SYNOPSIS synopsis, int initSeed, int chainSeed, long nSteps, int every, const std::string &out) {
     Random::gen.seed(chainSeed);
     std::unique_ptr<TracedSampler<occ_t>> sp;
     std::string ctorLog;
     {
         SilenceStdout quiet;
-        sp.reset(new TracedSampler<occ_t>(problem.tableau, problem.posterior.factors,
-                                          problem.posterior.perturbableFunctionFactory(), init, problem.kappa));
+        sp.reset(new TracedSampler<occ_t>(tableau, factors, std::move(importance), init, kappa));
         ctorLog = quiet.sink.str();
     }
     auto &s = *sp;
@@ -300,8 +300,6 @@ int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int ev
     // nextSampleWithInfeasibleImportance (SparseBasisSampler.h:247) hands out, i.e. the state after every step that ends
     // feasible, mapped by TrajectoryToModelState(T,T) (ModelState.h:27-36) and synopsis() (FiguresForPaper.h:245-263) --
     // the reference's own code -- and summed as Sum<ModelState> / MeanAndVariance do
-    typedef PredPreyAgent<G> Agent;
-    const int T = problem.nTimesteps();
     std::vector<double> smpEnd(Agent::domainSize(), 0.0);
     MeanAndVariance smpSyn;
     long nFeasible = 0;
@@ -313,7 +311,7 @@ int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int ev
         if (s.currentInfeasibility == 0) {
             ModelState<Agent> endState(s.X, T, T);
             for (int q = 0; q < Agent::domainSize(); ++q) smpEnd[q] += endState[q];
-            smpSyn(FiguresForPaper<G, 1>::synopsis(endState));
+            smpSyn(synopsis(endState));
             ++nFeasible;
         }
         if ((k + 1) % every == 0 || k + 1 == nSteps) {
@@ -325,7 +323,7 @@ int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int ev
             ckInf.push_back(int32_t(s.currentInfeasibility));
             ModelState<Agent> endState(s.X, T, T);
             for (int q = 0; q < Agent::domainSize(); ++q) ckEnd.push_back(int32_t(endState[q]));
-            for (double v : FiguresForPaper<G, 1>::synopsis(endState)) ckSyn.push_back(int32_t(v));
+            for (double v : synopsis(endState)) ckSyn.push_back(int32_t(v));
         }
     }
     t.i32["ck_endstate"] = ckEnd;        // [checkpoints][S]  ModelState(X,T,T)
@@ -353,6 +351,17 @@ int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int ev
     fprintf(stderr, "trace: init_iters=%d steps=%ld accepted=%d feasible-ending=%d\n", initIters, nSteps,
             s.stats.totalAccepted(), s.stats.nFeasibleSamples());
     return 0;
+}
+
+template <int G>
+int cmdTrace(const AbmpFile &f, int initSeed, int chainSeed, long nSteps, int every, const std::string &out) {
+    PredPreyProblem<G> problem = importProblem<G>(f);
+    Random::gen.seed(initSeed);
+    std::vector<occ_t> init = priorSample<G>(problem);
+    return traceSampler<PredPreyAgent<G>>(problem.tableau, problem.posterior.factors, problem.posterior.perturbableFunctionFactory(), init,
+                                          problem.kappa, problem.nTimesteps(),
+                                          [](const ModelState<PredPreyAgent<G>> &e) { return FiguresForPaper<G, 1>::synopsis(e); }, initSeed,
+                                          chainSeed, nSteps, every, out);
 }
 
 // Proves TracedSampler::step() == the unmodified operator(): two samplers, same seeds, one driven
@@ -880,6 +889,104 @@ static int cmdSingleObservationExperiment(const std::string &out, const std::str
     return 0;
 }
 
+// The reference's validation experiments on its OTHER agent types (Experiments.cpp:21-47, 70-125): BinomialAgent<3> with one noisy
+// observation (closed-form answer :32), CatMouseAgent with one observation, CatMouseAgent assimilation of a random trajectory
+// (checked against the exhaustive ExactSolver, :113-124).  Writes the problem as an ABMP file whose agent is described by tables
+// (flattenAgentImportance), together with the answers the experiment compares against -- end-state means of the reference's
+// RejectionSampler and, where the support is enumerable, the exact posterior over trajectories -- and a golden step trace of the
+// reference sampler started, as in the experiments, from the empty trajectory (SparseBasisSampler(posterior, kappa)).
+#include "agents/BinomialAgent.h"
+#include "agents/CatMouseAgent.h"
+#include "BernoulliStartState.h"
+#include "ExactSolver.h"
+template <class Agent>
+static int toyExperiment(Prior<Agent> &prior, Likelihood<Agent> &likelihood, int T, double kappa, int chainSeed, long nSteps,
+                         int every, long nRejection, const std::string &problemOut, const std::string &traceOut) {
+    auto posterior = likelihood * prior;
+    std::unique_ptr<TableauNormMinimiser<occ_t>> tableau;
+    {
+        SilenceStdout quiet;
+        tableau.reset(new TableauNormMinimiser<occ_t>(posterior.constraints));   // the constructor runs findMinimalBasis()
+    }
+    AbmpFile f;
+    abmcmc::flattenTableau<TableauNormMinimiser<occ_t>, occ_t>(f, *tableau, posterior.factors, kappa);
+    abmcmc::flattenAgentImportance<Agent>(f, T);
+    const int S = Agent::domainSize();
+    std::vector<double> rej(S, 0.0), exact(S, 0.0), exactP;
+    std::vector<int8_t> exactTraj;
+    if (nRejection > 0) {
+        RejectionSampler<Trajectory<Agent>> rejectionSampler(prior, likelihood);
+        for (long n = 0; n < nRejection; ++n) {
+            ModelState<Agent> endState(rejectionSampler(), T, T);
+            for (int k = 0; k < S; ++k) rej[k] += endState[k];
+        }
+        for (double &v : rej) v /= double(nRejection);
+    }
+    {
+        ExactSolver<Agent> solver(posterior);
+        for (const auto &tp : solver.pmf) {
+            ModelState<Agent> endState(tp.first, T, T);
+            for (int k = 0; k < S; ++k) exact[k] += tp.second * endState[k];
+            exactTraj.insert(exactTraj.end(), tp.first.begin(), tp.first.end());
+            exactP.push_back(tp.second);
+        }
+    }
+    f.f64["rejection_endstate_mean"] = rej;
+    f.f64["exact_endstate_mean"] = exact;      // over the binary trajectories ExactSolver enumerates (BinarySolutionSet)
+    f.i8["exact_traj"] = exactTraj;            // [n][nEvents]
+    f.f64["exact_p"] = exactP;
+    f.f64["counts"] = {double(nRejection)};
+    f.write(problemOut);
+    const auto &d = f.I("dims");
+    fprintf(stderr, "toy: tableau %d x %d, nNonBasic=%d nnz=%d, %d agent classes, %zu trajectories in the exact support\n", d[0], d[1], d[3],
+            d[4], f.I("ag_meta")[3], exactP.size());
+    return traceSampler<Agent>(*tableau, posterior.factors, posterior.perturbableFunctionFactory(), std::vector<occ_t>(), kappa, T,
+                               [](const ModelState<Agent> &) { return std::valarray<double>(); }, 0, chainSeed, nSteps, every, traceOut);
+}
+
+static int cmdToy(const std::string &kind, int seed, int chainSeed, long nSteps, int every, long nRejection, const std::string &problemOut,
+                  const std::string &traceOut) {
+    Random::gen.seed(seed);
+    if (kind == "binomial") {          // Experiments::BinomialAgentSingleObservation (:21-33)
+        constexpr int T = 2;
+        typedef BinomialAgent<T + 1> Agent;
+        Prior<Agent> prior(T, BernoulliStartState<Agent>({1.0, 0.1, 0.0}));
+        Likelihood<Agent> likelihood(AgentStateObservation<Agent>(State<Agent>(1, 0), 1, 0.9));
+        return toyExperiment<Agent>(prior, likelihood, T, 1.0, chainSeed, nSteps, every, nRejection, problemOut, traceOut);
+    }
+    if (kind == "catmouse") {          // Experiments::CatMouseSingleObservation (:36-46)
+        constexpr int T = 2;
+        typedef CatMouseAgent Agent;
+        Prior<Agent> prior(T, BernoulliStartState<Agent>({0.9, 0.1, 0.1, 0.9}));
+        Likelihood<Agent> likelihood(AgentStateObservation<Agent>(State<Agent>(1, Agent(Agent::CAT, Agent::LEFT)), 1, 1.0));
+        return toyExperiment<Agent>(prior, likelihood, T, 1.75, chainSeed, nSteps, every, nRejection, problemOut, traceOut);
+    }
+    if (kind == "catmouse-assim") {    // Experiments::CatMouseAssimilation (:70-125)
+        constexpr int T = 2;
+        typedef CatMouseAgent Agent;
+        Prior<Agent> prior(T, PoissonStartState<Agent>({0.5, 0.5, 0.3, 0.3}));
+        Trajectory<Agent> realTrajectory = prior.nextSample(true);
+        Likelihood<Agent> likelihood(realTrajectory, 0.2, 1.0);
+        return toyExperiment<Agent>(prior, likelihood, T, 1.25, chainSeed, nSteps, every, nRejection, problemOut, traceOut);
+    }
+    fprintf(stderr, "toy: unknown experiment %s\n", kind.c_str());
+    return 2;
+}
+
+// A PredPrey problem re-described as a table agent: pp_meta dropped, the ag_* tables of flattenAgentImportance<PredPreyAgent<G>>
+// (found by probing timestep()) in its place.  The oracle and the GPU library must produce the very same chain from either
+// description -- the check that the table path means what the geometry path means, with PredPrey's non-trivial log-ratios.
+template <int G>
+int cmdAsTable(AbmpFile f, const std::string &out) {
+    const int T = f.I("pp_meta")[1];
+    f.i32.erase("pp_meta");
+    f.f64.erase("pp_actpmf");
+    abmcmc::flattenAgentImportance<PredPreyAgent<G>>(f, T);
+    f.write(out);
+    fprintf(stderr, "astable: %d agent states, %d classes\n", f.I("ag_meta")[0], f.I("ag_meta")[3]);
+    return 0;
+}
+
 #define DISPATCH_G(G_, CALL)                                   \
     switch (G_) {                                              \
         case 3: { constexpr int G = 3; return CALL; }          \
@@ -905,7 +1012,9 @@ static int run(int argc, char **argv) {
                 "  abm_ref series in.abmp nThreads nSamples burnin out.abmp\n"
                 "  abm_ref posterior in.abmp nThreads nSamples burnin batch thin out.abmp [seedBase]\n"
                 "  abm_ref refstats series.abmp [splitHalves]\n"
-                "  abm_ref constraints in.abmp out.abmp [rebuild: 1 = also time the reference TableauNormMinimiser on them]\n");
+                "  abm_ref constraints in.abmp out.abmp [rebuild: 1 = also time the reference TableauNormMinimiser on them]\n"
+                "  abm_ref astable in.abmp out.abmp\n"
+                "  abm_ref toy binomial|catmouse|catmouse-assim seed chainSeed nSteps checkpointEvery nRejection problem.abmp trace.abmp\n");
         return 2;
     }
     std::string cmd = argv[1];
@@ -925,11 +1034,14 @@ static int run(int argc, char **argv) {
         const bool fastBasis = argc > 12 && std::string(argv[12]) == "fastbasis";
         DISPATCH_G(g, cmdGen<G>(T, seed, kappa, out, pPred, pPrey, pObs, pObsIf, startKind, fastBasis));
     }
+    if (cmd == "toy")   // toy binomial|catmouse|catmouse-assim seed chainSeed nSteps checkpointEvery nRejection problem.abmp trace.abmp
+        return cmdToy(argv[2], atoi(argv[3]), atoi(argv[4]), atol(argv[5]), atoi(argv[6]), atol(argv[7]), argv[8], argv[9]);
     if (cmd == "experiment3")   // experiment3 problem.abmp marginals.abmp nSamples nBurnin nRejection seed
         return cmdSingleObservationExperiment(argv[2], argv[3], atol(argv[4]), atol(argv[5]), atol(argv[6]), atoi(argv[7]));
     AbmpFile f = AbmpFile::read(argv[2]);
     if (cmd == "refstats") return cmdRefStats(f, argc > 3 ? atoi(argv[3]) : 0);   // refstats series.abmp [split each sequence in halves]
     int g = f.I("pp_meta")[0];
+    if (cmd == "astable") { DISPATCH_G(g, cmdAsTable<G>(f, argv[3])); }   // astable in.abmp out.abmp
     if (cmd == "init") { DISPATCH_G(g, cmdInit<G>(f, atoi(argv[3]), atoi(argv[4]), argv[5])); }
     if (cmd == "trace") { DISPATCH_G(g, cmdTrace<G>(f, atoi(argv[3]), atoi(argv[4]), atol(argv[5]), atoi(argv[6]), argv[7])); }
     if (cmd == "selfcheck") { DISPATCH_G(g, cmdSelfcheck<G>(f, atoi(argv[3]))); }

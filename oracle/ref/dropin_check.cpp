@@ -1,5 +1,5 @@
-// dropin_check: the reference's own host code (PredPreyProblem, TableauNormMinimiser, factor closures,
-// TrajectoryImportance) drives the GPU sampler through the reference constructor signature, side by side with the
+// dropin_check: the reference's own host code (PredPreyProblem / Prior * Likelihood, TableauNormMinimiser, factor closures,
+// TrajectoryImportance<AGENT>) drives the GPU sampler through the reference constructor signature, side by side with the
 // unmodified reference SparseBasisSampler on the same Random::gen stream; every returned sample must be identical.
 // TEST INFRASTRUCTURE (built by `make -C oracle dropin` into oracle/_ref/, run by tests/test_gpu_dropin.py).
 #include <boost/serialization/access.hpp>
@@ -8,6 +8,8 @@
 #include "Likelihood.h"
 #include "PredPreyProblem.h"
 #include "SparseBasisSampler.h"
+#include "agents/BinomialAgent.h"   // before gpu_sampler.hpp: the adaptor offers the agent types whose headers it can see
+#include "agents/CatMouseAgent.h"
 
 #include "abmcmc_b200/gpu_sampler.hpp"
 #include <cmath>
@@ -105,19 +107,20 @@ int run(int T, int nSamples) {
     return 0;
 }
 
-// The reference's validation experiment for this path (Experiments::PredPreySingleObservation, Experiments.cpp:49-65, body
-// of doSingleObservationExperiment, :129-168) with the GPU sampler constructed exactly as the experiment constructs the
-// reference one -- `sampler(posterior, kappa)`, empty initial trajectory -- next to the unmodified sampler on the same
-// Random::gen stream: burn-in, then nSamples samples summed into a ModelState; samples and aggregate must be identical.
+// The reference's validation experiments for this path (Experiments.cpp:21-125; body of doSingleObservationExperiment, :129-168)
+// with the GPU sampler constructed exactly as the experiments construct the reference one -- `sampler(posterior, kappa)`, empty
+// initial trajectory -- next to the unmodified sampler on the same Random::gen stream: burn-in, then nSamples samples summed
+// into a ModelState; samples and aggregate must be identical.  Then, as the experiments do, the answer is checked against an
+// independent solver: the batched GPU chains' end-state means against the exhaustive ExactSolver where the support is
+// enumerable (the agents other than PredPrey).
 #include "PoissonStartState.h"
+#include "BernoulliStartState.h"
 #include "ModelState.h"
-int runExperiment(int nSamples) {
-    constexpr int GRIDSIZE = 3, nTimesteps = 2, nBurnin = 1000;
-    constexpr double pPredator = 0.1, pPrey = 2.0 * pPredator, kappa = 3.0;
-    typedef PredPreyAgent<GRIDSIZE> AGENT;
+#include "ExactSolver.h"
+template <class AGENT>
+int runExperiment(const char *name, Prior<AGENT> &prior, Likelihood<AGENT> &likelihood, int nTimesteps, double kappa, int nBurnin, int nSamples,
+                  bool exactCheck) {
     std::streambuf *old = std::cout.rdbuf(nullptr);
-    Prior<AGENT> prior(nTimesteps, PoissonStartState<AGENT>([](AGENT agent) { return agent.type() == AGENT::PREDATOR ? pPredator : pPrey; }));
-    Likelihood<AGENT> likelihood(AgentStateObservation<AGENT>(State<AGENT>(1, AGENT(1, 1, AGENT::PREY)), 1, 1.0));
     auto posterior = likelihood * prior;
     Random::gen.seed(2021);
     SparseBasisSampler<ABM::occupation_type> ref(posterior, kappa);
@@ -142,13 +145,76 @@ int runExperiment(int nSamples) {
             aggGpu += ModelState<AGENT>(b, nTimesteps, nTimesteps);
         }
     }
-    for (int i = 0; i < AGENT::domainSize(); ++i)
+    const int S = AGENT::domainSize();
+    for (int i = 0; i < S; ++i)
         if (aggRef[i] != aggGpu[i]) { printf("FAIL: aggregate state differs\n"); return 1; }
-    double total = 0.0;
-    for (int i = 0; i < AGENT::domainSize(); ++i) total += aggGpu[i];
-    printf("OK: PredPreySingleObservation: %d samples identical to the reference SparseBasisSampler (%d Metropolis steps), mean agents at T = %.4f\n",
-           nSamples, ref.stats.nSamples(), total / nSamples);
+    bool statsEqual = true;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+            statsEqual = statsEqual && ref.stats.nProposals[a][b] == gpu.stats.nProposals[a][b] && ref.stats.nAccepted[a][b] == gpu.stats.nAccepted[a][b];
+    if (!statsEqual) { printf("FAIL: MCMCStatistics differ\n"); return 1; }
+    double total = 0.0, worst = 0.0;
+    for (int i = 0; i < S; ++i) total += aggGpu[i];
+    if (exactCheck) {
+        // p(exact) against p(mcmc) as Experiments.cpp:113-124 prints them, on the end-state means, with the MCMC side run as
+        // 512 batched chains x 4000 samples on the device
+        std::vector<double> exact(S, 0.0);
+        ExactSolver<AGENT> solver(posterior);
+        for (const auto &tp : solver.pmf) {
+            ModelState<AGENT> endState(tp.first, nTimesteps, nTimesteps);
+            for (int i = 0; i < S; ++i) exact[i] += tp.second * endState[i];
+        }
+        const int nChains = 512, perChain = 4000;
+        gpu.batched(nChains, 4242);
+        gpu.step(2000);
+        abmcmc::detail::check(abm_chains_reset_statistics(gpu.chains()), "reset_statistics");
+        gpu.sample(perChain);
+        std::vector<int64_t> end(S), ns(nChains);
+        abmcmc::detail::check(abm_chains_get_statistics(gpu.chains(), end.data(), nullptr, nullptr, ns.data(), 0), "get_statistics");
+        int64_t n = 0;
+        for (int64_t v : ns) n += v;
+        if (n != int64_t(nChains) * perChain) { printf("FAIL: %lld samples instead of %lld\n", (long long)n, (long long)nChains * perChain); return 1; }
+        for (int i = 0; i < S; ++i) worst = std::max(worst, std::fabs(double(end[i]) / double(n) - exact[i]));
+        if (worst > 4e-3) { printf("FAIL: batched end-state means are %.5f away from the exact solver\n", worst); return 1; }
+    }
+    printf("OK: %s: %d samples identical to the reference SparseBasisSampler (%d Metropolis steps), mean agents at T = %.4f", name, nSamples,
+           ref.stats.nSamples(), total / nSamples);
+    if (exactCheck) printf("; 2 048 000 batched samples within %.5f of the exact end-state means", worst);
+    printf("\n");
     return 0;
+}
+
+int runNamedExperiment(const std::string &which, int nSamples) {
+    constexpr int T = 2;
+    if (which == "predprey") {            // Experiments::PredPreySingleObservation (:49-65)
+        typedef PredPreyAgent<3> AGENT;
+        constexpr double pPredator = 0.1, pPrey = 2.0 * pPredator;
+        Prior<AGENT> prior(T, PoissonStartState<AGENT>([](AGENT agent) { return agent.type() == AGENT::PREDATOR ? pPredator : pPrey; }));
+        Likelihood<AGENT> likelihood(AgentStateObservation<AGENT>(State<AGENT>(1, AGENT(1, 1, AGENT::PREY)), 1, 1.0));
+        return runExperiment<AGENT>("PredPreySingleObservation", prior, likelihood, T, 3.0, 1000, nSamples, false);
+    }
+    if (which == "binomial") {            // Experiments::BinomialAgentSingleObservation (:21-33): a noisy observation (p = 0.9)
+        typedef BinomialAgent<T + 1> AGENT;
+        Prior<AGENT> prior(T, BernoulliStartState<AGENT>({1.0, 0.1, 0.0}));
+        Likelihood<AGENT> likelihood(AgentStateObservation<AGENT>(State<AGENT>(1, 0), 1, 0.9));
+        return runExperiment<AGENT>("BinomialAgentSingleObservation", prior, likelihood, T, 1.0, 100, nSamples, true);
+    }
+    if (which == "catmouse") {            // Experiments::CatMouseSingleObservation (:36-46)
+        typedef CatMouseAgent AGENT;
+        Prior<AGENT> prior(T, BernoulliStartState<AGENT>({0.9, 0.1, 0.1, 0.9}));
+        Likelihood<AGENT> likelihood(AgentStateObservation<AGENT>(State<AGENT>(1, AGENT(AGENT::CAT, AGENT::LEFT)), 1, 1.0));
+        return runExperiment<AGENT>("CatMouseSingleObservation", prior, likelihood, T, 1.75, 100, nSamples, true);
+    }
+    if (which == "catmouse-assim") {      // Experiments::CatMouseAssimilation (:70-125)
+        typedef CatMouseAgent AGENT;
+        Random::gen.seed(1234);
+        Prior<AGENT> prior(T, PoissonStartState<AGENT>({0.5, 0.5, 0.3, 0.3}));
+        Trajectory<AGENT> realTrajectory = prior.nextSample(true);
+        Likelihood<AGENT> likelihood(realTrajectory, 0.2, 1.0);
+        return runExperiment<AGENT>("CatMouseAssimilation", prior, likelihood, T, 1.25, 100, nSamples, true);
+    }
+    printf("unknown experiment\n");
+    return 2;
 }
 
 // Multi-GPU ensemble reduction from a C++ host: `dropin_check moments <rank> <nRanks> <idFile>
@@ -211,10 +277,14 @@ int main(int argc, char **argv) {
         try { return runMoments(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]); }
         catch (const std::exception &e) { printf("FAIL: %s\n", e.what()); return 1; }
     }
+    if (argc > 3 && std::string(argv[1]) == "experiment") {   // experiment predprey|binomial|catmouse|catmouse-assim nSamples
+        try { return runNamedExperiment(argv[2], atoi(argv[3])); }
+        catch (const std::exception &e) { printf("FAIL: %s\n", e.what()); return 1; }
+    }
     int g = argc > 1 ? atoi(argv[1]) : 8, T = argc > 2 ? atoi(argv[2]) : 4, n = argc > 3 ? atoi(argv[3]) : 300;
     if (argc > 4) abmcmc::GpuSparseBasisSampler<ABM::occupation_type>::feasibilityBlock() = atol(argv[4]);
     try {
-        if (g == 3) return runExperiment(n);
+        if (g == 3) return runNamedExperiment("predprey", n);
         if (g == 8) return run<8>(T, n);
         if (g == 16) return run<16>(T, n);
         printf("unsupported grid\n");

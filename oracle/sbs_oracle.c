@@ -86,11 +86,26 @@ typedef struct {
     int *facLo, *facOff;           /* per row: table domain start, offset into facVal            */
     double *facVal;
     double kappa;
-    /* PredPrey importance (TrajectoryImportance<PredPreyAgent<G>>); G==0 -> no importance       */
+    /* importance TrajectoryImportance<AGENT>; S==0 -> no importance.  The agent -- PredPreyAgent<G> (G>0, tables filled from
+     * its geometry below) or any other agent type (orc_problem_set_agent) -- is four tables of its own functions:
+     * class of a state, the states its timestep() reads (influencers), neighbours(), consequences(act)            */
     int G, T, S, A;
     double lgammaTab[8];
-    double logRatio[2][2][6];
+    int nCls, *agCls, *agInfl, *agNbPtr, *agNb, *agCqPtr, *agCq;
+    double *ratio;                 /* [nCls][2][A] log(pmf/marginal) by class, "any influencer occupied", act       */
 } OrcProblem;
+
+static void agentTablesAlloc(OrcProblem *p, int nNb, int nCq) {
+    int S = p->S, A = p->A;
+    p->agCls = (int *)calloc((size_t)S, sizeof(int));
+    p->agInfl = (int *)malloc(sizeof(int) * 4 * (size_t)S);
+    p->agNbPtr = (int *)calloc((size_t)S + 1, sizeof(int));
+    p->agNb = (int *)malloc(sizeof(int) * (size_t)(nNb + 1));
+    p->agCqPtr = (int *)calloc((size_t)S * A + 1, sizeof(int));
+    p->agCq = (int *)malloc(sizeof(int) * (size_t)(nCq + 1));
+    p->ratio = (double *)calloc((size_t)p->nCls * 2 * A, sizeof(double));
+    for (int k = 0; k < 4 * S; ++k) p->agInfl[k] = -1;
+}
 
 ORC_API OrcProblem *orc_problem_create(int nTabRows, int nNonBasic, const int32_t *tabL, const int32_t *tabU,
                                        const int32_t *tabF, const int32_t *nbCol, const int32_t *nbPtr,
@@ -158,16 +173,58 @@ ORC_API OrcProblem *orc_problem_create(int nTabRows, int nNonBasic, const int32_
     p->S = 2 * G * G;
     p->nEvents = T * p->S * p->A;
     if (G > 0) {
+        int GG = G * G, A = p->A;
         memcpy(p->lgammaTab, lgammaTab, sizeof(double) * 7);
-        memcpy(p->logRatio, logRatio, sizeof(double) * 24);
+        p->nCls = 2; /* PREDATOR, PREY */
+        agentTablesAlloc(p, 4 * p->S, 7 * p->S);
+        memcpy(p->ratio, logRatio, sizeof(double) * 24);
+        int nNb = 0, nCq = 0;
+        for (int psi = 0; psi < p->S; ++psi) {
+            int x = psi % G, y = (psi / G) % G, type = psi / GG, other = (1 - type) * GG, own = type * GG;
+            int xl = (x + G - 1) % G, xr = (x + 1) % G, yu = (y + 1) % G, yd = (y + G - 1) % G;
+            p->agCls[psi] = type;
+            /* PredPreyAgent.h:199-207 neighbours(): left, right, up, down of the other species; the same four cells are what
+             * timestep() reads through surroundingCountOf (:86-91 with xLeft..yDown :65-68) */
+            int nb4[4] = {other + xl + G * y, other + xr + G * y, other + x + G * yu, other + x + G * yd};
+            for (int k = 0; k < 4; ++k) { p->agInfl[4 * psi + k] = nb4[k]; p->agNb[nNb++] = nb4[k]; }
+            p->agNbPtr[psi + 1] = nNb;
+            /* PredPreyAgent.h:98-115 consequences(): DIE nothing, the four moves, GIVEBIRTH parent stays + child to the right */
+            for (int a = 0; a < A; ++a) {
+                if (a == 1) p->agCq[nCq++] = own + xl + G * y;
+                else if (a == 2) p->agCq[nCq++] = own + xr + G * y;
+                else if (a == 3) p->agCq[nCq++] = own + x + G * yu;
+                else if (a == 4) p->agCq[nCq++] = own + x + G * yd;
+                else if (a == 5) { p->agCq[nCq++] = own + x + G * y; p->agCq[nCq++] = own + xr + G * y; }
+                p->agCqPtr[psi * A + a + 1] = nCq;
+            }
+        }
     }
     return p;
+}
+
+/* An agent type other than PredPrey, by tables (include/abmcmc_b200/reference_flatten.hpp flattenAgentImportance fills them
+ * from the agent's own timestep / marginalTimestep / neighbours / consequences); call on a problem created with G == 0. */
+ORC_API void orc_problem_set_agent(OrcProblem *p, int S, int A, int T, int nCls, const int32_t *cls, const int32_t *infl,
+                                   const int32_t *nbPtr, const int32_t *nb, const int32_t *cqPtr, const int32_t *cq,
+                                   const double *lgammaTab, const double *logRatio) {
+    p->G = 0; p->S = S; p->A = A; p->T = T; p->nCls = nCls;
+    p->nEvents = T * S * A;
+    memcpy(p->lgammaTab, lgammaTab, sizeof(double) * 7);
+    agentTablesAlloc(p, nbPtr[S], cqPtr[S * A]);
+    for (int k = 0; k < S; ++k) p->agCls[k] = cls[k];
+    for (int k = 0; k < 4 * S; ++k) p->agInfl[k] = infl[k];
+    for (int k = 0; k <= S; ++k) p->agNbPtr[k] = nbPtr[k];
+    for (int k = 0; k < nbPtr[S]; ++k) p->agNb[k] = nb[k];
+    for (int k = 0; k <= S * A; ++k) p->agCqPtr[k] = cqPtr[k];
+    for (int k = 0; k < cqPtr[S * A]; ++k) p->agCq[k] = cq[k];
+    memcpy(p->ratio, logRatio, sizeof(double) * (size_t)nCls * 2 * A);
 }
 
 ORC_API void orc_problem_destroy(OrcProblem *p) {
     if (!p) return;
     free(p->colPtr); free(p->colIdx); free(p->colVal); free(p->rowPtr); free(p->rowIdx); free(p->rowVal);
     free(p->L); free(p->U); free(p->F); free(p->colEvent); free(p->facLo); free(p->facOff); free(p->facVal);
+    free(p->agCls); free(p->agInfl); free(p->agNbPtr); free(p->agNb); free(p->agCqPtr); free(p->agCq); free(p->ratio);
     free(p);
 }
 
@@ -309,15 +366,17 @@ static int tree_sample(OrcChain *c, double u) {
     return index;
 }
 
-/* --- PredPrey importance ------------------------------------------------------------------ */
-/* PredPreyAgent.h:86-91 with xLeft..yDown (:65-68): opposite-species occupation of the 4 neighbours */
-static int hasOppositeNeighbour(const OrcChain *c, int t, int psi) {
+/* --- trajectory importance ------------------------------------------------------------------ */
+/* what timestep() of (t, psi) reads of the other agents: is any of its influencer states occupied -- for PredPrey the
+ * opposite-species occupation of the 4 neighbours, PredPreyAgent.h:86-91 with xLeft..yDown (:65-68); for CatMouse the cat at
+ * the mouse's position, CatMouseAgent.cpp:14 */
+static int anyInfluencerOccupied(const OrcChain *c, int t, int psi) {
     const OrcProblem *p = c->p;
-    int G = p->G, GG = G * G;
-    int x = psi % G, y = (psi / G) % G, type = psi / GG, other = 1 - type;
-    const int *occ = c->occ + t * p->S + other * GG;
-    int cnt = occ[(x + 1) % G + G * y] + occ[(x + G - 1) % G + G * y] + occ[x + G * ((y + 1) % G)] +
-              occ[x + G * ((y + G - 1) % G)];
+    int cnt = 0;
+    for (int k = 0; k < 4; ++k) {
+        int q = p->agInfl[4 * psi + k];
+        if (q >= 0) cnt += c->occ[t * p->S + q];
+    }
     return cnt >= 1;
 }
 /* the newLogP computation shared by refresh (:96-108) and setState (:125-134) */
@@ -327,9 +386,10 @@ static double factorLogP(const OrcChain *c, int sid) {
     int occ = c->occ[sid];
     double logP = (occ > 1) ? p->lgammaTab[occ] : 0.0;
     if (occ > 0) {
-        int type = psi / (p->G * p->G), flag = hasOppositeNeighbour(c, t, psi);
+        int flag = anyInfluencerOccupied(c, t, psi);
+        const double *row = p->ratio + (size_t)(p->agCls[psi] * 2 + flag) * p->A;
         for (int a = 0; a < p->A; ++a)
-            if (c->X[sid * p->A + a] > 0) logP += p->logRatio[type][flag][a]; /* 0.0 where pmf[a]==0 */
+            if (c->X[sid * p->A + a] > 0) logP += row[a]; /* 0.0 where pmf[a]==0 */
     }
     return logP;
 }
@@ -355,10 +415,9 @@ static void imp_insertFactor(OrcChain *c, int sid) { /* IndexSet.h:28-35 + :46,4
  * duplicates and is not restated) */
 static void imp_perturb(OrcChain *c, const int *idx, int n) {
     const OrcProblem *p = c->p;
-    if (p->G == 0) return;
+    if (p->S == 0) return;
     imp_clearUndo(c);
     c->totalUndo = c->totalLogP;
-    int G = p->G, GG = G * G;
     for (int k = 0; k < n; ++k) {
         int i = idx[k];
         if (i < p->nEvents) {
@@ -370,12 +429,8 @@ static void imp_perturb(OrcChain *c, const int *idx, int n) {
             }
             imp_insertFactor(c, sid);
             int t = sid / p->S, psi = sid % p->S;
-            int x = psi % G, y = (psi / G) % G, other = 1 - psi / GG;
-            int base = t * p->S + other * GG; /* PredPreyAgent.h:199-207: left, right, up, down */
-            imp_insertFactor(c, base + (x + G - 1) % G + G * y);
-            imp_insertFactor(c, base + (x + 1) % G + G * y);
-            imp_insertFactor(c, base + x + G * ((y + 1) % G));
-            imp_insertFactor(c, base + x + G * ((y + G - 1) % G));
+            for (int q = p->agNbPtr[psi]; q < p->agNbPtr[psi + 1]; ++q) /* agent().neighbours(), :48-51 */
+                imp_insertFactor(c, t * p->S + p->agNb[q]);
         }
     }
 }
@@ -391,7 +446,7 @@ static void imp_refresh(OrcChain *c) {
 }
 /* TrajectoryImportance.h:69-79 */
 static void imp_undo(OrcChain *c) {
-    if (c->p->G == 0) return;
+    if (c->p->S == 0) return;
     for (int k = 0; k < c->nStaleStates; ++k) c->occ[c->staleStates[k]] = c->occUndo[k];
     for (int k = 0; k < c->nStaleFactors; ++k) c->facLogP[c->staleFactors[k]] = c->facUndo[k];
     c->totalLogP = c->totalUndo;
@@ -400,7 +455,7 @@ static void imp_undo(OrcChain *c) {
 /* TrajectoryImportance.h:116-140 */
 static void imp_setState(OrcChain *c) {
     const OrcProblem *p = c->p;
-    if (p->G == 0) { c->totalLogP = 0.0; return; }
+    if (p->S == 0) { c->totalLogP = 0.0; return; }
     c->totalLogP = 0.0;
     for (int t = 0; t < p->T; ++t) {
         for (int a = 0; a < p->S; ++a) c->occ[t * p->S + a] = fermionicOcc(c, t * p->S + a);
@@ -415,7 +470,7 @@ static void imp_setState(OrcChain *c) {
     imp_clearUndo(c);
 }
 static double imp_getLogValue(OrcChain *c) { /* :82-85 */
-    if (c->p->G == 0) return 0.0;
+    if (c->p->S == 0) return 0.0;
     imp_refresh(c);
     return c->totalLogP;
 }
@@ -436,7 +491,7 @@ ORC_API OrcChain *orc_chain_create(const OrcProblem *p, const int8_t *initState,
     c->newDE = (double *)malloc(sizeof(double) * nC);
     c->newX = (int *)malloc(sizeof(int) * nR);
     for (int j = 0; j < nC; ++j) c->slot[j] = -1;
-    int nStates = p->G > 0 ? p->T * p->S : 1;
+    int nStates = p->S > 0 ? p->T * p->S : 1;
     c->occ = (int *)calloc(nStates, sizeof(int));
     c->facLogP = (double *)calloc(nStates, sizeof(double));
     c->staleStates = (int *)malloc(sizeof(int) * nStates);
@@ -657,24 +712,15 @@ ORC_API uint64_t orc_chain_hash_X(const OrcChain *c) {
     for (int i = 0; i < c->p->nRows; ++i) h += (uint64_t)(int64_t)c->X[i] * mix64((uint64_t)i);
     return h;
 }
-/* End-state occupancy ModelState(traj,T,T) (ModelState.h:27-36; State.h:57-63 with the PredPrey
- * consequences() PredPreyAgent.h:98-115): out[psi] = sum of incoming events at t = T-1. */
+/* End-state occupancy ModelState(traj,T,T) (ModelState.h:27-36; State.h:57-63 over the agent's consequences(), e.g.
+ * PredPreyAgent.h:98-115): out[psi] = sum of incoming events at t = T-1. */
 ORC_API void orc_chain_end_state(const OrcChain *c, int32_t *out) {
     const OrcProblem *p = c->p;
-    int G = p->G, GG = G * G, S = p->S, A = p->A;
+    int S = p->S, A = p->A;
     for (int k = 0; k < S; ++k) out[k] = 0;
     const int *Xt = c->X + (p->T - 1) * S * A;
-    for (int psi = 0; psi < S; ++psi) {
-        int x = psi % G, y = (psi / G) % G, base = (psi / GG) * GG;
-        int left = base + (x + G - 1) % G + G * y, right = base + (x + 1) % G + G * y;
-        int up = base + x + G * ((y + 1) % G), down = base + x + G * ((y + G - 1) % G);
-        out[left] += Xt[psi * A + 1];
-        out[right] += Xt[psi * A + 2];
-        out[up] += Xt[psi * A + 3];
-        out[down] += Xt[psi * A + 4];
-        out[psi] += Xt[psi * A + 5];   /* GIVEBIRTH: parent stays ... */
-        out[right] += Xt[psi * A + 5]; /* ... and the child appears to the right */
-    }
+    for (int e = 0; e < S * A; ++e)
+        for (int q = p->agCqPtr[e]; q < p->agCqPtr[e + 1]; ++q) out[p->agCq[q]] += Xt[e];
 }
 /* The reference's per-sample statistics (FiguresForPaper.h:93-104): for every feasible sample, the end state
  * ModelState(traj,T,T) is summed (Dataflow Sum) and the synopsis (FiguresForPaper.h:245-263: agents inside nested

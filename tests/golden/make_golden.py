@@ -2,7 +2,7 @@
 """Regenerates the golden fixtures in this directory from the UNMODIFIED reference.
 
 Needs /root/reference (read-only) and a host compiler; run from the repository root:
-    make -C oracle ref && python tests/golden/make_golden.py [--with-32] [--with-sweep]
+    make -C oracle ref && python tests/golden/make_golden.py [--with-32] [--with-sweep] [--traces-only | --agents-only]
 --with-32 adds the paper-scale problem (32x32, T = 16; ~4 minutes of TableauNormMinimiser), --with-sweep the window sweep's
 problems (32x32, T = 4, 8, 32; T = 32 at density 0.02 because the reference cannot draw an act-Fermionic real trajectory of
 32 steps at 0.05, Forecast.h:145-147; ~20 minutes).
@@ -42,9 +42,34 @@ def traces_only():
         xz(out, HERE / f"trace_{name}_{s1}.abmp.xz")
 
 
+# The reference's validation experiments on its other agent types (Experiments.cpp:21-47, 70-125) -- `abm_ref toy`: problem
+# (agent described by tables), the rejection sampler's end-state means over 2e6 samples, the exact posterior over trajectories,
+# and a golden step trace of 20000 steps -- and PredPrey problems re-described as table agents (`abm_ref astable`), which the
+# existing PredPrey traces must keep matching.
+TOYS = [("binomial", 1234, 401), ("catmouse", 1234, 402), ("catmouse-assim", 1234, 403)]
+AS_TABLE = ["pp8-4", "exp_pp3-2-single"]
+
+
+def agents_only():
+    tmp = Path(tempfile.mkdtemp())
+    for kind, seed, chain_seed in TOYS:
+        prob, trace = tmp / f"toy_{kind}.abmp", tmp / f"trace_toy_{kind}_{chain_seed}.abmp"
+        subprocess.run([str(REF), "toy", kind, str(seed), str(chain_seed), "20000", "500", "2000000", str(prob), str(trace)], check=True)
+        xz(prob, HERE / prob.with_suffix(".abmp.xz").name)
+        xz(trace, HERE / trace.with_suffix(".abmp.xz").name)
+    for name in AS_TABLE:
+        raw = tmp / f"{name}.abmp"
+        raw.write_bytes(lzma.decompress((HERE / f"{name}.abmp.xz").read_bytes()))
+        out = tmp / f"{name}-astable.abmp"
+        subprocess.run([str(REF), "astable", str(raw), str(out)], check=True)
+        xz(out, HERE / f"{name}-astable.abmp.xz")
+
+
 def main():
     if "--traces-only" in sys.argv:
         return traces_only()
+    if "--agents-only" in sys.argv:
+        return agents_only()
     with32 = "--with-32" in sys.argv
     tmp = Path(tempfile.mkdtemp())
     problems = [(8, 4), (16, 8)] + ([(32, 16)] if with32 else [])
@@ -106,6 +131,7 @@ def main():
     raw = tmp / "marginals_pp8-4.abmp"
     subprocess.run([str(REF), "marginals", str(tmp / "pp8-4.abmp"), "64", "60000", "60000", str(raw)], check=True)
     xz(raw, HERE / "marginals_pp8-4.abmp.xz")
+    agents_only()
 
 
 if __name__ == "__main__":

@@ -25,6 +25,20 @@ def test_cpp_dropin_matches_reference_sample_for_sample(grid, T, n, block):
     assert out.stdout.strip().startswith("OK:")
 
 
+@pytest.mark.parametrize("which,n", [("binomial", 3000), ("catmouse", 3000), ("catmouse-assim", 3000), ("predprey", 2000)])
+def test_cpp_reference_experiments_sample_for_sample(which, n):
+    """The reference's four validation experiments for this path (Experiments.cpp:21-125) with the GPU sampler constructed as
+    they construct the reference one -- `sampler(posterior, kappa)` from Prior * Likelihood of BinomialAgent<3> (noisy
+    observation), CatMouseAgent (single observation; assimilation of a random trajectory) and PredPreyAgent<3>: every sample equal
+    to the unmodified sampler's on the same Random::gen stream, and, for the enumerable ones, 512 batched device chains within
+    4e-3 of the ExactSolver's end-state means (what Experiments.cpp:113-124 compares)."""
+    if not EXE.exists():
+        pytest.skip("oracle/_ref/dropin_check not built (needs /root/reference at build time)")
+    out = subprocess.run([str(EXE), "experiment", which, str(n)], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip().startswith("OK:")
+
+
 def _run_moment_ranks(n_ranks, tmp_path):
     import numpy as np
     procs = [subprocess.Popen([str(EXE), "moments", str(r), str(n_ranks), str(tmp_path / "nccl.id"), str(tmp_path / "mom")],

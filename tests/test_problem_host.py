@@ -114,3 +114,21 @@ def test_malformed_descriptors_are_rejected_not_dereferenced():
     assert status(lambda d, k: k["nb_ptr"].__setitem__(5, int(k["nb_ptr"][4]) - 1)) == -1
     assert status(lambda d, k: k["ut_off"].__setitem__(1, 0)) == -1
     assert L.abm_problem_validate(None, None) == -1
+
+
+def test_table_agent_descriptor_is_validated():
+    """Agents described by tables (abm_problem_desc::agent_*): the reference's toy experiments validate, malformed tables are
+    refused on the host."""
+    S = _S()
+    p = dict(load_golden("toy_catmouse.abmp.xz"))
+    info = S.validate_problem(p)
+    assert info.n_states == 8 and info.n_events == 16   # T = 2, CatMouseAgent: 4 agent states x 2 acts
+    for name in ("toy_binomial", "toy_catmouse-assim", "pp8-4-astable", "exp_pp3-2-single-astable"):
+        S.validate_problem(load_golden(f"{name}.abmp.xz"))
+    for key, bad in (("ag_class", np.array([0, 0, 0, 7], np.int32)), ("ag_infl", np.full(16, 9, np.int32)),
+                     ("ag_nb", np.array([2, 40], np.int32)), ("ag_cq", np.full(8, -3, np.int32)),
+                     ("ag_nb_ptr", np.array([0, 2, 1, 2, 2], np.int32)), ("ag_meta", np.array([4, 9, 2, 1], np.int32))):
+        q = dict(p)
+        q[key] = bad
+        with pytest.raises(S.AbmError):
+            S.validate_problem(q)
