@@ -84,3 +84,77 @@ def test_table_agent_posterior_matches_exact_solver(name):
     freq = counts / n_chains
     sigma = np.sqrt(prob * (1 - prob) / n_chains)
     assert np.all(np.abs(freq - prob) < 5 * sigma + 2e-3)
+
+
+def _random_table_agent(p, rng, n_acts):
+    """The tableau of a PredPrey problem with a RANDOM agent description laid over its events: S' x n_acts acts per timestep
+    (same event count), random classes, 0..4 influencers per state, neighbours() = the states a state influences plus random
+    extras in random order, random consequences, random log-ratio rows.  Not a model of anything -- a differential input for
+    the table path (oracle/sbs_oracle.c against the kernels)."""
+    q = {k: v for k, v in p.items() if k not in ("pp_meta", "pp_actpmf", "pp_params")}
+    G, T, n_events = (int(v) for v in p["pp_meta"][:3])
+    S = n_events // (T * n_acts)
+    assert S * T * n_acts == n_events
+    n_cls = 5
+    infl = np.full((S, 4), -1, np.int32)
+    nb = [[] for _ in range(S)]
+    for s in range(S):
+        k = int(rng.integers(0, 5))
+        cand = rng.choice(S, size=k, replace=False) if k else []
+        infl[s, :k] = cand
+        for c in cand:
+            nb[int(c)].append(s)
+    for s in range(S):
+        extra = rng.choice(S, size=int(rng.integers(0, 3)), replace=False).tolist()
+        lst = list(dict.fromkeys(nb[s] + extra))
+        rng.shuffle(lst)
+        nb[s] = lst
+    cq = [rng.choice(S, size=int(rng.integers(0, 3)), replace=False).tolist() for _ in range(S * n_acts)]
+    q["ag_meta"] = np.array([S, n_acts, T, n_cls], np.int32)
+    q["ag_class"] = rng.integers(0, n_cls, S).astype(np.int32)
+    q["ag_infl"] = infl.ravel()
+    q["ag_nb_ptr"] = np.concatenate([[0], np.cumsum([len(v) for v in nb])]).astype(np.int32)
+    q["ag_nb"] = np.array([x for v in nb for x in v], np.int32)
+    q["ag_cq_ptr"] = np.concatenate([[0], np.cumsum([len(v) for v in cq])]).astype(np.int32)
+    q["ag_cq"] = np.array([x for v in cq for x in v], np.int32)
+    q["imp_lgamma"] = np.array([0.0, 0.0] + [float(np.log(np.arange(1, k + 1)).sum()) for k in range(2, 7)])
+    q["imp_logratio"] = rng.normal(0.0, 0.4, n_cls * 2 * n_acts) * (rng.random(n_cls * 2 * n_acts) < 0.8)
+    return q
+
+
+@pytest.mark.parametrize("tree", ["blocked", "reference"])
+@pytest.mark.parametrize("n_acts,seed", [(6, 1), (4, 2), (3, 3), (2, 4), (1, 5)])
+def test_random_table_agents_match_oracle(n_acts, seed, tree):
+    """Differential run of the table path on inputs no agent of the reference produces: 1..6 acts, 0..4 influencers, several
+    classes, non-trivial log-ratios, asymmetric neighbour lists.  Device chains against the oracle's chains on the same Philox
+    streams (decisions, states, log importance), then the sampling statistics (end-state sums over the feasible states)."""
+    from oracle.oracle import OracleChain, OracleProblem
+    S = _gpu()
+    rng = np.random.default_rng(100 + seed)
+    p = _random_table_agent(load_golden("pp8-4.abmp.xz"), rng, n_acts)
+    n_chains, n_steps, key = 6, 2500, 0xA6E27 + seed
+    P = S.Problem(p, sum_tree=tree)
+    init = (rng.random((n_chains, P.n_events)) < 0.02).astype(np.int8)
+    smp = S.SparseBasisSampler(P, init, seed=key)
+    OP = OracleProblem(p)
+    j, acc, pinf = smp.step_traced(n_steps)
+    chains = []
+    for c in range(n_chains):
+        oc = OracleChain(OP, init[c])
+        oc.seed_philox(key, c)
+        assert oc.find_feasible() == int(smp.init_iterations[c])
+        oj, oacc, oinf = oc.step(n_steps, trace=True)
+        assert np.array_equal(j[c], oj) and np.array_equal(acc[c], oacc) and np.array_equal(pinf[c], oinf)
+        X, delta, DE, tr, logimp, inf = smp.state(c)
+        assert np.array_equal(X, oc.X) and np.array_equal(delta, oc.delta) and inf == oc.infeasibility
+        assert np.isclose(logimp, oc.log_importance, rtol=1e-9, atol=1e-10)
+        chains.append(oc)
+    # statistics: 300 further feasible samples per chain
+    smp.sample(300)
+    end, _, _, ns = smp.statistics()
+    ref_end = np.zeros(P.n_agent_states, np.int64)
+    for c, oc in enumerate(chains):
+        s1, s2 = np.zeros(8, np.int64), np.zeros(8, np.int64)
+        assert oc.sample_stats(300, 10 ** 9, ref_end, s1, s2) == 300 == int(ns[c])
+        assert np.array_equal(smp.state(c)[0], oc.X)
+    assert np.array_equal(end, ref_end)
