@@ -97,6 +97,14 @@ constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 #ifndef ABM_POOL
 #define ABM_POOL 0
 #endif
+// ABM_SYN_LAZY: sample launches: the synopsis sums are advanced only when the synopsis changes (value x samples since the last
+// change, like the end-state accumulators) instead of once per feasible sample
+#ifndef ABM_SYN_LAZY
+#define ABM_SYN_LAZY 0
+#endif
+#if ABM_SYN_LAZY && !ABM_END_DEFERRED
+#error "ABM_SYN_LAZY needs ABM_END_DEFERRED"
+#endif
 #ifndef ABM_UNIT_ONLY
 #define ABM_UNIT_ONLY 0
 #endif
@@ -529,8 +537,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         }
         if (chainValid && gl < P.nSynopsis) syn = S.synNow[(size_t)chain * P.nSynopsis + gl];
         if (gl < 16) sSyn[gl] = 0;
+        if (ABM_SYN_LAZY && gl == 0) sCtx[7] = 0;   // samples of this launch already folded into the synopsis sums
         __syncwarp();
     }
+    // ABM_SYN_LAZY: before the synopsis changes, the samples since the last change are folded into the sums with the old value
+    // (called where the two chains of a warp may have diverged: the barriers name the chain's own lanes)
+    auto foldSynopsis = [&](int nSampNow) {
+        const unsigned own = (W == 32 ? 0xffffffffu : ((1u << W) - 1u)) << gBase;
+        const int cnt = nSampNow - sCtx[7];
+        __syncwarp(own);
+        if (gl < P.nSynopsis) {
+            sSyn[gl] += (long long)syn * cnt;
+            sSyn[8 + gl] += (long long)syn * syn * cnt;
+        }
+        if (gl == 0) sCtx[7] = nSampNow;
+        __syncwarp(own);
+    };
 
     const int nStepsLaunch = (int)R.nSteps;
 #pragma unroll 1
@@ -1150,7 +1172,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 fxN = __ldg(fx) * dj;                    // nEnd, signed by delta_j (nEnd >= 1 for such a column)
                 fxK = __ldg(fx + 3 + gl);                // speculative beyond nEnd: the record table is padded
                 fxS = __ldg(fx + 1 + (gl >> 2));
-                if (abs(fxN) > W) fxN = 0, syn += endStateEffects(fx, dj, P.nSynopsis, S.endRec + (size_t)chainC * P.S, nSamp, gl, W);
+                if (abs(fxN) > W) {
+                    fxN = 0;
+                    if (ABM_SYN_LAZY) foldSynopsis(nSamp);
+                    syn += endStateEffects(fx, dj, P.nSynopsis, S.endRec + (size_t)chainC * P.S, nSamp, gl, W);
+                }
             }
 #else
             if (__any_sync(kFull, accept && colTouchesEnd))
@@ -1398,6 +1424,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             if (gl < abs(fxN))
                 atomicAdd(reinterpret_cast<unsigned long long *>(&S.endRec[(size_t)chainC * P.S + (fxK & 0xffffff)].pend),
                           (unsigned long long)((long long)(sgn * (fxK >> 24)) * (long long)nSamp));
+            if (ABM_SYN_LAZY) foldSynopsis(nSamp);
             if (gl < P.nSynopsis) syn += sgn * (int)(int8_t)(fxS >> (8 * (gl & 3)));
             fxN = 0;
         }
@@ -1406,8 +1433,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             // the do-while at SparseBasisSampler.h:247 hands out the state whenever it is feasible after a step
             if (act && infeas == 0) {
                 if (gl < P.nSynopsis) {   // MeanAndVariance::operator(), diagnostics/MeanAndVariance.h:35-45 (exact in int64)
-                    sSyn[gl] += syn;
-                    sSyn[8 + gl] += (long long)syn * syn;
+                    if (!ABM_SYN_LAZY) {
+                        sSyn[gl] += syn;
+                        sSyn[8 + gl] += (long long)syn * syn;
+                    }
                     if (serLeft == 0) recordSeries(R.series, R.seriesThin, R.seriesCap, P.nSynopsis, chainC, S.nSamples[chainC] + nSamp, gl, syn);
                 }
                 serLeft = serLeft == 0 ? R.seriesThin - 1 : serLeft - 1;
@@ -1424,6 +1453,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         }
     if (t2s && chainValid)
         for (int k = gl; k < P.t2Len; k += W) ch.tier2[k] = sT2[k];
+    if (kSample && ABM_SYN_LAZY) foldSynopsis(nSamp);
     if (kSample && chainValid) {   // the lazy accumulators are settled by sampleEndKernel
         if (gl < P.nSynopsis) {
             S.synSum[(size_t)chain * P.nSynopsis + gl] += sSyn[gl];

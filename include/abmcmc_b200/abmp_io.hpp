@@ -5,8 +5,10 @@
 // reference's class layout.  ABMP is our own format: a list of named little-endian arrays that
 // hold exactly what the SparseBasisSampler constructor consumes (SparseBasisSampler.h:107-185):
 // the reduced tableau (non-basic columns over all tableau rows, L/U/F per row), the factor
-// closures tabulated over each row's reachable domain, and the PredPrey importance tables
-// (TrajectoryImportance.h:90-113 evaluated through PredPreyAgent.h:124-182).
+// closures tabulated over each row's reachable domain, and the importance tables of the agent
+// (TrajectoryImportance.h:90-113 evaluated through PredPreyAgent.h:124-182: pp_meta, imp_*; or, for any other agent type,
+// through its own timestep / neighbours / consequences: ag_meta, ag_class, ag_infl, ag_nb*, ag_cq*, imp_* --
+// reference_flatten.hpp).
 //
 // Layout:  "ABMPROB1" | u32 nArrays | nArrays x { char name[24] | u32 dtype | u64 count | data }
 // dtype: 0 = int32, 1 = float64, 2 = uint8, 3 = int8.  Data is padded to 8 bytes.

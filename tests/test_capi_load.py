@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(L, sym), f"{sym} declared in abmcmc_b200.h but not exported"
     assert declared == set(_capi.SYMBOLS)
-    assert L.abm_version() >= 1
+    assert L.abm_version() >= 2   # 2: abm_problem_desc carries the agent_* tables
 
 
 def test_no_cpu_fallback_without_device():
@@ -32,3 +32,20 @@ def test_no_cpu_fallback_without_device():
     from agentbasedmcmc_b200 import sampler
     with pytest.raises(sampler.AbmError):
         sampler.Problem(load_golden("pp8-4.abmp.xz"))
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The Python mirror of abm_problem_desc / abm_problem_info has the C layout (size and the offsets of the fields after which
+    the struct grew): compiled from include/abmcmc_b200.h with the host compiler."""
+    import subprocess
+    from agentbasedmcmc_b200 import _capi
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "abmcmc_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(abm_problem_desc), offsetof(abm_problem_desc, kappa),\n'
+                   '    offsetof(abm_problem_desc, sum_tree), offsetof(abm_problem_desc, n_agent_states), offsetof(abm_problem_desc, agent_cq),\n'
+                   '    sizeof(abm_problem_info)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    D, I = _capi.ProblemDesc, _capi.ProblemInfo
+    assert got == [C.sizeof(D), D.kappa.offset, D.sum_tree.offset, D.n_agent_states.offset, D.agent_cq.offset, C.sizeof(I)]
