@@ -98,12 +98,32 @@ constexpr bool kImpEarly = ABM_IMP_EARLY != 0;
 #define ABM_POOL 0
 #endif
 // ABM_SYN_LAZY: sample launches: the synopsis sums are advanced only when the synopsis changes (value x samples since the last
-// change, like the end-state accumulators) instead of once per feasible sample
+// change, like the end-state accumulators) instead of once per feasible sample.  Alone it changes nothing measurable (35.4 ->
+// 35.5 ms per 8192 x 2000 steps, profiles/r2g_e2e_ab.log); it is what lets ABM_SMP_SMEM == 2 keep the synopsis out of the registers.
 #ifndef ABM_SYN_LAZY
-#define ABM_SYN_LAZY 0
+#define ABM_SYN_LAZY 1
 #endif
 #if ABM_SYN_LAZY && !ABM_END_DEFERRED
 #error "ABM_SYN_LAZY needs ABM_END_DEFERRED"
+#endif
+// ABM_SMP_SMEM: sample launches keep their rarely used state out of the step loop's registers: whether (and with which sign) the
+// accepted proposal moves the end state is one shared-memory word per chain, and the effect list is fetched AFTER the commit by
+// the out-of-line endStateEffects from the record address kept in shared memory (instead of three registers holding the
+// prefetched list across the commit); the series countdown lives in shared memory and is touched only when a series is
+// recorded.  The sampling kernels carry 4 registers less through the loop, which is what made the compiler re-derive lane ids
+// and pointers inside it (131 against 65 instructions per step in the Metropolis kernel; profiles/r2h_step_vs_sample_*).
+// Sampling launch of 8192 x 2000 steps at 32x32x16: 35.2 ms (0) -> 34.8 ms (1) -> 34.7 ms (2); a Metropolis launch: 32.3 ms
+// (profiles/r2i_e2e_ab.log).
+#ifndef ABM_SMP_SMEM
+#define ABM_SMP_SMEM 2
+#endif
+// ABM_SMP_SMEM == 2 (needs ABM_SYN_LAZY): the sample count and the synopsis of the current state live in shared memory as well;
+// a sampling launch then carries NO register through the step loop that a Metropolis launch does not.
+#if ABM_SMP_SMEM == 2 && !ABM_SYN_LAZY
+#error "ABM_SMP_SMEM == 2 needs ABM_SYN_LAZY"
+#endif
+#if ABM_SMP_SMEM && ABM_POOL
+#error "ABM_SMP_SMEM uses the shared-memory words of ABM_POOL"
 #endif
 #ifndef ABM_UNIT_ONLY
 #define ABM_UNIT_ONLY 0
@@ -353,8 +373,9 @@ __device__ __forceinline__ int selectDescending(const double (&v)[32 / W], doubl
 // nodeCap: 32 doubles of descent / summation staging (reference tree; 0 for the blocked tree); t2Cap: the blocked tree's sums of
 // 1024 leaves when they are kept in shared memory for the launch (0 otherwise)
 // suCap: the coupled-column ids of a step (reference tree: sCap; the blocked tree reads them from the record window: 0)
+constexpr int kCtxBytes = ABM_SMP_SMEM == 2 ? 64 : 32;   // sCtx: 8 ints (+ 8 with the sampling state in shared memory)
 __host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs, int nodeCap, int t2Cap, int suCap) {
-    return (kRecWinBytes + 16 + 32 + scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + 8 + 8 * 4 + suCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
+    return (kRecWinBytes + 16 + kCtxBytes + scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + 8 + 8 * 4 + suCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
 }
 
 // MODE_SAMPLE: an accepted proposal (dj != 0) with events in the last timestep moves the end state ModelState(traj,T,T).
@@ -451,7 +472,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     unsigned long long *sBar = reinterpret_cast<unsigned long long *>(gs + kRecWinBytes);   // mbarrier of the record copy
     int *sCtx = reinterpret_cast<int *>(gs + kRecWinBytes + 16);          // [8] this step's record header fields, for the partner
                                                                          //   half-warp when it serves this chain (ABM_POOL)
-    double2 *sScr = reinterpret_cast<double2 *>(gs + kRecWinBytes + 16 + 32);  // [scrCap] blocked tree: {DE', signed leaf} of the first
+    double2 *sScr = reinterpret_cast<double2 *>(gs + kRecWinBytes + 16 + kCtxBytes);  // [scrCap] blocked tree: {DE', signed leaf} of the first
                                                                          //   coupled columns of a step (the rest: S.scratch)
     double *sDl = reinterpret_cast<double *>(sScr + cScrCap);            // [sCap] delta of set() per coupled column
     double *sG = sDl + cSCap;                                            // [rowsCap][2 maxAbs] per row: DE' term for a coupled
@@ -526,15 +547,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     // ---- MODE_SAMPLE state: current end-state occupancy ModelState(traj,T,T) (ModelState.h:27-36 via
     // State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115), kept
     // incrementally, with per-state accumulators advanced lazily (occupancy x samples since the last change)
+#if ABM_SMP_SMEM == 2
+#define nSamp sCtx[0]
+#define syn sCtx[8 + (gl & 7)]
+    if (gl == 0) sCtx[0] = 0;
+    if (gl < 8) sCtx[8 + gl] = 0;
+#else
     int nSamp = 0;                      // feasible samples taken in this launch
     int fxN = 0, fxK = 0, fxS = 0;      // pending end-state effect of an accepted proposal (ABM_END_DEFERRED)
     int syn = 0;                        // lane k < nSynopsis: agents inside the k-th nested square (FiguresForPaper.h:245-263)
+#endif
     int serLeft = 0x7fffffff;           // feasible samples until the next one that goes to the thinned series
     if (kSample) {   // end-state occupancy and synopsis were prepared by sampleBeginKernel
         if (R.series && chainValid && chainC < R.nSeriesChains) {
             const long long r = S.nSamples[chainC] % R.seriesThin;
             serLeft = r == 0 ? 0 : (int)(R.seriesThin - r);
         }
+        if (ABM_SMP_SMEM && gl == 0) { sCtx[1] = serLeft; sCtx[3] = 0; }
         if (chainValid && gl < P.nSynopsis) syn = S.synNow[(size_t)chain * P.nSynopsis + gl];
         if (gl < 16) sSyn[gl] = 0;
         if (ABM_SYN_LAZY && gl == 0) sCtx[7] = 0;   // samples of this launch already folded into the synopsis sums
@@ -1165,7 +1194,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         if (kSample) {
             // events of the last timestep changed by an accepted proposal move the end state (evaluated here, while the
             // record pointers of the proposal are still live)
-#if ABM_END_DEFERRED
+#if ABM_SMP_SMEM
+            // the sign with which the accepted proposal moves the end state (0: it does not) and its record, for after the commit
+            if (gl == 0) { sCtx[2] = (int)ri.x; sCtx[3] = (accept && colTouchesEnd) ? dj : 0; }
+#elif ABM_END_DEFERRED
             // the effect list is requested now and applied after the commit, so its round trip overlaps the commit
             if (accept && colTouchesEnd) {
                 const int32_t *__restrict__ fx = reinterpret_cast<const int32_t *>(recG) + fxOff;
@@ -1418,7 +1450,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
             }
         }
         __syncwarp();
-#if ABM_END_DEFERRED
+#if ABM_SMP_SMEM
+        if (kSample) {
+            const int djE = sCtx[3];
+            if (djE != 0) {   // one accepted proposal in ~T: the header in the record window still is this step's
+                const uint32_t hb0 = sRec[0], hb1 = sRec[1];
+                const int off = 4 + 2 * (int)(hb0 & 0xff) + (int)((hb0 >> 8) & 0xff) + (int)((hb0 >> 16) << ((hb1 >> 30) & 1)) + (int)((hb1 >> 8) & 0x3fff);
+                const int32_t *fx = reinterpret_cast<const int32_t *>(P.rec + (size_t)(unsigned)sCtx[2] * 4) + off;
+                if (ABM_SYN_LAZY) foldSynopsis(nSamp);
+                const int dSyn = endStateEffects(fx, djE, P.nSynopsis, S.endRec + (size_t)chainC * P.S, nSamp, gl, W);
+                if (gl < P.nSynopsis) syn += dSyn;
+            }
+        }
+#elif ABM_END_DEFERRED
         if (kSample && fxN != 0) {
             const int sgn = fxN < 0 ? -1 : 1;
             if (gl < abs(fxN))
@@ -1437,10 +1481,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                         sSyn[gl] += syn;
                         sSyn[8 + gl] += (long long)syn * syn;
                     }
+#if !ABM_SMP_SMEM
                     if (serLeft == 0) recordSeries(R.series, R.seriesThin, R.seriesCap, P.nSynopsis, chainC, S.nSamples[chainC] + nSamp, gl, syn);
+#endif
                 }
+#if ABM_SMP_SMEM
+                if (R.series) {   // the countdown to the next sample of the thinned series
+                    const unsigned own = (W == 32 ? 0xffffffffu : ((1u << W) - 1u)) << gBase;
+                    const int left = sCtx[1];
+                    if (left == 0 && gl < P.nSynopsis)
+                        recordSeries(R.series, R.seriesThin, R.seriesCap, P.nSynopsis, chainC, S.nSamples[chainC] + nSamp, gl, syn);
+                    __syncwarp(own);
+                    if (gl == 0) sCtx[1] = left == 0 ? R.seriesThin - 1 : left - 1;
+                }
+#else
                 serLeft = serLeft == 0 ? R.seriesThin - 1 : serLeft - 1;
+#endif
+#if ABM_SMP_SMEM == 2
+                {
+                    const unsigned own = (W == 32 ? 0xffffffffu : ((1u << W) - 1u)) << gBase;
+                    __syncwarp(own);
+                    if (gl == 0) sCtx[0] += 1;
+                    __syncwarp(own);
+                }
+#else
                 ++nSamp;
+#endif
             }
         }
         if (act) ++itersDone;
@@ -1474,6 +1540,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         }
     }
 }
+#if ABM_SMP_SMEM == 2
+#undef nSamp
+#undef syn
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Construction kernels: SparseBasisSampler.h:144-178.
