@@ -548,8 +548,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     // State::backwardOccupation, State.h:57-63, and PredPreyAgent::consequences, PredPreyAgent.h:98-115), kept
     // incrementally, with per-state accumulators advanced lazily (occupancy x samples since the last change)
 #if ABM_SMP_SMEM == 2
-#define nSamp sCtx[0]
-#define syn sCtx[8 + (gl & 7)]
+    int &nSamp = sCtx[0];               // feasible samples taken in this launch (written by lane 0 of the chain)
+    int &syn = sCtx[8 + (gl & 7)];      // lane k < nSynopsis: agents inside the k-th nested square (FiguresForPaper.h:245-263);
+                                        // only lanes below nSynopsis (<= 8) write it
     if (gl == 0) sCtx[0] = 0;
     if (gl < 8) sCtx[8 + gl] = 0;
 #else
@@ -1540,10 +1541,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         }
     }
 }
-#if ABM_SMP_SMEM == 2
-#undef nSamp
-#undef syn
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // Construction kernels: SparseBasisSampler.h:144-178.
