@@ -585,7 +585,8 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     d.t2Cap = 0;
     // the compile-time shared-memory layout (stepKernel<..., FIX>): blocked tree, 16 lanes per chain, unit entries, sizes within
     // its constants -- true of the paper's PredPrey problems at every size; ABM_FIX_LAYOUT=0 forces the run-time layout
-    d.fixLayout = d.blockedTree && W == 16 && maxAbs == 1 && d.rowsCap <= kFixRowsCap && d.sCap <= kFixSCap && !ABM_T2_SMEM && !ABM_SMEM_SCRATCH;
+    d.fixLayout = d.blockedTree && W == 16 && maxAbs == 1 && d.rowsCap <= kFixRowsCap && d.sCap <= kFixSCap && !ABM_T2_SMEM && !ABM_SMEM_SCRATCH &&
+                  (!kFixWinWhole || maxRecWords <= size_t(kFixWinWords));   // a whole-record window: every record must fit
     if (const char *e = getenv("ABM_FIX_LAYOUT")) if (!atoi(e)) d.fixLayout = 0;
     if (d.fixLayout) { d.rowsCap = kFixRowsCap; d.sCap = kFixSCap; }
     if (d.blockedTree && !d.fixLayout) {
@@ -791,7 +792,7 @@ static cudaError_t launchStepWBF(const abm_chains *c, const RunParams &r) {
     constexpr int NG = 32 / W;
     const int chainsPerCta = kWarpsPerCta * NG;
     const int grid = (c->n + chainsPerCta - 1) / chainsPerCta;
-    const size_t smem = size_t(chainsPerCta) * (FIX ? groupSmemBytes(kFixRowsCap, kFixSCap, 0, kFixScrCap, 1, 0, 0, 0)
+    const size_t smem = size_t(chainsPerCta) * (FIX ? groupSmemBytes(kFixRowsCap, kFixSCap, 0, kFixScrCap, 1, 0, 0, 0, kFixWinBytes)
                                                     : groupSmemBytes(P.rowsCap, P.sCap, P.tCap, P.scrCap, P.maxAbs, P.nodeCap, P.t2Cap, BLK ? 0 : P.sCap));
     auto kernel = stepKernel<MODE, W, BLK, FIX>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -196,6 +196,16 @@ __device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefet
 // Record fetch: one bulk asynchronous copy per proposal (cp.async.bulk: global -> shared memory by the copy engine, no
 // registers, no per-lane address arithmetic) whose completion is counted in bytes on an mbarrier in shared memory.
 constexpr int kRecWinWords = 128, kRecWinBytes = kRecWinWords * 4;   // the head of a record that is staged in shared memory
+// ABM_FIX_WIN_WORDS: the window of the compile-time layout (stepKernel<..., FIX>).  128: as above, every record word is read
+// through `index < window ? shared : global`.  288 (1152 bytes, the longest record of the paper's problems is 1104): the host
+// selects the layout only when every record fits, and the FIX kernels read the window unconditionally (about 90 instructions
+// per step less; 3.6 instead of 3.0 KB of shared memory per chain, still 7 CTAs per SM).  Measured (32x32x16, 8192 chains,
+// profiles/r2l_pp32_ab.log): 511 -> 543 M chain-steps/s straight after the search, sampling launches 34.7 -> 33.5 ms.
+#ifndef ABM_FIX_WIN_WORDS
+#define ABM_FIX_WIN_WORDS 288
+#endif
+constexpr int kFixWinWords = ABM_FIX_WIN_WORDS, kFixWinBytes = kFixWinWords * 4;
+constexpr bool kFixWinWhole = kFixWinWords > kRecWinWords;   // the FIX layout holds whole records
 __device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void barInit(unsigned long long *bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(bar)) : "memory");
@@ -374,8 +384,9 @@ __device__ __forceinline__ int selectDescending(const double (&v)[32 / W], doubl
 // 1024 leaves when they are kept in shared memory for the launch (0 otherwise)
 // suCap: the coupled-column ids of a step (reference tree: sCap; the blocked tree reads them from the record window: 0)
 constexpr int kCtxBytes = ABM_SMP_SMEM == 2 ? 64 : 32;   // sCtx: 8 ints (+ 8 with the sampling state in shared memory)
-__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs, int nodeCap, int t2Cap, int suCap) {
-    return (kRecWinBytes + 16 + kCtxBytes + scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + 8 + 8 * 4 + suCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
+__host__ __device__ inline int groupSmemBytes(int rowsCap, int sCap, int tCap, int scrCap, int maxAbs, int nodeCap, int t2Cap, int suCap,
+                                              int winBytes = kRecWinBytes) {
+    return (winBytes + 16 + kCtxBytes + scrCap * 16 + sCap * 8 + rowsCap * 16 * maxAbs + nodeCap * 8 + t2Cap * 8 + 32 * 8 + 16 * 8 + 8 + 8 * 4 + suCap * 4 + rowsCap * 4 + ((tCap * 2 + rowsCap * 2 + 7) & ~7) + 15) & ~15;
 }
 
 // MODE_SAMPLE: an accepted proposal (dj != 0) with events in the last timestep moves the end state ModelState(traj,T,T).
@@ -463,16 +474,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
     const int cRowsCap = FIX ? kFixRowsCap : P.rowsCap, cSCap = FIX ? kFixSCap : P.sCap, cTCap = FIX ? 0 : P.tCap;
     const int cScrCap = FIX ? kFixScrCap : P.scrCap, cNodeCap = FIX ? 0 : P.nodeCap, cT2Cap = FIX ? 0 : P.t2Cap, cMaxAbs = FIX ? 1 : P.maxAbs;
     const int cSUCap = BLK ? 0 : cSCap;
-    const int gBytes = groupSmemBytes(cRowsCap, cSCap, cTCap, cScrCap, cMaxAbs, cNodeCap, cT2Cap, cSUCap);
+    constexpr int kWinWords = FIX ? kFixWinWords : kRecWinWords, kWinBytes = kWinWords * 4;
+    constexpr bool kWinWhole = FIX && kFixWinWhole;   // every record lies inside the window: no bounds check on its words
+    const int gBytes = groupSmemBytes(cRowsCap, cSCap, cTCap, cScrCap, cMaxAbs, cNodeCap, cT2Cap, cSUCap, kWinBytes);
     unsigned char *gs = smemRaw + (size_t)(warp * NG + g) * gBytes;
 #if ABM_PIN_IDS == 1
     asm volatile("" : "+l"(gs));
 #endif
     uint32_t *sRec = reinterpret_cast<uint32_t *>(gs);                   // [kRecWinWords] head of the proposed column's record
-    unsigned long long *sBar = reinterpret_cast<unsigned long long *>(gs + kRecWinBytes);   // mbarrier of the record copy
-    int *sCtx = reinterpret_cast<int *>(gs + kRecWinBytes + 16);          // [8] this step's record header fields, for the partner
+    unsigned long long *sBar = reinterpret_cast<unsigned long long *>(gs + kWinBytes);   // mbarrier of the record copy
+    int *sCtx = reinterpret_cast<int *>(gs + kWinBytes + 16);          // [8] this step's record header fields, for the partner
                                                                          //   half-warp when it serves this chain (ABM_POOL)
-    double2 *sScr = reinterpret_cast<double2 *>(gs + kRecWinBytes + 16 + kCtxBytes);  // [scrCap] blocked tree: {DE', signed leaf} of the first
+    double2 *sScr = reinterpret_cast<double2 *>(gs + kWinBytes + 16 + kCtxBytes);  // [scrCap] blocked tree: {DE', signed leaf} of the first
                                                                          //   coupled columns of a step (the rest: S.scratch)
     double *sDl = reinterpret_cast<double *>(sScr + cScrCap);            // [sCap] delta of set() per coupled column
     double *sG = sDl + cSCap;                                            // [rowsCap][2 maxAbs] per row: DE' term for a coupled
@@ -738,13 +751,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         const uint32_t *__restrict__ recG = P.rec + (size_t)ri.x * 4;
 #if !ABM_REC_BULK
         if (act) {
-            const unsigned nv = min(ri.y, (unsigned)kRecWinBytes) >> 4;
+            const unsigned nv = min(ri.y, (unsigned)kWinBytes) >> 4;
             for (unsigned q = gl; q < nv; q += W) reinterpret_cast<uint4 *>(sRec)[q] = __ldg(reinterpret_cast<const uint4 *>(recG) + q);
         }
 #elif ABM_REC_EVICT_LAST
-        if (act && gl == 0) bulkLoadHint(sRec, recG, min(ri.y, (unsigned)kRecWinBytes), sBar, recPolicy);
+        if (act && gl == 0) bulkLoadHint(sRec, recG, min(ri.y, (unsigned)kWinBytes), sBar, recPolicy);
 #else
-        if (act && gl == 0) bulkLoad(sRec, recG, min(ri.y, (unsigned)kRecWinBytes), sBar);
+        if (act && gl == 0) bulkLoad(sRec, recG, min(ri.y, (unsigned)kWinBytes), sBar);
 #endif
         // BLK: delta_u is the sign bit of the stored leaf p_u (p_u >= 0), so a coupled column costs one 16-byte load
         int dj = 1;
@@ -754,7 +767,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 #else
         if (act) { barWait(sBar, barPhase); barPhase ^= 1u; }
 #endif
-        auto recWord = [&](int i) -> uint32_t { return i < kRecWinWords ? sRec[i] : __ldg(recG + i); };
+        auto recWord = [&](int i) -> uint32_t { return (kWinWhole || i < kWinWords) ? sRec[i] : __ldg(recG + i); };
         const uint32_t h0 = act ? sRec[0] : 0u, h1 = act ? sRec[1] : 0u;
         const int n = h0 & 0xff, nSF = (h0 >> 8) & 0xff, C = h0 >> 16;
         const int nEv = h1 & 0xff, nXt = (h1 >> 8) & 0x3fff;
@@ -961,7 +974,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                         const uint32_t *recX = ofGroup(sRec, grp);
                         const uint32_t *recGX = P.rec + (size_t)(unsigned)cx[6] * 4;
                         const int so = cx[1], wd = cx[3];
-                        auto rw = [&](int i) -> uint32_t { return i < kRecWinWords ? recX[i] : __ldg(recGX + i); };
+                        auto rw = [&](int i) -> uint32_t { return (kWinWhole || i < kWinWords) ? recX[i] : __ldg(recGX + i); };
                         sw_ = rw(so + (slot << wd) + wd);
                         u_ = wd ? (int)rw(so + 2 * slot) : cx[2] + (int)(sw_ & 0xffffu);
                         cr_ = (colRec0 + (size_t)grp * nCols)[u_];
@@ -1001,7 +1014,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                 if (__any_sync(kFull, ext)) {   // pair lists of columns sharing more than two rows with the proposed one
                     const uint32_t *recX = ofGroup(sRec, grp);
                     const uint32_t *recGX = P.rec + (size_t)(unsigned)cx[6] * 4;
-                    auto rw = [&](int i) -> uint32_t { return i < kRecWinWords ? recX[i] : __ldg(recGX + i); };
+                    auto rw = [&](int i) -> uint32_t { return (kWinWhole || i < kWinWords) ? recX[i] : __ldg(recGX + i); };
                     const int lw = cx[4] + (int)p1;
                     unsigned long long lst = 0ull;
                     if (ext) lst = (unsigned long long)rw(lw) | ((unsigned long long)rw(lw + 1) << 32);
@@ -1272,7 +1285,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
                     const uint32_t *recX = ofGroup(sRec, grp);
                     const uint32_t *recGX = P.rec + (size_t)(unsigned)cx[6] * 4;
                     const int so = cx[1], wd = cx[3];
-                    auto rw = [&](int i) -> uint32_t { return i < kRecWinWords ? recX[i] : __ldg(recGX + i); };
+                    auto rw = [&](int i) -> uint32_t { return (kWinWhole || i < kWinWords) ? recX[i] : __ldg(recGX + i); };
                     u = wd ? rw(so + 2 * l) : (unsigned)cx[2] + (rw(so + l) & 0xffffu);
                 }
                 const double dl = valid ? ofGroup(sDl, grp)[l] : 0.0;
