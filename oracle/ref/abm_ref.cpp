@@ -899,6 +899,7 @@ static int cmdSingleObservationExperiment(const std::string &out, const std::str
 #include "agents/CatMouseAgent.h"
 #include "BernoulliStartState.h"
 #include "ExactSolver.h"
+#include "test_agents.h"
 template <class Agent>
 static int toyExperiment(Prior<Agent> &prior, Likelihood<Agent> &likelihood, int T, double kappa, int chainSeed, long nSteps,
                          int every, long nRejection, const std::string &problemOut, const std::string &traceOut) {
@@ -922,7 +923,7 @@ static int toyExperiment(Prior<Agent> &prior, Likelihood<Agent> &likelihood, int
         }
         for (double &v : rej) v /= double(nRejection);
     }
-    {
+    if (nRejection > 0) {   // (the exhaustive enumeration takes a minute on the larger toy problems: fixtures only)
         ExactSolver<Agent> solver(posterior);
         for (const auto &tp : solver.pmf) {
             ModelState<Agent> endState(tp.first, T, T);
@@ -969,6 +970,20 @@ static int cmdToy(const std::string &kind, int seed, int chainSeed, long nSteps,
         Likelihood<Agent> likelihood(realTrajectory, 0.2, 1.0);
         return toyExperiment<Agent>(prior, likelihood, T, 1.25, chainSeed, nSteps, every, nRejection, problemOut, traceOut);
     }
+    if (kind == "ring") {              // own test agent with non-trivial importance factors (oracle/ref/test_agents.h)
+        constexpr int T = 3;
+        typedef RingAgent<5> Agent;
+        Prior<Agent> prior(T, BernoulliStartState<Agent>({0.5, 0.3, 0.5, 0.3, 0.5}));
+        Likelihood<Agent> likelihood(AgentStateObservation<Agent>(State<Agent>(1, 2), 1, 1.0));
+        return toyExperiment<Agent>(prior, likelihood, T, 1.5, chainSeed, nSteps, every, nRejection, problemOut, traceOut);
+    }
+    if (kind == "crowded-ring") {      // an agent the tables cannot describe: must be refused by flattenAgentImportance
+        constexpr int T = 2;
+        typedef CrowdedRingAgent<4> Agent;
+        Prior<Agent> prior(T, BernoulliStartState<Agent>({0.5, 0.3, 0.5, 0.3}));
+        Likelihood<Agent> likelihood(AgentStateObservation<Agent>(State<Agent>(1, 2), 1, 1.0));
+        return toyExperiment<Agent>(prior, likelihood, T, 1.5, chainSeed, nSteps, every, nRejection, problemOut, traceOut);
+    }
     fprintf(stderr, "toy: unknown experiment %s\n", kind.c_str());
     return 2;
 }
@@ -1014,7 +1029,7 @@ static int run(int argc, char **argv) {
                 "  abm_ref refstats series.abmp [splitHalves]\n"
                 "  abm_ref constraints in.abmp out.abmp [rebuild: 1 = also time the reference TableauNormMinimiser on them]\n"
                 "  abm_ref astable in.abmp out.abmp\n"
-                "  abm_ref toy binomial|catmouse|catmouse-assim seed chainSeed nSteps checkpointEvery nRejection problem.abmp trace.abmp\n");
+                "  abm_ref toy binomial|catmouse|catmouse-assim|ring|crowded-ring seed chainSeed nSteps checkpointEvery nRejection problem.abmp trace.abmp\n");
         return 2;
     }
     std::string cmd = argv[1];
@@ -1034,7 +1049,7 @@ static int run(int argc, char **argv) {
         const bool fastBasis = argc > 12 && std::string(argv[12]) == "fastbasis";
         DISPATCH_G(g, cmdGen<G>(T, seed, kappa, out, pPred, pPrey, pObs, pObsIf, startKind, fastBasis));
     }
-    if (cmd == "toy")   // toy binomial|catmouse|catmouse-assim seed chainSeed nSteps checkpointEvery nRejection problem.abmp trace.abmp
+    if (cmd == "toy")   // toy binomial|catmouse|catmouse-assim|ring|crowded-ring seed chainSeed nSteps checkpointEvery nRejection problem.abmp trace.abmp
         return cmdToy(argv[2], atoi(argv[3]), atoi(argv[4]), atol(argv[5]), atoi(argv[6]), atol(argv[7]), argv[8], argv[9]);
     if (cmd == "experiment3")   // experiment3 problem.abmp marginals.abmp nSamples nBurnin nRejection seed
         return cmdSingleObservationExperiment(argv[2], argv[3], atol(argv[4]), atol(argv[5]), atol(argv[6]), atoi(argv[7]));

@@ -46,7 +46,8 @@ def traces_only():
 # (agent described by tables), the rejection sampler's end-state means over 2e6 samples, the exact posterior over trajectories,
 # and a golden step trace of 20000 steps -- and PredPrey problems re-described as table agents (`abm_ref astable`), which the
 # existing PredPrey traces must keep matching.
-TOYS = [("binomial", 1234, 401), ("catmouse", 1234, 402), ("catmouse-assim", 1234, 403)]
+TOYS = [("binomial", 1234, 401), ("catmouse", 1234, 402), ("catmouse-assim", 1234, 403),
+        ("ring", 1234, 404)]   # own test agent with non-trivial importance factors (oracle/ref/test_agents.h)
 AS_TABLE = ["pp8-4", "exp_pp3-2-single"]
 
 

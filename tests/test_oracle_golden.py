@@ -18,6 +18,8 @@ TRACES = [("pp8-4.abmp.xz", "trace_pp8-4_101.abmp.xz"), ("pp8-4.abmp.xz", "trace
           # noisy observation, CatMouseAgent with one observation, CatMouseAgent assimilation), agents described by tables
           ("toy_binomial.abmp.xz", "trace_toy_binomial_401.abmp.xz"), ("toy_catmouse.abmp.xz", "trace_toy_catmouse_402.abmp.xz"),
           ("toy_catmouse-assim.abmp.xz", "trace_toy_catmouse-assim_403.abmp.xz"),
+          # own test agent with non-trivial importance factors (oracle/ref/test_agents.h RingAgent<5>, T = 3)
+          ("toy_ring.abmp.xz", "trace_toy_ring_404.abmp.xz"),
           # PredPrey re-described as a table agent (tables found by probing PredPreyAgent::timestep): the same traces must come out
           ("pp8-4-astable.abmp.xz", "trace_pp8-4_101.abmp.xz"), ("exp_pp3-2-single-astable.abmp.xz", "trace_exp_pp3-2-single_301.abmp.xz")]
 
@@ -61,6 +63,42 @@ def test_oracle_matches_reference_on_fresh_problems(grid, T, seed, start, tmp_pa
     subprocess.run([str(ref), "trace", str(prob), str(seed + 100), str(seed + 200), "4000", "500", str(trace)], check=True,
                    capture_output=True, timeout=600)
     check_trace(read_abmp(prob), read_abmp(trace))
+
+
+@pytest.mark.parametrize("kind,seed", [("binomial", 31), ("catmouse", 32), ("catmouse-assim", 33), ("catmouse-assim", 34),
+                                       # own test agent (oracle/ref/test_agents.h): two classes, every log-ratio non-zero
+                                       ("ring", 35), ("ring", 36)])
+def test_oracle_matches_reference_on_fresh_agent_experiments(kind, seed, tmp_path):
+    """The same differential run for the agents described by tables: `abm_ref toy` builds the reference's validation
+    experiments on BinomialAgent / CatMouseAgent (Experiments.cpp:21-47, 70-125) under another seed (another real trajectory
+    and observation set for the assimilation experiment), flattens the agent by probing its timestep(), and traces the
+    unmodified sampler; the oracle must reproduce the trace bit for bit from the tables alone."""
+    import subprocess
+    from pathlib import Path
+    from agentbasedmcmc_b200.abmp import read_abmp
+    ref = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "abm_ref"
+    if not ref.exists():
+        pytest.skip("oracle/_ref/abm_ref not built (needs /root/reference at build time)")
+    prob, trace = tmp_path / "p.abmp", tmp_path / "t.abmp"
+    subprocess.run([str(ref), "toy", kind, str(seed), str(seed + 100), "6000", "500", "0", str(prob), str(trace)], check=True,
+                   capture_output=True, timeout=600)
+    p = read_abmp(prob)
+    assert "ag_meta" in p and "pp_meta" not in p
+    check_trace(p, read_abmp(trace))
+
+
+def test_agent_outside_the_table_form_is_refused(tmp_path):
+    """flattenAgentImportance verifies the form it tabulates by probing timestep(); an agent whose act pmf depends on HOW MANY
+    agents sit on another state (oracle/ref/test_agents.h CrowdedRingAgent) must be refused, not approximated."""
+    import subprocess
+    from pathlib import Path
+    ref = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "abm_ref"
+    if not ref.exists():
+        pytest.skip("oracle/_ref/abm_ref not built (needs /root/reference at build time)")
+    out = subprocess.run([str(ref), "toy", "crowded-ring", "1", "2", "100", "50", "0", str(tmp_path / "p.abmp"), str(tmp_path / "t.abmp")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and "depends on more than whether any influencer state is occupied" in out.stderr
+    assert not (tmp_path / "p.abmp").exists()
 
 
 def check_trace(p, t):
