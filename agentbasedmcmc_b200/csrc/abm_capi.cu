@@ -174,6 +174,8 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     // the agent: PredPrey by its grid geometry, or any other agent type by tables (abmcmc_b200.h); either way the host works
     // from the same four tables: class, influencers, neighbours(), consequences()
     const bool tableAgent = G == 0 && desc->n_agent_states > 0;
+    if (G < 0 || G > 4096 || desc->n_agent_states < 0 || desc->n_agent_states > (1 << 22) || T < 0 || T > (1 << 16))
+        return fail(ABM_ERR_INVALID, "agent description out of range (grid size, agent states or timesteps)");
     const int A = tableAgent ? desc->n_acts : kActs;
     const int S = tableAgent ? desc->n_agent_states : 2 * G * G, nStates = T * S, nEvents = nStates * A;
     const int nCls = tableAgent ? desc->n_agent_classes : 2;
