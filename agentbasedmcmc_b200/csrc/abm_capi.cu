@@ -361,6 +361,8 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     }
 
     // column records (layout: abm_device.h)
+    bool blockedTree = desc->sum_tree != ABM_TREE_REFERENCE;
+    if (const char *e = getenv("ABM_TREE")) blockedTree = std::string(e) != "reference";
     std::vector<uint2> recIdx(nCols);
     std::vector<uint32_t> rec;
     rec.reserve((size_t)nnz * 12);
@@ -414,16 +416,18 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
                 for (size_t q = 0; q < bytes.size(); q += 4) xtra.push_back(bytes[q] | bytes[q + 1] << 8 | bytes[q + 2] << 16 | bytes[q + 3] << 24);
             }
             slots.push_back(w);
-            int a3 = u;
-            nodes.push_back(a3);
-            while (a3) { a3 &= a3 - 1; nodes.push_back(a3); }
+            if (!blockedTree) {   // the reference tree's commit lists the nodes it touches: u and its ancestors
+                int a3 = u;
+                nodes.push_back(a3);
+                while (a3) { a3 &= a3 - 1; nodes.push_back(a3); }
+            }
             a2 = b2;
         }
         const int C = int(slots.size()) / (wide ? 2 : 1);
         maxCoupled = std::max(maxCoupled, C);
-        // distinct tree nodes a commit of this column touches (sizes the reference tree's task list)
+        // distinct tree nodes a commit of this column touches (sizes the reference tree's task list; the blocked tree keeps none)
         std::sort(nodes.begin(), nodes.end());
-        {
+        if (!blockedTree) {
             const int nn = int(std::unique(nodes.begin(), nodes.end()) - nodes.begin());
             int ta = 0, tb = 0, tc = 0;
             for (int q = 0; q < nn; ++q) {
@@ -569,8 +573,7 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     if (d.nTop > 32) return fail(ABM_ERR_INVALID, "internal: too many top tree nodes");
     d.evBytes = evBytes;
     d.G = G; d.S = S; d.T = T; d.nStates = nStates;
-    d.blockedTree = desc->sum_tree == ABM_TREE_REFERENCE ? 0 : 1;
-    if (const char *e = getenv("ABM_TREE")) d.blockedTree = std::string(e) != "reference";
+    d.blockedTree = blockedTree ? 1 : 0;
     if (d.blockedTree && nCols > (1 << 20)) return fail(ABM_ERR_INVALID, "blocked tree supports up to 2^20 columns");
     d.gShift = gShift;
     d.groupWidth = W;
