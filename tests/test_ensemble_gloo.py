@@ -86,3 +86,19 @@ def test_summarize_moments_equals_the_packed_route():
     for x, y in ((a.W, b.W), (a.B, b.B), (a.var_plus, b.var_plus), (a.rhat, b.rhat), (a.end_state_mean, b.end_state_mean),
                  (a.synopsis_mean, b.synopsis_mean)):
         assert np.allclose(x, y, rtol=1e-10)
+
+
+def test_summarize_moments_without_synopsis_statistics():
+    """Agents described by tables have end-state statistics only (no nested-square synopsis): the summary of their moments is the
+    end-state means and the counters, with empty diagnostics."""
+    from agentbasedmcmc_b200 import _capi, ensemble as E
+    S = 4
+    exact = np.zeros(_capi.MOMENTS_EXACT_HEAD + S, np.int64)
+    exact[0], exact[1] = 10, 1000
+    exact[2:10] = [100, 50, 60, 300, 80, 40, 40, 250]
+    exact[_capi.MOMENTS_EXACT_HEAD:] = [500, 200, 10, 900]
+    r = E.summarize_moments(exact, np.zeros(_capi.MOMENTS_REAL), 0)
+    assert r.n_chains == 10 and r.n_samples == 1000
+    assert np.allclose(r.end_state_mean, [0.5, 0.2, 0.01, 0.9])
+    assert r.rhat.size == 0 and r.synopsis_mean.size == 0
+    assert np.array_equal(r.counters, exact[2:10])
