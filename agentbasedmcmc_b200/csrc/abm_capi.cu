@@ -597,7 +597,7 @@ static int problemCreateImpl(const abm_problem_desc *desc, int device, abm_probl
     if (d.blockedTree && !d.fixLayout) {
         // what 7 resident CTAs per SM leave to one chain (228 KB per SM, 1 KB reserved per CTA), after the fixed arrays
         const int chainsPerCta = kWarpsPerCta * (32 / W);
-        const int budget = (((228 * 1024) / 7 - 1024) / chainsPerCta) & ~15;
+        [[maybe_unused]] const int budget = (((228 * 1024) / 7 - 1024) / chainsPerCta) & ~15;
 #if ABM_T2_SMEM
         if (groupSmemBytes(d.rowsCap, d.sCap, d.tCap, 0, d.maxAbs, d.nodeCap, d.t2Len, 0) <= budget) d.t2Cap = d.t2Len;
 #endif

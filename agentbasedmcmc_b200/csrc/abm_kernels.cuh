@@ -481,8 +481,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
 #if ABM_PIN_IDS == 1
     asm volatile("" : "+l"(gs));
 #endif
-    uint32_t *sRec = reinterpret_cast<uint32_t *>(gs);                   // [kRecWinWords] head of the proposed column's record
-    unsigned long long *sBar = reinterpret_cast<unsigned long long *>(gs + kWinBytes);   // mbarrier of the record copy
+    uint32_t *sRec = reinterpret_cast<uint32_t *>(gs);                   // [kWinWords] the proposed column's record (FIX), or its head
+    [[maybe_unused]] unsigned long long *sBar = reinterpret_cast<unsigned long long *>(gs + kWinBytes);   // mbarrier of the record copy (ABM_REC_BULK)
     int *sCtx = reinterpret_cast<int *>(gs + kWinBytes + 16);          // [8] this step's record header fields, for the partner
                                                                          //   half-warp when it serves this chain (ABM_POOL)
     double2 *sScr = reinterpret_cast<double2 *>(gs + kWinBytes + 16 + kCtxBytes);  // [scrCap] blocked tree: {DE', signed leaf} of the first
@@ -774,7 +774,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) stepKernel(DevProblem P,
         const int wide = (h1 >> 30) & 1;                                    // slots of two words: {u, pairs}                 // nEv: leading rows that are events (row id < nEvents)
         const bool colTouchesEnd = (int)h1 < 0;                             // the column has an event row in the last timestep
         const int uBase = act ? (int)sRec[2] : 0;
-        const int staleOff = 4 + 2 * n, slotOff = staleOff + nSF, xtraOff = slotOff + (C << wide), fxOff = xtraOff + nXt;
+        const int staleOff = 4 + 2 * n, slotOff = staleOff + nSF, xtraOff = slotOff + (C << wide);
+        [[maybe_unused]] const int fxOff = xtraOff + nXt;   // end-state effects (read here only without ABM_SMP_SMEM)
         // slot l of the record: its pair word, and the column it names
         auto slotWord = [&](int l) -> uint32_t { return recWord(slotOff + (l << wide) + wide); };
         auto slotCol = [&](int l, uint32_t w) -> int { return wide ? (int)recWord(slotOff + 2 * l) : uBase + (int)(w & 0xffffu); };
