@@ -1,7 +1,7 @@
 """An agent type that is not in the reference, through the table description, on the GPU: RingAgent<5> (oracle/ref/test_agents.h:
 two classes of log-ratio rows, every entry non-zero, one influencer per state; T = 3).  The fixture holds a 20 000-step golden
 trace of the UNMODIFIED reference sampler running TrajectoryImportance<RingAgent<5>>, the reference RejectionSampler's end-state
-means and the exact posterior (`abm_ref toy ring`).  Runs last in the GPU suite (added with the final commits of round 2)."""
+means and the exact posterior (`abm_ref toy ring`)."""
 import numpy as np
 import pytest
 
